@@ -1,0 +1,58 @@
+"""Import the *real* reference functions from ``/root/reference`` (build container only).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/diga_oracle.py``).  The reference tree does not exist on
+the GPU box and its sources are never copied into this repo, so this loader is used for two
+things that both happen here, in the build container:
+
+* ``tests/golden/make_golden.py`` — generate the committed golden fixtures;
+* ``tests/test_oracle_golden.py`` — pin ``diga_oracle`` against the live reference (skipped when
+  ``/root/reference`` is absent).
+
+Shims: the reference imports ``kornia`` and ``matplotlib`` at module
+top (unused by the hot path) and hard-codes ``.cuda()``; on a CUDA-less host that call is made a
+no-op.  One reference tree per process (``G/`` and ``S/`` both define ``util.*``).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("DIGA_REF", "/root/reference")
+TREES = {
+    "G": "domain_adaptation/GTA5",
+    "S": "domain_adaptation/Synthia",
+}
+
+
+def available(tree: str = "G") -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, TREES[tree], "calc_centroids.py"))
+
+
+def load(tree: str = "G") -> types.SimpleNamespace:
+    """Returns a namespace with ``distillation_loss``, ``process_label``, ``Class_Features``."""
+    if not available(tree):
+        raise FileNotFoundError(f"reference tree {tree} not found under {REF_ROOT}")
+    loaded = getattr(load, "_tree", None)
+    if loaded is not None and loaded != tree:
+        raise RuntimeError(f"reference tree {loaded} already imported in this process; start a new one for {tree}")
+    for name in ("kornia", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    path = os.path.join(REF_ROOT, TREES[tree])
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from util.loss import distillation_loss          # noqa: E402
+        from util.utils import process_label             # noqa: E402
+        from calc_centroids import Class_Features        # noqa: E402
+    load._tree = tree
+    return types.SimpleNamespace(distillation_loss=distillation_loss, process_label=process_label,
+                                 Class_Features=Class_Features, tree=tree)

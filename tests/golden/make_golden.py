@@ -1,0 +1,208 @@
+"""Generate the committed golden fixtures by running the REFERENCE ITSELF (build container only).
+
+Run:  ``python tests/golden/make_golden.py``  (needs ``/root/reference``; writes ``tests/golden/*.npz``).
+
+* Function-level hot path (``distillation_loss``, ``process_label``, ``Class_Features``): the real
+  functions are imported through ``oracle/ref_loader.py``.
+* Inline script blocks (pseudo-label math, ClassMix, consensus selection, online centroid update):
+  the scripts cannot be imported (argparse / dataset / checkpoint side effects at module level),
+  so the exact source *line ranges* are read from the reference file at generation time and
+  ``exec``-ed over seeded inputs.  No reference source text is stored in this repo; only the
+  numeric inputs and outputs are.
+
+Every fixture stores its inputs, so tests never need the reference at run time.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import textwrap
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+G = os.path.join(ref_loader.REF_ROOT, ref_loader.TREES["G"])
+
+
+def _lines(relpath: str, first: int, last: int) -> str:
+    """Source text of 1-based inclusive line range of a reference file, dedented."""
+    with open(os.path.join(G, relpath)) as f:
+        src = f.readlines()[first - 1:last]
+    return textwrap.dedent("".join(src))
+
+
+def _blocky_labels(gen, b, h, w, block, n_cls=19, p_ignore=0.1):
+    """Piecewise-constant int64 label maps with ~p_ignore of the blocks set to 255."""
+    gh, gw = (h + block - 1) // block, (w + block - 1) // block
+    coarse = torch.randint(0, n_cls, (b, gh, gw), generator=gen)
+    coarse[torch.rand((b, gh, gw), generator=gen) < p_ignore] = 255
+    lab = coarse.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :h, :w]
+    return lab.contiguous().long()
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def main():
+    ref = ref_loader.load("G")
+    gen = torch.Generator().manual_seed(20231017)
+
+    # ---- a1 KD loss fwd + bwd (G/util/loss.py:125-143) ------------------------------------
+    for tag, shape, scale, sigma in (("kd_c19", (4, 19, 8, 16), 0.5, 3.0),
+                                     ("kd_c16_s025", (2, 16, 6, 10), 0.25, 3.0),
+                                     ("kd_saturated", (4, 19, 4, 12), 0.5, 12.0)):
+        t = sigma * torch.randn(shape, generator=gen)
+        s = (sigma * torch.randn(shape, generator=gen)).requires_grad_(True)
+        loss = ref.distillation_loss(t, s, scale)
+        (loss * 0.25).backward()                       # upstream grad 0.25 (lambda_distil-like)
+        save(tag, teacher=t, student=s, scale=scale, upstream=0.25, loss=loss, grad=s.grad)
+
+    # ---- process_label (G/util/utils.py:158-163) -------------------------------------------
+    lab = torch.randint(0, 19, (2, 1, 5, 7), generator=gen).float()
+    lab[0, 0, 0, :3] = 255.0
+    lab[1, 0, 2, 2] = 19.0
+    save("process_label", label=lab, onehot=ref.process_label(lab))
+
+    # ---- a6 calculate_mean_vector, with and without labels (G/calc_centroids.py:120-145) ---
+    cf = ref.Class_Features(numbers=19)
+    n, d, h, w = 2, 32, 9, 11
+    feat = torch.randn((n, d, h, w), generator=gen)
+    out = 3.0 * torch.randn((n, 19, h, w), generator=gen)
+    out[:, 5:] -= 4.0                                   # few dominant classes -> counts >= 5, some < 5
+    labels = F.softmax(out, 1).argmax(1, keepdim=True).float()
+    flip = torch.rand((n, 1, h, w), generator=gen) < 0.3
+    labels[flip] = torch.randint(0, 19, (int(flip.sum()),), generator=gen).float()
+    labels[0, 0, :2, :] = 255.0
+    v0, i0 = cf.calculate_mean_vector(feat, out)
+    v1, i1 = cf.calculate_mean_vector(feat, out, labels)
+    v2, i2 = cf.calculate_mean_vector_by_output(feat, out)
+    save("mean_vector", feat=feat, out=out, labels=labels,
+         vec_nolabel=torch.stack(v0).reshape(len(i0), d), ids_nolabel=np.array(i0),
+         vec_label=torch.stack(v1).reshape(len(i1), d), ids_label=np.array(i1),
+         vec_by_output=torch.stack(v2).reshape(len(i2), d), ids_by_output=np.array(i2))
+
+    # ---- a7 update_objective_SingleVector sequences (G/calc_centroids.py:147-164) ----------
+    cf = ref.Class_Features(numbers=19)
+    cf.objective_vectors = torch.zeros(19, 8)
+    seq_ids, seq_vecs, seq_modes, seq_sm = [], [], [], []
+    modes = ["mean", "moving_average"]
+    for k in range(260):
+        cid = int(torch.randint(0, 4, (1,), generator=gen))
+        vec = torch.randn(8, 1, 1, generator=gen)
+        if k % 37 == 5:
+            vec = torch.zeros(8, 1, 1)                   # all-zero vector -> skipped (:148)
+        mode = modes[k % 2]
+        sm = bool(k % 3)
+        seq_ids.append(cid), seq_vecs.append(vec.reshape(8)), seq_modes.append(k % 2), seq_sm.append(sm)
+        cf.update_objective_SingleVector(cid, vec if k % 5 else vec.numpy(), mode, start_mean=sm)
+    # clamp at 3000 (:156,161)
+    cf.objective_vectors_num[3] = 2999.0
+    for k in range(3):
+        vec = torch.randn(8, 1, 1, generator=gen)
+        seq_ids.append(3), seq_vecs.append(vec.reshape(8)), seq_modes.append(0), seq_sm.append(False)
+        cf.update_objective_SingleVector(3, vec, "mean", start_mean=False)
+    save("centroid_update", ids=np.array(seq_ids), vecs=torch.stack(seq_vecs), modes=np.array(seq_modes),
+         start_mean=np.array(seq_sm), clamp_inject_at=260, clamp_inject_class=3, clamp_inject_value=2999.0,
+         objective_vectors=cf.objective_vectors, objective_vectors_num=cf.objective_vectors_num)
+
+    # ---- a5 distance / weight (G/calc_centroids.py:166-180) ---------------------------------
+    cf = ref.Class_Features(numbers=19)
+    for tag, d, hh, ww in (("proto_d256", 256, 5, 7), ("proto_d64", 64, 9, 13)):
+        feat = torch.randn((2, d, hh, ww), generator=gen)
+        cf.objective_vectors = 0.5 * torch.randn((19, d), generator=gen) + feat.mean()
+        save(tag, feat=feat, centroids=cf.objective_vectors, dist=cf.feat_centroid_distance(feat),
+             weight=cf.get_centroid_weight(feat), negdist=cf.get_centroid_distance(feat))
+
+    # ---- a3 pseudo-label math: exec G/pseudolabel_generator.py:80-85 ------------------------
+    block = _lines("pseudolabel_generator.py", 80, 85)
+    for tag, sigma in (("pseudo_label", 3.0), ("pseudo_label_sat", 10.0)):
+        z = sigma * torch.randn((1, 19, 24, 40), generator=gen)
+        z_ds = sigma * torch.randn((1, 19, 24, 40), generator=gen)
+        ns = {"torch": torch, "nn": nn, "np": np, "output": z.clone(), "output_ds": z_ds.clone()}
+        exec(block, ns)
+        save(tag, output=z, output_ds=z_ds, label=ns["label"], prob_hwc=ns["output"])
+    # with the two bilinear up-samplings of :77-78 in front (CPU interpolation kernel)
+    up = nn.Upsample(size=[64, 96], mode="bilinear", align_corners=True)
+    lo, lo_ds = 3.0 * torch.randn((1, 19, 9, 13), generator=gen), 3.0 * torch.randn((1, 19, 5, 7), generator=gen)
+    ns = {"torch": torch, "nn": nn, "np": np, "upsample_1024": up, "output": lo.clone(), "output_ds": lo_ds.clone()}
+    exec(_lines("pseudolabel_generator.py", 77, 85), ns)
+    save("pseudo_label_two_scale", logits=lo, logits_ds=lo_ds, size=np.array([64, 96]), label=ns["label"])
+
+    # ---- a2 ClassMix: exec self_training.py:259-275 (image only) and :306-325 (DACS) -------
+    b, hh, ww = 3, 32, 48
+    slabel = _blocky_labels(gen, b, hh, ww, 8)
+    slabel[2] = 255                                                   # an all-ignore image
+    img_a = torch.randn((b, 3, hh, ww), generator=gen).clamp(-1, 1)
+    img_b = torch.randn((b, 3, hh, ww), generator=gen).clamp(-1, 1)
+    img_a[0, 0, 0, 0] = -0.0
+    tl = _blocky_labels(gen, b, hh, ww, 8)
+    rnd = random.Random(77)
+    ns = {"torch": torch, "random": rnd, "i_iter": 0, "slabelv": slabel.clone(),
+          "rec_s2t": img_a.clone(), "sdatav_aug": img_b.clone()}
+    exec(_lines("train_DiGA_gta2city_self_training.py", 259, 275), ns)
+    rnd2 = random.Random(78)
+    ns2 = {"torch": torch, "random": rnd2, "i_iter": 0, "slabelv": slabel.clone(), "tlabelv_pseudo": tl.clone(),
+           "tdatav_aug": img_a.clone(), "sdatav": img_b.clone()}
+    exec(_lines("train_DiGA_gta2city_self_training.py", 306, 325), ns2)
+    save("classmix", slabel=slabel, a=img_a, b=img_b, tlabel=tl, seed_img=77, seed_dacs=78,
+         mask_img=ns["mask"], mix_img=ns["sdatav_aug_crdomix"],
+         mask_dacs=ns2["mask"], mix_dacs=ns2["cross_mix"], mixlabel_dacs=ns2["crossmix_label"])
+
+    # ---- a4 consensus selection: exec self_training.py:298-304 ------------------------------
+    cf = ref.Class_Features(numbers=19)
+    d, fh, fw, oh, ow = 32, 9, 13, 64, 96
+    t_feat = torch.randn((2, d, fh, fw), generator=gen)
+    cf.objective_vectors = 0.5 * torch.randn((19, d), generator=gen)
+    pp = _blocky_labels(gen, 2, oh, ow, 8)
+    t_pred = 3.0 * torch.randn((2, 19, fh, fw), generator=gen)
+    ns = {"torch": torch, "class_features": cf, "tlabelv_pseudo_prob": pp.clone(), "tdatav": None,
+          "teacher": lambda x: (None, None, t_pred, t_feat),
+          "upsample_tgt": nn.Upsample(size=[oh, ow], mode="bilinear", align_corners=True)}
+    exec(_lines("train_DiGA_gta2city_self_training.py", 298, 304), ns)
+    up_w = ns["feat_weights"]
+    top2 = up_w.topk(2, dim=1).values
+    save("consensus", t_feat=t_feat, centroids=cf.objective_vectors, pseudo_prob=pp, out_size=np.array([oh, ow]),
+         weights_lowres=cf.get_centroid_weight(t_feat), tlabelv_pseudo=ns["tlabelv_pseudo"],
+         feat_pseudo=ns["feat_pseudo"], top2_margin=(top2[:, 0] - top2[:, 1]))
+
+    # ---- online centroid update block: exec self_training.py:327-341 -----------------------
+    cf = ref.Class_Features(numbers=19)
+    cf.objective_vectors = 0.5 * torch.randn((19, d), generator=gen)
+    cf.objective_vectors_num = torch.full((19,), 150.0)
+    before = cf.objective_vectors.clone()
+    sl = _blocky_labels(gen, 2, oh, ow, 8)
+    s_feat = torch.randn((2, d, fh, fw), generator=gen)
+    s_pred = 3.0 * torch.randn((2, 19, fh, fw), generator=gen)
+    s_pred[:, :4] += 5.0
+    t_pred2 = t_pred.clone()
+    t_pred2[:, 2:6] += 5.0
+    ns = {"torch": torch, "F": F, "class_features": cf, "tlabelv_pseudo": ns["tlabelv_pseudo"].clone(),
+          "t_feat_tea": t_feat, "t_pred_tea": t_pred2, "slabelv": sl, "s_feat_tea_aug": s_feat,
+          "s_pred_tea_aug_raw": s_pred}
+    exec(_lines("train_DiGA_gta2city_self_training.py", 327, 341), ns)
+    save("online_update", tlabelv_pseudo=ns["tlabelv_pseudo"], t_feat=t_feat, t_pred=t_pred2, slabel=sl,
+         s_feat=s_feat, s_pred=s_pred, centroids_before=before, num_before=np.full(19, 150.0, np.float32),
+         centroids_after=cf.objective_vectors, num_after=cf.objective_vectors_num,
+         ids_t=np.array(ns["ids_t"]), ids_s=np.array(ns["ids_s"]),
+         newlabels_t=ns["newlabels_t"], newlabels_s=ns["newlabels_s"])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+"""Pin the CPU oracle (oracle/diga_oracle.py) against outputs of the reference itself.
+
+The fixtures under tests/golden/ were produced by tests/golden/make_golden.py, which runs the real
+reference functions and the real reference script line ranges.  Bar: bit-exact (same torch ops on
+the same CPU).  When /root/reference is present the live reference functions are checked too.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import diga_oracle as O
+from oracle import ref_loader
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("name", ["kd_c19", "kd_c16_s025", "kd_saturated"])
+def test_kd_matches_reference_bitwise(golden, name):
+    g = golden(name)
+    t, s = T(g["teacher"]), T(g["student"]).requires_grad_(True)
+    loss = O.distillation_loss(t, s, float(g["scale"]))
+    (loss * float(g["upstream"])).backward()
+    assert np.array_equal(loss.detach().numpy(), g["loss"])
+    assert np.array_equal(s.grad.numpy(), g["grad"])
+    # closed-form gradient agrees to fp32 rounding
+    cf = O.distillation_grad_closed_form(t, s.detach(), float(g["scale"]), float(g["upstream"])).numpy()
+    assert np.abs(cf - g["grad"]).max() <= 1e-5 * np.abs(g["grad"]).max()
+
+
+def test_process_label(golden):
+    g = golden("process_label")
+    assert np.array_equal(O.process_label(T(g["label"])).numpy(), g["onehot"])
+
+
+def test_mean_vector(golden):
+    g = golden("mean_vector")
+    cf = O.ClassFeaturesOracle(19, g["feat"].shape[1])
+    for tag, labels in (("nolabel", None), ("label", T(g["labels"]))):
+        vec, ids = cf.calculate_mean_vector(T(g["feat"]), T(g["out"]), labels)
+        assert ids == g["ids_" + tag].tolist()
+        assert vec[0].shape == (g["feat"].shape[1], 1, 1)
+        assert np.array_equal(torch.stack(vec).reshape(len(ids), -1).numpy(), g["vec_" + tag])
+    vec, ids = cf.calculate_mean_vector_by_output(T(g["feat"]), T(g["out"]))
+    assert ids == g["ids_by_output"].tolist()
+    assert np.array_equal(torch.stack(vec).reshape(len(ids), -1).numpy(), g["vec_by_output"])
+    # the fixture exercises the "<5 pixels -> skipped" rule
+    assert len(g["ids_nolabel"]) < 2 * 19 and len(g["ids_label"]) <= len(g["ids_nolabel"])
+
+
+def replay_updates(cf, g):
+    modes = ["mean", "moving_average"]
+    at = int(g["clamp_inject_at"])
+    for k, (cid, vec, m, sm) in enumerate(zip(g["ids"], g["vecs"], g["modes"], g["start_mean"])):
+        if k == at:
+            cf.objective_vectors_num[int(g["clamp_inject_class"])] = float(g["clamp_inject_value"])
+        cf.update_objective_SingleVector(int(cid), T(vec).reshape(-1, 1, 1), modes[int(m)], start_mean=bool(sm))
+
+
+def test_centroid_update_sequence(golden):
+    g = golden("centroid_update")
+    cf = O.ClassFeaturesOracle(19, g["vecs"].shape[1])
+    replay_updates(cf, g)
+    assert np.array_equal(cf.objective_vectors.numpy(), g["objective_vectors"])
+    assert np.array_equal(cf.objective_vectors_num.numpy(), g["objective_vectors_num"])
+    assert g["objective_vectors_num"][3] == 3000.0
+    with pytest.raises(NotImplementedError):
+        cf.update_objective_SingleVector(0, torch.ones(8, 1, 1), "median", start_mean=False)
+
+
+@pytest.mark.parametrize("name", ["proto_d256", "proto_d64"])
+def test_proto_distance(golden, name):
+    g = golden(name)
+    cf = O.ClassFeaturesOracle(19, g["feat"].shape[1])
+    cf.objective_vectors = T(g["centroids"])
+    assert np.array_equal(cf.feat_centroid_distance(T(g["feat"])).numpy(), g["dist"])
+    assert np.array_equal(cf.get_centroid_weight(T(g["feat"])).numpy(), g["weight"])
+    assert np.array_equal(cf.get_centroid_distance(T(g["feat"])).numpy(), g["negdist"])
+
+
+@pytest.mark.parametrize("name", ["pseudo_label", "pseudo_label_sat"])
+def test_pseudo_label(golden, name):
+    g = golden(name)
+    label, conf = O.pseudo_label_from_logits(T(g["output"]), T(g["output_ds"]))
+    assert np.array_equal(label, g["label"])
+    assert np.array_equal(conf, g["prob_hwc"].max(axis=2))
+
+
+def test_pseudo_label_two_scale(golden):
+    g = golden("pseudo_label_two_scale")
+    label, _ = O.pseudo_label_two_scale(T(g["logits"]), T(g["logits_ds"]), g["size"].tolist())
+    assert np.array_equal(label, g["label"])
+    assert O.pseudo_label_to_uint8(label).dtype == np.uint8
+
+
+def test_classmix(golden):
+    g = golden("classmix")
+    sl, a, b, tl = T(g["slabel"]), T(g["a"]), T(g["b"]), T(g["tlabel"])
+    mask, mix = O.classmix(sl, a, b, rng=random.Random(int(g["seed_img"])))
+    assert np.array_equal(mask.numpy(), g["mask_img"])
+    assert np.array_equal(mix.numpy().view(np.uint32), g["mix_img"].view(np.uint32))
+    mask, mix, ml = O.classmix(sl, a, b, tl, rng=random.Random(int(g["seed_dacs"])))
+    assert np.array_equal(mask.numpy(), g["mask_dacs"])
+    assert np.array_equal(mix.numpy().view(np.uint32), g["mix_dacs"].view(np.uint32))
+    assert ml.dtype == torch.int64 and np.array_equal(ml.numpy(), g["mixlabel_dacs"])
+    # every-label-255 batch: the reference never creates the mix tensor
+    m2, mix2 = O.classmix(torch.full_like(sl, 255), a, b, rng=random.Random(0))
+    assert mix2 is None and bool((m2 == 1).all())
+
+
+def test_consensus(golden):
+    g = golden("consensus")
+    cf = O.ClassFeaturesOracle(19, g["t_feat"].shape[1])
+    cf.objective_vectors = T(g["centroids"])
+    w = cf.get_centroid_weight(T(g["t_feat"]))
+    assert np.array_equal(w.numpy(), g["weights_lowres"])
+    kept, fp = O.consensus_select(T(g["pseudo_prob"]), w, g["out_size"].tolist())
+    assert np.array_equal(kept.numpy(), g["tlabelv_pseudo"])
+    assert np.array_equal(fp.numpy(), g["feat_pseudo"])
+
+
+def test_online_update_block(golden):
+    """self_training.py:327-341 — nearest label down-sampling, label-gated means, EMA updates."""
+    g = golden("online_update")
+    d = g["t_feat"].shape[1]
+    cf = O.ClassFeaturesOracle(19, d)
+    cf.objective_vectors = T(g["centroids_before"]).clone()
+    cf.objective_vectors_num = T(g["num_before"]).clone()
+    for lab, feat, pred, key in ((g["tlabelv_pseudo"], g["t_feat"], g["t_pred"], "t"),
+                                 (g["slabel"], g["s_feat"], g["s_pred"], "s")):
+        nl = O.nearest_labels_to_feature_grid(T(lab), feat.shape[2:])
+        assert np.array_equal(nl.numpy(), g["newlabels_" + key])
+        vec, ids = cf.calculate_mean_vector(T(feat), T(pred), nl)
+        assert ids == g["ids_" + key].tolist()
+        for v, i in zip(vec, ids):
+            cf.update_objective_SingleVector(i, v.detach(), start_mean=False)
+    assert np.array_equal(cf.objective_vectors.numpy(), g["centroids_after"])
+    assert np.array_equal(cf.objective_vectors_num.numpy(), g["num_after"])
+
+
+@pytest.mark.skipif(not ref_loader.available("G"), reason="/root/reference not present (GPU box)")
+def test_oracle_vs_live_reference():
+    ref = ref_loader.load("G")
+    gen = torch.Generator().manual_seed(5)
+    t, s = 3 * torch.randn((6, 19, 12, 20), generator=gen), 3 * torch.randn((6, 19, 12, 20), generator=gen)
+    assert torch.equal(ref.distillation_loss(t, s), O.distillation_loss(t, s))
+    feat, out = torch.randn((3, 48, 17, 19), generator=gen), 3 * torch.randn((3, 19, 17, 19), generator=gen)
+    rcf, ocf = ref.Class_Features(19), O.ClassFeaturesOracle(19, 48)
+    rcf.objective_vectors = torch.zeros(19, 48)
+    for _ in range(2):
+        rv, ri = rcf.calculate_mean_vector(feat, out)
+        ov, oi = ocf.calculate_mean_vector(feat, out)
+        assert ri == oi and all(torch.equal(a, b) for a, b in zip(rv, ov))
+        for v, i in zip(rv, ri):
+            rcf.update_objective_SingleVector(i, v.detach().cpu().numpy(), "mean")
+            ocf.update_objective_SingleVector(i, v.detach().cpu().numpy(), "mean")
+    assert torch.equal(rcf.objective_vectors, ocf.objective_vectors)
+    assert torch.equal(rcf.get_centroid_weight(feat), ocf.get_centroid_weight(feat))
