@@ -1,0 +1,25 @@
+"""diga_b200 — B200-native (sm_100a) implementation of DiGA's per-pixel adaptation hot path.
+
+Host side mirrors the reference's interface for this path:
+
+* ``diga_b200.util.loss.distillation_loss``          <- ``util/loss.py:125``
+* ``diga_b200.util.utils.process_label``             <- ``util/utils.py:158``
+* ``diga_b200.calc_centroids.Class_Features`` / ``calc_centroids`` <- ``calc_centroids.py:84`` / ``:17``
+* ``diga_b200.classmix.classmix``                    <- inline block ``train_DiGA_gta2city_self_training.py:259-275, 306-325``
+* ``diga_b200.selection.consensus_select``           <- inline block ``:298-304``
+* ``diga_b200.pseudolabel.pseudo_label``             <- inline block ``pseudolabel_generator.py:77-85``
+
+Everything runs through ``libdiga_b200.so`` (C ABI in ``include/diga_b200.h``); importing this package fails
+loudly when the library has not been built.  There is no CPU fallback.
+"""
+from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
+from .calc_centroids import Class_Features, calc_centroids
+from .classmix import classmix
+from .pseudolabel import pseudo_label, pseudo_label_two_scale
+from .selection import consensus_select
+from .util.loss import distillation_loss, distillation_loss_and_grad
+from .util.utils import process_label
+
+__all__ = ["Class_Features", "calc_centroids", "classmix", "pseudo_label", "pseudo_label_two_scale",
+           "consensus_select", "distillation_loss", "distillation_loss_and_grad", "process_label"]
+__version__ = "0.1.0"

@@ -1,0 +1,120 @@
+"""ctypes binding of ``libdiga_b200.so`` (the C ABI declared in ``include/diga_b200.h``).
+
+There is no CPU fallback and no alternative backend: if the shared library has not been built
+(``python -m diga_b200.build``) importing this module raises, and every wrapper refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiga_b200.so")
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m diga_b200.build` "
+        "(nvcc, sm_100a). diga_b200 has no CPU or PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_f = C.c_float
+_d = C.c_double
+_i = C.c_int
+
+# name -> (restype, argtypes); kept in the same order as include/diga_b200.h
+SIGNATURES = {
+    "diga_version": (_i, []),
+    "diga_last_error_string": (C.c_char_p, []),
+    "diga_launch_count": (_i64, []),
+    "diga_set_tunable": (_i, [C.c_char_p, _i]),
+    "diga_kd_workspace_bytes": (C.c_size_t, []),
+    "diga_kd_fwd": (_i, [_p, _p, _i64, _i64, _i64, _f, _p, _p, _p]),
+    "diga_kd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _f, _p, _p, _p]),
+    "diga_kd_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
+    "diga_pseudo_label": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_class_presence": (_i, [_p, _i64, _i64, _p, _p, _p]),
+    "diga_classmix_blend": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_centroid_assign": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "diga_centroid_accum": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p]),
+    "diga_centroid_means": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_centroid_update": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
+    "diga_centroid_update_single": (_i, [_p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
+    "diga_centroid_reduce_images": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p]),
+    "diga_onehot_labels": (_i, [_p, _i64, _i64, _i64, _p, _p]),
+    "diga_proto_workspace_bytes": (C.c_size_t, [_i64, _i64]),
+    "diga_proto_distance": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_consensus_select": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "diga_upsample_bilinear": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "diga_pseudo_label_upsampled": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)      # AttributeError here == the .so is stale; rebuild
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+UPDATE_MEAN, UPDATE_MOVING_AVERAGE = 0, 1
+
+
+def last_error() -> str:
+    return lib.diga_last_error_string().decode()
+
+
+def check(rc: int) -> None:
+    """Non-zero C return code -> RuntimeError carrying diga_last_error_string()."""
+    if rc != 0:
+        raise RuntimeError(f"diga_b200 error {rc}: {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib.diga_launch_count())
+
+
+def set_tunable(name: str, value: int) -> None:
+    lib.diga_set_tunable(name.encode(), int(value))
+
+
+def ptr(t):
+    """data_ptr of a tensor, or NULL for None."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors, what="input") -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(f"diga_b200: {what} must be a CUDA tensor (there is no CPU fallback); got {t.device}")
+
+
+def f32c(t):
+    """Contiguous fp32 view of ``t`` (the reference tensors already are; this is a no-op for them)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def i64c(t):
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+_workspaces = {}
+
+
+def kd_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised KD reduction workspace, one per (device, stream)."""
+    key = (device.index, stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.diga_kd_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

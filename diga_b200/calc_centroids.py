@@ -1,0 +1,238 @@
+"""Drop-in for ``calc_centroids.py`` of the reference: ``Class_Features`` and the ``calc_centroids`` driver.
+
+Reference: ``domain_adaptation/GTA5/calc_centroids.py`` — class ``Class_Features`` :84-180, driver :17-81.
+Names, arguments and return structures are the reference's; the work is done by the sm_100a kernels in
+``csrc/centroid.cu`` (a6/a7) and ``csrc/proto.cu`` / ``csrc/proto_umma.cu`` (a5).  State lives on the GPU.
+
+What changes for the caller: nothing in the signatures.  ``calculate_mean_vector`` costs one host sync
+(the list of class ids is a Python list) instead of ~95; ``update_objective_SingleVector`` costs none.
+The fused entry points ``update_from_features`` / ``accumulate_mean_pass`` (not in the reference) do the
+whole a6 -> a7 chain without any host sync and are what the ``calc_centroids`` driver below uses.
+"""
+from __future__ import annotations
+
+import os
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from .classmix import classmix
+
+_MODES = {"mean": L.UPDATE_MEAN, "moving_average": L.UPDATE_MOVING_AVERAGE}
+
+
+class Class_Features:
+    """Per-class feature centroids (prototypes); reference ``calc_centroids.py:84-95``.
+
+    Attributes kept from the reference: ``class_numbers``, ``objective_vectors [C,D]`` (D = 256 until
+    re-assigned; the self-training script assigns a loaded tensor from outside, self_training.py:168-170),
+    ``objective_vectors_num [C]``, ``centroid_momentum``.  Both tensors are fp32 CUDA tensors here; assigning
+    a CPU tensor or array moves it to the device.
+    """
+
+    def __init__(self, numbers=19, feat_dim=256, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("diga_b200.Class_Features needs a CUDA device (there is no CPU fallback)")
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.class_numbers = numbers
+        self.objective_vectors = torch.zeros([numbers, feat_dim])
+        self.objective_vectors_num = torch.zeros([numbers])
+        self.centroid_momentum = 0.0001
+        self.valid_classes = list(range(numbers))
+        self._proto_ws = None
+
+    # -- state ----------------------------------------------------------------------------------
+    def _to_state(self, value):
+        if isinstance(value, np.ndarray):
+            value = torch.from_numpy(value)
+        return torch.as_tensor(value).detach().to(device=self._device, dtype=torch.float32).contiguous()
+
+    @property
+    def objective_vectors(self):
+        return self._objective_vectors
+
+    @objective_vectors.setter
+    def objective_vectors(self, value):
+        self._objective_vectors = self._to_state(value)
+
+    @property
+    def objective_vectors_num(self):
+        return self._objective_vectors_num
+
+    @objective_vectors_num.setter
+    def objective_vectors_num(self, value):
+        self._objective_vectors_num = self._to_state(value)
+
+    @property
+    def feat_dim(self):
+        return int(self._objective_vectors.shape[1])
+
+    # -- a6 -------------------------------------------------------------------------------------
+    def _masked_means(self, feat_cls, outputs, labels_val):
+        """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C])."""
+        L.require_cuda(feat_cls, outputs, labels_val, what="Class_Features input")
+        feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
+        n, d, h, w = feat.shape
+        c = self.class_numbers
+        if out.shape != (n, c, h, w):
+            raise ValueError(f"outputs must be [{n},{c},{h},{w}], got {tuple(out.shape)}")
+        lab = None
+        if labels_val is not None:
+            lab = L.f32c(labels_val.detach())
+            if lab.shape != (n, 1, h, w):
+                raise ValueError(f"labels_val must be [{n},1,{h},{w}], got {tuple(lab.shape)}")
+        dev, hw, st = feat.device, h * w, L.stream()
+        cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
+        counts = torch.empty((n, c), dtype=torch.int32, device=dev)
+        sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
+        vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
+        vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
+        valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
+        L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(), st))
+        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, c, hw, sums.data_ptr(), st))
+        L.check(L.lib.diga_centroid_means(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, vec.data_ptr(),
+                                          vecsum.data_ptr(), valid.data_ptr(), st))
+        return vec, vecsum, valid
+
+    def calculate_mean_vector(self, feat_cls, outputs, labels_val=None, model=None):
+        """Reference ``calc_centroids.py:120-145``: per image and class the mean feature over the pixels whose
+        arg-max prediction (and, if given, label) is that class; classes with < 5 pixels are skipped.
+        Returns ``(vectors, ids)`` — ``[D,1,1]`` tensors and Python ints, ordered by (image, class)."""
+        vec, _, valid = self._masked_means(feat_cls, outputs, labels_val)
+        keep = valid.cpu().numpy().astype(bool)                      # the single host sync of this call
+        d = vec.shape[2]
+        vectors, ids = [], []
+        for n, t in zip(*np.nonzero(keep)):
+            vectors.append(vec[n, t].view(d, 1, 1))
+            ids.append(int(t))
+        return vectors, ids
+
+    def calculate_mean_vector_by_output(self, feat_cls, outputs):
+        """Reference ``calc_centroids.py:97-118`` (prediction only)."""
+        return self.calculate_mean_vector(feat_cls, outputs, None)
+
+    # -- a7 -------------------------------------------------------------------------------------
+    def _mode(self, name):
+        if name not in _MODES:
+            raise NotImplementedError('no such updating way of objective vectors {}'.format(name))
+        return _MODES[name]
+
+    def update_objective_SingleVector(self, id, vector, name='moving_average', start_mean=True):
+        """Reference ``calc_centroids.py:147-164``.  ``vector`` may be a torch tensor (any device) or a numpy
+        array of D elements.  All conditions (zero vector, ``num < 100``) are evaluated on the GPU."""
+        mode = self._mode(name)
+        if isinstance(vector, np.ndarray):
+            vector = torch.from_numpy(vector)
+        v = vector.detach().to(device=self._device, dtype=torch.float32).reshape(-1).contiguous()
+        if v.numel() != self.feat_dim:
+            raise ValueError(f"vector has {v.numel()} elements, centroids have {self.feat_dim}")
+        L.check(L.lib.diga_centroid_update_single(v.data_ptr(), int(id), self.class_numbers, self.feat_dim,
+                                                  self._objective_vectors.data_ptr(),
+                                                  self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
+                                                  float(self.centroid_momentum), L.stream()))
+
+    def update_from_features(self, feat_cls, outputs, labels_val=None, name='moving_average', start_mean=True):
+        """Fused a6 -> a7 (not in the reference): equals ``calculate_mean_vector`` followed by
+        ``update_objective_SingleVector`` on every returned vector in order, with no host sync."""
+        mode = self._mode(name)
+        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val)
+        n, c, d = vec.shape
+        if d != self.feat_dim:
+            raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")
+        L.check(L.lib.diga_centroid_update(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d,
+                                           self._objective_vectors.data_ptr(), self._objective_vectors_num.data_ptr(),
+                                           mode, int(bool(start_mean)), float(self.centroid_momentum), L.stream()))
+
+    def accumulate_mean_pass(self, acc, feat_cls, outputs, labels_val=None):
+        """Multi-GPU 'mean' pass: ``acc [C, D+1]`` += (sum of per-image class means, image count).
+        ``diga_b200.parallel.finish_mean_pass`` all-reduces ``acc`` and writes the centroids."""
+        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val)
+        n, c, d = vec.shape
+        if tuple(acc.shape) != (c, d + 1) or acc.dtype != torch.float32 or not acc.is_cuda:
+            raise ValueError(f"acc must be a CUDA fp32 [{c},{d + 1}] tensor")
+        L.check(L.lib.diga_centroid_reduce_images(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d,
+                                                  acc.data_ptr(), L.stream()))
+
+    # -- a5 -------------------------------------------------------------------------------------
+    def _proto(self, feat, want_dist, want_weight):
+        L.require_cuda(feat, what="Class_Features input")
+        f = L.f32c(feat.detach())
+        n, d, h, w = f.shape
+        c = self.class_numbers
+        if d != self.feat_dim:
+            raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")
+        cen = self._objective_vectors
+        if cen.device != f.device:
+            cen = cen.to(f.device)
+        need = int(L.lib.diga_proto_workspace_bytes(c, d))
+        if self._proto_ws is None or self._proto_ws.numel() < need or self._proto_ws.device != f.device:
+            self._proto_ws = torch.empty(need, dtype=torch.uint8, device=f.device)
+        dist = torch.empty((n, c, h, w), dtype=torch.float32, device=f.device) if want_dist else None
+        weight = torch.empty((n, c, h, w), dtype=torch.float32, device=f.device) if want_weight else None
+        L.check(L.lib.diga_proto_distance(f.data_ptr(), cen.data_ptr(), n, d, c, h * w, L.ptr(dist), L.ptr(weight),
+                                          self._proto_ws.data_ptr(), L.stream()))
+        return dist, weight
+
+    def feat_centroid_distance(self, feat):
+        """``[N,C,H,W]`` L2 distance of every feature pixel to every centroid; reference :166-171."""
+        return self._proto(feat, True, False)[0]
+
+    def get_centroid_weight(self, feat):
+        """``softmax(-distance)`` over classes; reference :173-176."""
+        return self._proto(feat, False, True)[1]
+
+    def get_centroid_distance(self, feat):
+        """Negated distance; reference :178-180."""
+        return self._proto(feat, True, False)[0].neg_()
+
+
+def _labels_on_feature_grid(labels_i64, size):
+    """self_training.py:329-330 / calc_centroids.py:60-62: [B,H,W] int64 -> [B,1,h,w] fp32, nearest."""
+    b, h, w = labels_i64.size()
+    return F.interpolate(labels_i64.reshape([b, 1, h, w]).float(), size=tuple(size), mode='nearest')
+
+
+def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full, target_loader):
+    """Reference driver ``calc_centroids.py:17-81``: five passes over the loader, running 'mean' update of the
+    class centroids, ``feat_centroids`` written next to ``opt.centroid_dir`` after every pass.
+
+    ``model(x)`` must return ``(_, _, logits, feat)`` like the reference ``SegModel``.  As in the reference the
+    target branch is always taken (``opt.source`` is overwritten with ``False``, :27); the source branch is kept
+    for completeness (:29-65).  Returns the ``Class_Features`` object (the reference returns ``None``).
+    """
+    class_features = Class_Features(numbers=19)
+    first = True
+    for epoch in range(5):
+        model.eval(), enc_s.eval(), dec_s2t.eval()
+        opt.source = False
+        if opt.source:
+            for index, (batch, batch_full) in enumerate(zip(source_loader, source_loader_full)):
+                sdatav = torch.cat([batch[0].cuda(), batch_full[0].cuda()], dim=0)
+                slabelv = torch.cat([batch[1].cuda(), batch_full[1].cuda()], dim=0)
+                with torch.no_grad():
+                    rec_s2t = dec_s2t(enc_s(sdatav))
+                    _, transmix = classmix(slabelv, rec_s2t, sdatav, rng=random)
+                    _, _, out, feature_s = model(transmix)
+                    if first:
+                        class_features.objective_vectors = torch.zeros([19, feature_s.shape[1]])
+                        first = False
+                    newlabels = _labels_on_feature_grid(slabelv, out.size()[2:])
+                    class_features.update_from_features(feature_s, out, newlabels, 'mean')
+        else:
+            for index, batch in enumerate(target_loader):
+                if index % 100 == 0:
+                    print('epoch', epoch)
+                    print('%d processd' % index)
+                tdatav = batch[0].cuda()
+                with torch.no_grad():
+                    _, _, out, feature_t = model(tdatav)
+                    if first:
+                        class_features.objective_vectors = torch.zeros([19, feature_t.shape[1]])
+                        first = False
+                    class_features.update_from_features(feature_t, out, None, 'mean')
+        save_path = os.path.join(os.path.dirname(opt.centroid_dir), "feat_centroids")
+        torch.save(class_features.objective_vectors.cpu(), save_path)
+    return class_features

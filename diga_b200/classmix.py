@@ -1,0 +1,88 @@
+"""Cross-domain ClassMix: class-presence bitmap on the GPU, class choice on the host, LUT blend on the GPU.
+
+The reference has no function for this; it is the statement block
+``train_DiGA_gta2city_self_training.py:259-275`` (image only), ``:306-325`` (DACS: image + label),
+``train_DiGA_gta2city_warm_up.py:240-259`` and ``calc_centroids.py:47-58``.  ``classmix`` has tensor-in /
+tensor-out semantics equal to those blocks; a patched script replaces each block by one call
+(INTEGRATION.md).  The host draws ``random.sample(sorted_present_classes, len // 2)`` per image exactly as
+the reference does, so a seeded ``random`` produces the same masks.
+"""
+from __future__ import annotations
+
+import random as _random
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+IGNORE = 255
+
+
+def present_classes(slabel: torch.Tensor):
+    """Per image, the sorted list of label values present — ``torch.unique(slabel[i]).tolist()`` (:265) — from a
+    256-bit device bitmap (32 B per image over PCIe instead of a sort + sync per image)."""
+    L.require_cuda(slabel, what="classmix label")
+    lab = L.i64c(slabel)
+    b = lab.shape[0]
+    hw = lab[0].numel() if b else 0
+    bitmap = torch.empty((b, 8), dtype=torch.int32, device=lab.device)
+    flags = torch.empty((1,), dtype=torch.int32, device=lab.device)
+    L.check(L.lib.diga_class_presence(lab.data_ptr(), b, hw, bitmap.data_ptr(), flags.data_ptr(), L.stream()))
+    host = torch.cat([bitmap.reshape(-1), flags]).cpu().numpy().view(np.uint32)     # the one host sync
+    if host[-1]:
+        raise ValueError("classmix: labels must lie in [0, 255] (trainIds plus the 255 ignore value)")
+    bits = np.unpackbits(host[:-1].view(np.uint8).reshape(b, 32), axis=1, bitorder="little")
+    return [np.nonzero(row)[0].tolist() for row in bits]
+
+
+def select_classes(present, rng=_random):
+    """``random.sample(label_list, len(label_list) // 2)`` then append 255 if absent (:266-268)."""
+    chosen = []
+    for label_list in present:
+        sel = rng.sample(label_list, len(label_list) // 2)
+        if IGNORE not in sel:
+            sel.append(IGNORE)
+        chosen.append(sel)
+    return chosen
+
+
+def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True):
+    """ClassMix mask build + blend.
+
+    ``slabel [B,H,W]`` int64 source labels; ``a``, ``b`` ``[B,CH,H,W]`` fp32; optional ``tlabel [B,H,W]`` int64.
+    ``mask = 1`` where ``slabel`` is one of the chosen classes; ``mix = a*(1-mask) + b*mask`` (bit-exact with
+    the reference expression); with ``tlabel``: ``mixlabel = where(mask, slabel, tlabel)``.
+    Returns ``(mask, mix)`` or ``(mask, mix, mixlabel)``; ``mix`` is ``None`` when every label is 255, the case
+    in which the reference never creates the tensor (:271 / :321).
+    """
+    L.require_cuda(slabel, a, b, tlabel, what="classmix input")
+    lab = L.i64c(slabel)
+    bsz = lab.shape[0]
+    present = None
+    if classes is None:
+        present = present_classes(lab)
+        classes = select_classes(present, rng)
+    lut_host = np.zeros((bsz, 256), dtype=np.uint8)
+    for i, sel in enumerate(classes):
+        lut_host[i, [c for c in sel if 0 <= c <= 255]] = 1
+    lut = torch.from_numpy(lut_host).to(lab.device, non_blocking=True)
+    hw = lab[0].numel() if bsz else 0
+    fa, fb = L.f32c(a), L.f32c(b)
+    if fa.shape != fb.shape or fa.shape[0] != bsz or fa[0, 0].numel() != hw:
+        raise ValueError("classmix: image / label shapes do not match")
+    if present is None:
+        all_ignore = bool(torch.all(torch.eq(lab, IGNORE)))
+    else:
+        all_ignore = all(p == [IGNORE] for p in present)
+    mask = torch.empty(lab.shape, dtype=torch.float32, device=lab.device) if return_mask else None
+    mix = None if all_ignore else torch.empty_like(fa)
+    tl = mixlabel = None
+    if tlabel is not None:
+        tl = L.i64c(tlabel)
+        mixlabel = torch.empty_like(tl)
+    L.check(L.lib.diga_classmix_blend(lab.data_ptr(), lut.data_ptr(), L.ptr(fa), L.ptr(fb), L.ptr(tl), bsz, fa.shape[1],
+                                      hw, L.ptr(mask), L.ptr(mix), L.ptr(mixlabel), L.stream()))
+    if tlabel is None:
+        return mask, mix
+    return mask, mix, mixlabel

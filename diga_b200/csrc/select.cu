@@ -1,0 +1,144 @@
+// a4 — bilateral-consensus ("threshold-free dynamic") pseudo-label selection.
+// Replaces train_DiGA_gta2city_self_training.py:298-304 of the reference: the stride-8 prototype weights
+// [B,C,h,w] are bilinearly up-sampled (align_corners=True) to [B,C,H,W], arg-maxed, and the stored
+// pseudo-label is kept only where it agrees.  The up-sampled tensor (76 B/px) is never materialised:
+// this kernel reads the low-resolution weights through L1/L2 (~1.2 B/px amortised), the int64
+// pseudo-labels (8 B/px) and writes the two int64 maps (16 B/px).
+#include "bilinear.cuh"
+#include "common.cuh"
+
+namespace diga {
+
+int tunable(const char* name, int dflt);
+
+// Generic up-sampler (materialising); used by tests to pin the interpolation against torch bit for bit
+// and by callers that need the up-sampled map itself.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+upsample_bilinear_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int H, int W, float sh, float sw,
+                         float* __restrict__ out) {
+  const int64_t total = planes * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < total; i += (int64_t)gridDim.x * BLOCK) {
+    const int X = (int)(i % W);
+    const int64_t r = i / W;
+    const int Y = (int)(r % H);
+    const int64_t pl = r / H;
+    const Tap ty = bilinear_tap(sh, Y, h), tx = bilinear_tap(sw, X, w);
+    const float* src = in + pl * h * w;
+    const float top = bilinear_row(tx, __ldg(src + (int64_t)ty.i0 * w + tx.i0), __ldg(src + (int64_t)ty.i0 * w + tx.i1));
+    const float bot = bilinear_row(tx, __ldg(src + (int64_t)ty.i1 * w + tx.i0), __ldg(src + (int64_t)ty.i1 * w + tx.i1));
+    out[i] = bilinear_col(ty, top, bot);
+  }
+}
+
+// One thread = PX adjacent output pixels of one row.  torch.max(dim=1) semantics: first index on ties.
+template <int C, bool PAD, int PX, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict__ pseudo, int nclass, int h, int w, int H,
+                        int W, float sh, float sw, int64_t* __restrict__ kept, int64_t* __restrict__ feat_pseudo) {
+  const int64_t img = blockIdx.z;
+  const int Y = blockIdx.y;
+  const int gx = blockIdx.x * BLOCK + threadIdx.x;
+  const int X0 = gx * PX;
+  if (X0 >= W) return;
+  const Tap ty = bilinear_tap(sh, Y, h);
+  const float* base = wl + img * nclass * h * w;
+  const int64_t plane = (int64_t)h * w;
+  int64_t lab[PX];
+  const int64_t o = (img * H + Y) * W + X0;
+  if constexpr (PX == 2) {
+    const longlong2 t = ld_stream_i64x2(pseudo + o);
+    lab[0] = t.x;
+    lab[1] = t.y;
+  } else {
+    lab[0] = ld_stream_i64(pseudo + o);
+  }
+  int64_t am[PX];
+#pragma unroll
+  for (int v = 0; v < PX; ++v) {
+    const Tap tx = bilinear_tap(sw, X0 + v, w);
+    const float* r0 = base + (int64_t)ty.i0 * w;
+    const float* r1 = base + (int64_t)ty.i1 * w;
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
+        const float* q0 = r0 + c * plane;
+        const float* q1 = r1 + c * plane;
+        const float top = bilinear_row(tx, __ldg(q0 + tx.i0), __ldg(q0 + tx.i1));
+        const float bot = bilinear_row(tx, __ldg(q1 + tx.i0), __ldg(q1 + tx.i1));
+        const float val = bilinear_col(ty, top, bot);
+        if (c == 0 || val > best) {
+          best = val;
+          arg = c;
+        }
+      }
+    am[v] = arg;
+  }
+  int64_t kp[PX];
+#pragma unroll
+  for (int v = 0; v < PX; ++v) kp[v] = (lab[v] == am[v]) ? lab[v] : (int64_t)DIGA_IGNORE_LABEL;   // :304
+  if constexpr (PX == 2) {
+    st_stream_i64x2(kept + o, kp[0], kp[1]);
+    if (feat_pseudo) st_stream_i64x2(feat_pseudo + o, am[0], am[1]);
+  } else {
+    st_stream_i64(kept + o, kp[0]);
+    if (feat_pseudo) st_stream_i64(feat_pseudo + o, am[0]);
+  }
+}
+
+}  // namespace diga
+
+extern "C" {
+
+int diga_upsample_bilinear(const float* in, int64_t planes, int64_t h, int64_t w, int64_t H, int64_t W, float* out,
+                           diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(in && out, DIGA_ERR_INVALID, "upsample_bilinear: null pointer");
+  DIGA_REQUIRE(planes >= 0 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && h < (1 << 24) && w < (1 << 24) && H < (1 << 24) &&
+                   W < (1 << 24),
+               DIGA_ERR_INVALID, "upsample_bilinear: bad sizes");
+  if (planes == 0) return DIGA_OK;
+  const int64_t total = planes * H * W;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  upsample_bilinear_kernel<256><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      in, planes, (int)h, (int)w, (int)H, (int)W, bilinear_scale_host(h, H), bilinear_scale_host(w, W), out);
+  DIGA_CHECK_LAUNCH("upsample_bilinear_kernel");
+  return DIGA_OK;
+}
+
+int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, int64_t B, int64_t C, int64_t h, int64_t w,
+                          int64_t H, int64_t W, int64_t* kept, int64_t* feat_pseudo, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(weights_lowres && pseudo && kept, DIGA_ERR_INVALID, "consensus_select: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "consensus_select: C=%lld outside [1,%d]", (long long)C,
+               DIGA_MAX_CLASSES);
+  DIGA_REQUIRE(B >= 0 && B <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && H <= 65535 && h < (1 << 24) && w < (1 << 24) &&
+                   W < (1 << 24),
+               DIGA_ERR_INVALID, "consensus_select: bad sizes");
+  DIGA_REQUIRE(aligned(weights_lowres, 4) && aligned(pseudo, 8) && aligned(kept, 8) && aligned(feat_pseudo, 8),
+               DIGA_ERR_MISALIGNED, "consensus_select: misaligned pointer");
+  if (B == 0) return DIGA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
+  const bool pair = (W % 2) == 0 && aligned(pseudo, 16) && aligned(kept, 16) && aligned(feat_pseudo, 16);
+  constexpr int BLOCK = 128;
+  DIGA_DISPATCH_C(C, {
+    if (pair) {
+      dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), (unsigned)H, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 2, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
+                                                                         (int)H, (int)W, sh, sw, kept, feat_pseudo);
+    } else {
+      dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), (unsigned)H, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 1, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
+                                                                         (int)H, (int)W, sh, sw, kept, feat_pseudo);
+    }
+  });
+  DIGA_CHECK_LAUNCH("consensus_select_kernel");
+  return DIGA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+/*
+ * diga_b200 — C ABI of the B200 (sm_100a) implementation of DiGA's per-pixel adaptation hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (fy-vision/DiGA) is pure Python, so "the FFI a maintainer would bind" is a ctypes stub; it is
+ * shown in INTEGRATION.md and implemented in diga_b200/_lib.py.  Each entry point names the
+ * reference code it replaces; paths are relative to domain_adaptation/GTA5/ of the reference.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller unless the name ends in _host;
+ *   - tensors are contiguous NCHW fp32, labels are int64 (the reference's LongTensor);
+ *   - `hw` is H*W of one plane, `stream` is a cudaStream_t (NULL = legacy default stream);
+ *   - a call only enqueues work: no allocation, no host synchronisation, no exceptions;
+ *   - return 0 on success, a negative diga_status otherwise; diga_last_error_string()
+ *     describes the last failure on the calling thread.
+ */
+#ifndef DIGA_B200_H_
+#define DIGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* diga_stream_t; /* cudaStream_t */
+
+enum diga_status {
+  DIGA_OK = 0,
+  DIGA_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported class count */
+  DIGA_ERR_MISALIGNED = -2,  /* pointer not aligned to its element size */
+  DIGA_ERR_CUDA = -3,        /* launch failed; see diga_last_error_string() */
+  DIGA_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+enum diga_update_mode { DIGA_UPDATE_MEAN = 0, DIGA_UPDATE_MOVING_AVERAGE = 1 };
+
+#define DIGA_MAX_CLASSES 32
+#define DIGA_IGNORE_LABEL 255
+
+int diga_version(void);
+const char* diga_last_error_string(void);
+/* Number of kernels this library has launched in the calling process (bench.py: gpu_launches). */
+int64_t diga_launch_count(void);
+/* Launch-shape tunables (vector width, waves per SM, kernel variant); not part of the reference-facing
+ * surface — used by tools/tune.py and the tests.  DIGA_TUNE_<NAME> in the environment does the same. */
+int diga_set_tunable(const char* name, int value);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  symmetric KD loss — util/loss.py:125-143 (scale 0.25: Synthia/util/loss.py:52)
+ *   teacher, student: [n2, C, hw] fp32, n2 = 2B even.  Student view v is supervised by
+ *   softmax(teacher view 1-v); the pair whose teacher is view 1 is weighted by `scale`.
+ *   loss = mean_{B,hw} CE(p0, s1) + scale * mean_{B,hw} CE(p1, s0).
+ * workspace: diga_kd_workspace_bytes() bytes, zero-filled once by the caller before first use
+ *   (the kernels leave it zeroed); one workspace per concurrently used stream.
+ * ------------------------------------------------------------------------------------------ */
+size_t diga_kd_workspace_bytes(void);
+/* forward: loss_out[0] = loss (deterministic two-stage reduction). */
+int diga_kd_fwd(const float* teacher, const float* student, int64_t n2, int64_t C, int64_t hw, float scale,
+                float* loss_out, void* workspace, diga_stream_t stream);
+/* backward (autograd of the above): dstudent = upstream[0] * dL/dstudent; `upstream` is a DEVICE
+ * scalar (the 0-dim grad_output), so no host sync is needed. */
+int diga_kd_bwd(const float* teacher, const float* student, int64_t n2, int64_t C, int64_t hw, float scale,
+                const float* upstream, float* dstudent, diga_stream_t stream);
+/* single pass: loss and upstream_host * gradient together (228 B/px instead of 152 + 228). */
+int diga_kd_fwd_bwd(const float* teacher, const float* student, int64_t n2, int64_t C, int64_t hw, float scale,
+                    float upstream_host, float* loss_out, float* dstudent, void* workspace, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  pseudo-label — pseudolabel_generator.py:80-85
+ *   z = max(logits, logits_ds) (logits_ds may be NULL); label = argmax_c softmax(z) (first index
+ *   on ties, taken on the logits); conf = max_c softmax(z).  Any output may be NULL.
+ *   logits: [n, C, hw]; label_u8/label_i64/conf: [n, hw].
+ * ------------------------------------------------------------------------------------------ */
+int diga_pseudo_label(const float* logits, const float* logits_ds, int64_t n, int64_t C, int64_t hw,
+                      uint8_t* label_u8, int64_t* label_i64, float* conf, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2  ClassMix — train_DiGA_gta2city_self_training.py:259-275 (image), :306-325 (DACS),
+ *     train_DiGA_gta2city_warm_up.py:240-259, calc_centroids.py:47-58
+ *   class_presence: bitmap[b][8] (256 bits) of label values present in image b — the device half
+ *     of torch.unique(slabel[b]); flags[0] |= 1 if a label lies outside [0,255].
+ *     bitmap and flags are cleared by the call.
+ *   classmix_blend: lut[b][256] (uint8, 1 = class selected for image b) ->
+ *     mask[b,p] = lut[b][slabel[b,p]]  (fp32 0/1, may be NULL)
+ *     mix[b,c,p] = a*(1-mask) + b*mask  (evaluated exactly as written, no FMA contraction)
+ *     mixlabel[b,p] = mask ? slabel : tlabel   (only if tlabel != NULL)
+ * ------------------------------------------------------------------------------------------ */
+int diga_class_presence(const int64_t* slabel, int64_t B, int64_t hw, uint32_t* bitmap, uint32_t* flags,
+                        diga_stream_t stream);
+int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut, const float* a, const float* b,
+                        const int64_t* tlabel, int64_t B, int64_t channels, int64_t hw,
+                        float* mask, float* mix, int64_t* mixlabel, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  per-image per-class masked feature mean — calc_centroids.py:120-145 (:97-118 by_output),
+ *     one-hot helper util/utils.py:158-163
+ *   assign: cls[n,p] = argmax_c logits[n,:,p] if (labels == NULL or (int64)labels[n,p] == argmax)
+ *           else 255; counts[n][c] = number of pixels assigned to c (cleared by the call).
+ *           labels: [n,1,hw] fp32 as produced by F.interpolate(mode='nearest') of the int64 map.
+ *   accum : sums[n][c][d] = sum over pixels of class c of feat[n,d,p]  (fully overwritten,
+ *           deterministic: every output element has exactly one writer, no atomics).
+ *   means : vec[n][c][d] = (sums/hw) / (counts/hw); valid[n][c] = counts >= 5;
+ *           vecsum[n][c] = sum_d vec (for the reference's `vector.sum() == 0` skip).
+ * ------------------------------------------------------------------------------------------ */
+int diga_centroid_assign(const float* logits, const float* labels, int64_t n, int64_t C, int64_t hw,
+                         uint8_t* cls, int32_t* counts, diga_stream_t stream);
+/* process_label (util/utils.py:158-163): label [B,1,hw] fp32 -> onehot [B,C+1,hw] fp32, ids >= C in channel C.
+ * Negative labels are outside the reference's domain (scatter_ would raise) and give an all-zero column. */
+int diga_onehot_labels(const float* label, int64_t B, int64_t C, int64_t hw, float* onehot, diga_stream_t stream);
+int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_t D, int64_t C, int64_t hw,
+                        float* sums, diga_stream_t stream);
+int diga_centroid_means(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw,
+                        float* vec, float* vecsum, uint8_t* valid, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7  centroid running update — calc_centroids.py:147-164
+ *   Applies, in (image, class) order, update_objective_SingleVector(c, vec[n][c], mode, start_mean)
+ *   for every (n, c) with valid[n][c] != 0 and vecsum[n][c] != 0.  valid may be NULL (all valid).
+ *   objective_vectors [C, D], objective_num [C] are updated in place (fp32, clamp at 3000,
+ *   start_mean forces 'mean' while num < 100).  `momentum` is a double because the reference
+ *   evaluates (1 - centroid_momentum) in Python double precision before torch rounds it to fp32.
+ * ------------------------------------------------------------------------------------------ */
+int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n, int64_t C,
+                         int64_t D, float* objective_vectors, float* objective_num, int mode, int start_mean,
+                         double momentum, diga_stream_t stream);
+/* single vector form (the reference's per-call API): class `id`, vector [D]. */
+int diga_centroid_update_single(const float* vector, int64_t id, int64_t C, int64_t D, float* objective_vectors,
+                                float* objective_num, int mode, int start_mean, double momentum,
+                                diga_stream_t stream);
+/* multi-GPU 'mean' pass: acc[c][0..D) += sum over valid images of vec, acc[c][D] += their number.
+ * acc: [C, D+1] fp32 (the buffer that is all-reduced over NCCL). */
+int diga_centroid_reduce_images(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n,
+                                int64_t C, int64_t D, float* acc, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  prototype distance + reweighted softmax — calc_centroids.py:166-180
+ *   dist[n,c,p] = || centroids[c,:] - feat[n,:,p] ||_2 ; weight = softmax_c(-dist).
+ *   Either output may be NULL.  feat: [n, D, hw]; centroids: [C, D]; outputs: [n, C, hw].
+ *   workspace: diga_proto_workspace_bytes(C, D) bytes (split centroid operands for the tensor-core path).
+ * ------------------------------------------------------------------------------------------ */
+size_t diga_proto_workspace_bytes(int64_t C, int64_t D);
+int diga_proto_distance(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw,
+                        float* dist, float* weight, void* workspace, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  bilateral-consensus selection — train_DiGA_gta2city_self_training.py:298-304
+ *   W = bilinear(align_corners=True) up-sampling of weights_lowres [B,C,h,w] to [B,C,H,W]
+ *   (never materialised); feat_pseudo = argmax_c W; kept = pseudo if pseudo == feat_pseudo else 255.
+ *   feat_pseudo may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, int64_t B, int64_t C,
+                          int64_t h, int64_t w, int64_t H, int64_t W, int64_t* kept, int64_t* feat_pseudo,
+                          diga_stream_t stream);
+
+/* The interpolation routine shared by a4 and the fused a3 variant, materialising:
+ * out[planes,H,W] = bilinear(align_corners=True) of in[planes,h,w], bit-identical to torch's CUDA kernel. */
+int diga_upsample_bilinear(const float* in, int64_t planes, int64_t h, int64_t w, int64_t H, int64_t W, float* out,
+                           diga_stream_t stream);
+
+/* (f)-next row 1: pseudo-label straight from the stride-8 logits, both bilinear up-samplings fused
+ * (pseudolabel_generator.py:77-85).  logits: [n,C,h1,w1], logits_ds: [n,C,h2,w2] or NULL. */
+int diga_pseudo_label_upsampled(const float* logits, int64_t h1, int64_t w1, const float* logits_ds, int64_t h2,
+                                int64_t w2, int64_t n, int64_t C, int64_t H, int64_t W, uint8_t* label_u8,
+                                int64_t* label_i64, float* conf, diga_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIGA_B200_H_ */

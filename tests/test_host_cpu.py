@@ -1,0 +1,143 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header declares, host logic
+(class choice, sharding, the multi-rank centroid reduction under gloo) and the product/oracle separation."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "diga_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(diga_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from diga_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/diga_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert lib.diga_version() >= 100
+    assert _lib.launch_count() == 0
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Validation happens before any CUDA call, so bad arguments are reported even on a GPU-less host."""
+    from diga_b200 import _lib as L
+    assert L.lib.diga_kd_fwd(None, None, 2, 19, 16, 0.5, None, None, None) == -1
+    assert "null" in L.last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert L.lib.diga_kd_fwd(p, p, 3, 19, 1, 0.5, p, p, None) == -1 and "even" in L.last_error()
+    assert L.lib.diga_pseudo_label(p, None, 1, 40, 1, None, None, p, None) == -1
+    assert L.lib.diga_pseudo_label(p + 2, None, 1, 19, 1, None, None, p, None) == -2
+    assert L.lib.diga_centroid_update(p, p, None, 1, 19, 2, p, p, 7, 1, 1e-4, None) == -1
+    assert "no such updating way" in L.last_error()
+    with pytest.raises(RuntimeError):
+        L.check(-1)
+
+
+def test_wrappers_refuse_cpu_tensors():
+    import diga_b200 as D
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D.distillation_loss(torch.zeros(2, 19, 4, 4), torch.zeros(2, 19, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D.classmix(torch.zeros(1, 4, 4, dtype=torch.int64), torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
+    with pytest.raises(RuntimeError):
+        D.process_label(torch.zeros(1, 1, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "diga_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in txt, f"{f} reads the reference tree"
+
+
+def test_class_choice_matches_oracle_rng_stream():
+    from diga_b200.classmix import select_classes
+    from oracle import diga_oracle as O
+    g = torch.Generator().manual_seed(1)
+    sl = torch.randint(0, 19, (4, 16, 16), generator=g)
+    sl[1, :4] = 255
+    sl[3] = 255
+    present = [torch.unique(sl[i]).tolist() for i in range(4)]
+    assert select_classes(present, random.Random(9)) == O.classmix_select_classes(sl, random.Random(9))
+
+
+def test_shard_indices_partition():
+    from diga_b200.parallel import shard_indices
+    for world in (1, 2, 4, 8):
+        parts = [shard_indices(2975, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(2975))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_feature_hw_matches_survey():
+    from diga_b200.synthetic import feature_hw
+    assert feature_hw(256, 512) == (33, 65)
+    assert feature_hw(512, 896) == (65, 113)
+    assert feature_hw(512, 1024) == (65, 129)
+    assert feature_hw(1024, 2048) == (129, 257)
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from diga_b200.parallel import shard_indices, new_mean_accumulator, finish_mean_pass
+from oracle import diga_oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+C, Dm, n_img = 19, 24, 14
+g = torch.Generator().manual_seed(0)
+feats = [torch.randn((1, Dm, 9, 11), generator=g) for _ in range(n_img)]
+outs = [3 * torch.randn((1, C, 9, 11), generator=g) for _ in range(n_img)]
+for o in outs: o[:, :6] += 3
+# every rank: the per-image vectors of its own shard (CPU oracle stands in for the kernels, host logic under test)
+acc = new_mean_accumulator(C, Dm, "cpu")
+cf = O.ClassFeaturesOracle(C, Dm)
+for i in shard_indices(n_img, rank, world):
+    vec, ids = cf.calculate_mean_vector(feats[i], outs[i])
+    for v, c in zip(vec, ids):
+        if v.sum().item() != 0:
+            acc[c, :Dm] += v.reshape(-1); acc[c, Dm] += 1
+vectors, num = finish_mean_pass(acc)
+ref = O.centroid_pass(feats, outs, C, Dm)            # single-rank sequential reference over the union
+err = (vectors - ref.objective_vectors).abs().max().item()
+scale = ref.objective_vectors.abs().max().item()
+assert err <= 1e-5 * scale, (err, scale)
+assert torch.equal(num, ref.objective_vectors_num), (num, ref.objective_vectors_num)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_mean_pass_allreduce_world2_gloo(tmp_path):
+    """N ranks over disjoint image shards + one all-reduce == the sequential single-rank running mean."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = 29500 + (os.getpid() % 400)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert "ok" in out
