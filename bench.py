@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""Benchmark of the per-pixel adaptation hot path (BASELINE.json metric: pixels/sec, % of HBM peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Step  = one pass of the hot path over one batch of synthetic input.  The headline workload is BASELINE
+config 2 (configs[1]): symmetric-KD loss forward + backward on Cityscapes-shaped logits
+[8,19,512,1024] (two views x batch 4) per GPU, called through the drop-in ``distillation_loss`` +
+autograd.  ``value`` = pixel-positions/s over all ranks with inputs resident in HBM; ``e2e`` = the same
+call with HOST (pinned) inputs, H2D copies and the D2H read of the loss inside the timed region.
+``roofline`` is the dominant kernel (KD backward, 228 B/px) timed with CUDA events inside the timed region.
+``stages`` carries the other §8 rows (pseudo-label, selection, ClassMix, centroids, distance) measured in the
+same run; ``cpu_baseline`` is the oracle port timed on this box's host cores on a bounded sample.
+
+Multi-GPU: images shard across ranks with no data-path collective for a1-a5 (weak scaling); the centroid
+stage ends in the one real exchange, an NCCL all-reduce of the [19, D+1] buffer.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+C = 19
+KD_SHAPE = (8, C, 512, 1024)          # config 2: B=4 per view
+KD_BYTES_FWD = 2 * C * 4              # teacher + student read
+KD_BYTES_BWD = 3 * C * 4              # teacher + student read, dstudent written
+UPSTREAM = 0.25
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, 10 ms period)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def max_over_ranks(x: float, world: int, device) -> float:
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_loop(fn, iters, warmup, world=1, device=None):
+    """CUDA-event timing of ``iters`` calls, barrier + synchronize on both sides, max over ranks -> ms per call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, device) / iters
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_kd_step(t, s, g):
+    from oracle import diga_oracle as O
+    s = s.detach().requires_grad_(True)
+    loss = O.distillation_loss(t, s, 0.5)
+    (grad,) = torch.autograd.grad(loss, s, grad_outputs=g)
+    return loss, grad
+
+
+def cpu_kd_inputs(n2):
+    gen = torch.Generator().manual_seed(1234)
+    shape = (n2,) + KD_SHAPE[1:]
+    return 3.0 * torch.randn(shape, generator=gen), 3.0 * torch.randn(shape, generator=gen), torch.tensor(UPSTREAM)
+
+
+def cpu_baseline(budget_s=20.0):
+    """Oracle port of config 2 on the host cores: bounded sample (about ``budget_s`` seconds of CPU work)."""
+    threads = torch.get_num_threads()
+    t, s, g = cpu_kd_inputs(2)
+    t0 = time.perf_counter()
+    cpu_kd_step(t, s, g)
+    probe = time.perf_counter() - t0                      # [2,19,512,1024] incl. first-touch
+    n2 = 8 if probe * 4 * 3 <= budget_s else (4 if probe * 2 * 3 <= budget_s else 2)
+    if n2 != 2:
+        t, s, g = cpu_kd_inputs(n2)
+        cpu_kd_step(t, s, g)
+    best = float("inf")
+    reps = 0
+    t_end = time.perf_counter() + budget_s
+    while reps < 3 or (time.perf_counter() < t_end and reps < 10):
+        t0 = time.perf_counter()
+        cpu_kd_step(t, s, g)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    px = n2 * KD_SHAPE[2] * KD_SHAPE[3]
+    return {"value": px / best, "unit": "pixel-positions/s", "cores": threads, "kind": "port",
+            "sample": f"oracle (torch CPU op chain of util/loss.py:125-143 + autograd) on [{n2},19,512,1024], "
+                      f"best of {reps}, {threads} threads of {os.cpu_count()} logical cores"}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    threads = torch.get_num_threads()
+    t, s, g = cpu_kd_inputs(2)
+    t0 = time.perf_counter()
+    cpu_kd_step(t, s, g)
+    probe = time.perf_counter() - t0
+    total_steps = args.steps + args.warmup
+    n2 = 8
+    while n2 > 2 and probe * (n2 / 2) * total_steps > 150.0:
+        n2 //= 2
+    t, s, g = cpu_kd_inputs(n2)
+    for _ in range(args.warmup):
+        cpu_kd_step(t, s, g)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_kd_step(t, s, g)
+    dt = time.perf_counter() - t0
+    px = n2 * KD_SHAPE[2] * KD_SHAPE[3]
+    value = px * args.steps / dt
+    sample = (f"oracle port (torch CPU op chain of util/loss.py:125-143 + autograd) on [{n2},19,512,1024] per step, "
+              f"{threads} threads of {os.cpu_count()} logical cores")
+    line = {"impl": "reference", "metric": "pixels/sec (symmetric KD loss fwd+bwd)", "value": value,
+            "unit": "pixel-positions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config 2: symmetric KD fwd+bwd, logits [8,19,512,1024] (B=4 per view), fp32",
+                       "sample_shape": [n2, 19, 512, 1024]},
+            "cpu_baseline": {"value": value, "unit": "pixel-positions/s", "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "pixel-positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# secondary stages (the other rows of SURVEY.md §8), per rank
+# --------------------------------------------------------------------------------------------------
+def bench_stages(D, S, dev, peak, world, quick):
+    import random
+    from diga_b200 import parallel as P
+    g = S.gen(4321 + dist_env()[0], dev)
+    iters, warm = (10, 3) if quick else (30, 5)
+    out = {}
+
+    def add(name, px, bytes_per_px, ms, unit="px", extra=None):
+        gbs = px * bytes_per_px / (ms * 1e-3) / 1e9
+        out[name] = {"px_per_s": px / (ms * 1e-3) * world, "unit": f"{unit}/s (all ranks)", "ms": ms,
+                     "algo_bytes_per_px": bytes_per_px, "gbs_per_gpu": gbs, "frac_hbm": gbs / peak}
+        if extra:
+            out[name].update(extra)
+
+    # a3 pseudo-label at 2048x1024, one and two scales (config 5 resolution), 4 images per call
+    n, hh, ww = 4, 1024, 2048
+    z = S.logits((n, C, hh, ww), g)
+    z2 = S.logits((n, C, hh, ww), g)
+    add("pseudo_label_1scale", n * hh * ww, 4 * C + 5, time_loop(lambda: D.pseudo_label(z), iters, warm, world, dev))
+    add("pseudo_label_2scale", n * hh * ww, 8 * C + 5, time_loop(lambda: D.pseudo_label(z, z2), iters, warm, world, dev))
+    del z, z2
+    # fused two-scale from stride-8 logits (next row f1): 5 B/px of HBM writes only
+    l1, l2 = S.logits((n, C, 129, 257), g), S.logits((n, C, 65, 129), g)
+    add("pseudo_label_fused_upsample", n * hh * ww, 5,
+        time_loop(lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww)), iters, warm, world, dev))
+
+    # config 3 pieces: B=8 @512x1024, features [8,2048,65,129]
+    b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
+    sl = S.block_labels(b, hh, ww, g)
+    tl = S.perturb_labels(sl, g)
+    xa, xb = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    rng = random.Random(1234)
+    add("classmix_dacs_total", b * hh * ww, 72,
+        time_loop(lambda: D.classmix(sl, xa, xb, tl, rng=rng, return_mask=False), iters, warm, world, dev),
+        extra={"note": "presence kernel (8 B/px) + host class choice + blend (64 B/px); includes the one D2H sync"})
+    from diga_b200.classmix import present_classes, select_classes
+    classes = select_classes(present_classes(sl), rng)
+    add("classmix_dacs_blend_kernel", b * hh * ww, 60,
+        time_loop(lambda: D.classmix(sl, xa, xb, tl, classes=classes, return_mask=False), iters, warm, world, dev))
+    del xa, xb
+
+    feat = S.features((b, d, h, w), g)
+    cf = D.Class_Features(C, d)
+    cf.objective_vectors = S.centroids(C, d, g)
+    add("proto_distance_softmax_d2048", b * h * w, d * 4 + C * 4,
+        time_loop(lambda: cf.get_centroid_weight(feat), iters, warm, world, dev), unit="feature-px")
+    wl = cf.get_centroid_weight(feat)
+    add("consensus_select", b * hh * ww, 24, time_loop(lambda: D.consensus_select(tl, wl), iters, warm, world, dev))
+
+    logits_lo = S.logits((b, C, h, w), g)
+    ms = time_loop(lambda: cf.update_from_features(feat, logits_lo, None, "mean"), iters, warm, world, dev)
+    add("centroid_accumulate_update_d2048", b * h * w, d * 4 + C * 4 + 1, ms, unit="feature-px",
+        extra={"images_per_s": b / (ms * 1e-3) * world})
+
+    # config 4 shape of the exchange: mean pass + ONE all-reduce of [19, D+1] (NCCL over NVLink when world > 1)
+    acc = P.new_mean_accumulator(C, d, dev)
+
+    def mean_pass():
+        acc.zero_()
+        cf.accumulate_mean_pass(acc, feat, logits_lo)
+        return P.finish_mean_pass(acc)
+
+    ms = time_loop(mean_pass, iters, warm, world, dev)
+    add("centroid_mean_pass_allreduce_d2048", b * h * w, d * 4 + C * 4 + 1, ms, unit="feature-px",
+        extra={"images_per_s": b / (ms * 1e-3) * world, "allreduce_bytes": C * (d + 1) * 4})
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# main arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="diga_b200", choices=["diga_b200", "reference"])
+    ap.add_argument("--no-stages", action="store_true", help="skip the secondary stage measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank, local_rank, world = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import diga_b200 as D
+    from diga_b200 import _lib as L, synthetic as S
+
+    peak, peak_src = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+    n2, _, hh, ww = KD_SHAPE
+    px_step = n2 * hh * ww
+    g = S.gen(1234 + rank, dev)
+    # three rotating input sets (each 638 MB, far beyond the 126 MB L2) so no step re-reads cached lines
+    sets = [(S.logits(KD_SHAPE, g), S.logits(KD_SHAPE, g)) for _ in range(3)]
+    up = torch.tensor(UPSTREAM, device=dev)
+
+    def step(i, ev=None):
+        t, s = sets[i % len(sets)]
+        s = s.detach().requires_grad_(True)
+        if ev:
+            ev[0].record()
+        loss = D.distillation_loss(t, s, 0.5)
+        if ev:
+            ev[1].record()
+        (grad,) = torch.autograd.grad(loss, s, grad_outputs=up)
+        if ev:
+            ev[2].record()
+        return loss, grad
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = L.launch_count()
+    barrier(world)
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step(i, events[i])
+        e1.record()
+        torch.cuda.synchronize()
+    barrier(world)
+    launches = L.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    ms_step = ms_total / K
+    value = world * px_step / (ms_step * 1e-3)
+    fwd_ms = statistics.mean(ev[0].elapsed_time(ev[1]) for ev in events)
+    bwd_ms = statistics.mean(ev[1].elapsed_time(ev[2]) for ev in events)
+    bwd_gbs = px_step * KD_BYTES_BWD / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = px_step * KD_BYTES_FWD / (fwd_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("kd_bwd_dram_bytes_per_launch")
+
+    # fused single-pass variant (228 B/px), same inputs
+    fused_ms = time_loop(lambda: D.distillation_loss_and_grad(sets[0][0], sets[0][1], 0.5, UPSTREAM), 20, 3, world, dev)
+
+    # ---- end to end: host (pinned) inputs -> H2D -> distillation_loss + backward -> D2H loss -----------------
+    e2e = None
+    if not args.no_e2e:
+        ke = max(3, min(K, 30))
+        host_t = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
+        host_s = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
+        host_t.copy_(sets[0][0])
+        host_s.copy_(sets[0][1])
+        host_loss = torch.empty((ke + 3,), dtype=torch.float32).pin_memory()
+        bufs = [(torch.empty(KD_SHAPE, device=dev), torch.empty(KD_SHAPE, device=dev)) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        main_stream = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_run(nsteps):
+            for f in freed:
+                f.record(main_stream)
+            for i in range(nsteps):
+                j = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[j])               # buffer j no longer read by step i-2
+                    bufs[j][0].copy_(host_t, non_blocking=True)
+                    bufs[j][1].copy_(host_s, non_blocking=True)
+                    ready[j].record(copy_stream)
+                main_stream.wait_event(ready[j])
+                s = bufs[j][1].detach().requires_grad_(True)
+                loss = D.distillation_loss(bufs[j][0], s, 0.5)
+                (grad,) = torch.autograd.grad(loss, s, grad_outputs=up)
+                host_loss[i].copy_(loss.detach(), non_blocking=True)   # the step's result, read back to the host
+                freed[j].record(main_stream)
+
+        e2e_run(3)
+        torch.cuda.synchronize()
+        barrier(world)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        e2e_run(ke)
+        a1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        e2e_ms = max_over_ranks(a0.elapsed_time(a1), world, dev) / ke
+        e2e = {"value": world * px_step / (e2e_ms * 1e-3), "unit": "pixel-positions/s",
+               "h2d_bytes_per_step": 2 * host_t.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+               "steps": ke, "note": "pinned host logits -> H2D (double-buffered on a copy stream) -> "
+                                    "distillation_loss + autograd.grad -> D2H loss; gradient stays on the device "
+                                    "for the backbone backward; PCIe-bound"}
+        del host_t, host_s, bufs
+
+    stages = None
+    if not args.no_stages:
+        del sets
+        torch.cuda.empty_cache()
+        stages = bench_stages(D, S, dev, peak, world, quick=(K < 50))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": "pixels/sec (symmetric KD loss fwd+bwd)", "value": value, "unit": "pixel-positions/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config 2: symmetric KD fwd+bwd, logits [8,19,512,1024] (B=4 per view) per GPU, "
+                                   "distillation_loss + autograd (fwd 152 B/px + bwd 228 B/px)",
+                       "shape": list(KD_SHAPE), "pixel_positions_per_step_per_gpu": px_step,
+                       "l2": "inputs 638 MB per step exceed the 126 MB L2; 3 rotating input sets",
+                       "parallelism": f"image-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "kd_kernel<GRAD> (backward)", "achieved": bwd_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algo_bytes_per_launch": px_step * KD_BYTES_BWD, "avg_launch_ms": bwd_ms,
+                         "frac_of_8000_spec": bwd_gbs / 8000.0},
+            "kernels": {"kd_fwd": {"ms": fwd_ms, "gbs": fwd_gbs, "frac": fwd_gbs / peak, "algo_bytes_per_px": KD_BYTES_FWD,
+                                   "note": "event pair brackets the Python autograd.Function call"},
+                        "kd_bwd": {"ms": bwd_ms, "gbs": bwd_gbs, "frac": bwd_gbs / peak, "algo_bytes_per_px": KD_BYTES_BWD},
+                        "kd_fused_fwd_bwd": {"ms": fused_ms, "gbs": px_step * KD_BYTES_BWD / (fused_ms * 1e-3) / 1e9,
+                                             "frac": px_step * KD_BYTES_BWD / (fused_ms * 1e-3) / 1e9 / peak,
+                                             "px_per_s": world * px_step / (fused_ms * 1e-3),
+                                             "note": "distillation_loss_and_grad: loss + gradient in one 228 B/px pass"}},
+            "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "stages": stages, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -344,11 +344,11 @@ int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_
   cudaStream_t st = (cudaStream_t)stream;
   const int variant = tunable("accum_variant", 0);
   switch (variant) {
-    case 1: return launch_accum<4, 4, 4>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 1: return launch_accum<4, 8, 4>(feat, cls, (int)C, n, D, hw, sums, st);
     case 2: return launch_accum<2, 8, 4>(feat, cls, (int)C, n, D, hw, sums, st);
     case 3: return launch_accum<4, 8, 2>(feat, cls, (int)C, n, D, hw, sums, st);
     case 4: return launch_accum<2, 4, 8>(feat, cls, (int)C, n, D, hw, sums, st);
-    default: return launch_accum<4, 8, 4>(feat, cls, (int)C, n, D, hw, sums, st);
+    default: return launch_accum<4, 4, 4>(feat, cls, (int)C, n, D, hw, sums, st);
   }
 }
 

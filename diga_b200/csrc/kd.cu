@@ -141,7 +141,10 @@ static int launch_kd(const float* tea, const float* stu, float* dstu, int nclass
   }
   const int64_t total = 2 * B * (hw / VEC);
   int64_t grid = (total + BLOCK - 1) / BLOCK;
-  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * tunable("kd_waves", 1);
+  // Grid = resident CTAs x waves.  Measured on B200 (tools/tune.py, profiles/tune_r01.md): the read-only forward
+  // is fastest as one persistent wave (1.00 of the copy peak); the kernels that also write 76 B/px want ~8 waves
+  // of shorter-lived CTAs (0.94 -> 1.00).
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * tunable(GRAD ? "kd_waves_bwd" : "kd_waves_fwd", GRAD ? 8 : 1);
   if (grid > cap) grid = cap;
   if (grid > kKdMaxPartials) grid = kKdMaxPartials;
   if (grid < 1) grid = 1;
@@ -168,7 +171,7 @@ static int dispatch_kd(const float* tea, const float* stu, float* dstu, int64_t 
   int vec = tunable("kd_vec", 2);
   const bool a8 = aligned(tea, 8) && aligned(stu, 8) && (!GRAD || aligned(dstu, 8));
   if (vec != 1 && !((hw % 2) == 0 && a8)) vec = 1;
-  const int block = tunable("kd_block", 256);
+  const int block = tunable("kd_block", (LOSS && GRAD) ? 128 : 256);
   KdWorkspace* ws = reinterpret_cast<KdWorkspace*>(workspace);
 #define DIGA_KD_GO(V, BL) \
   return launch_kd<kC, kPad, V, BL, LOSS, GRAD>(tea, stu, dstu, (int)C, B, hw, scale, up_dev, up_host, loss_out, ws, st)

@@ -108,7 +108,7 @@ static int launch_pl(const float* z1, const float* z2, int nclass, int64_t n, in
   }
   const int64_t total = n * (hw / VEC);
   int64_t grid = (total + BLOCK - 1) / BLOCK;
-  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * tunable("pl_waves", 1);
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * (HAS2 ? tunable("pl_waves2", 8) : tunable("pl_waves", 2));
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, BLOCK, 0, st>>>(z1, z2, nclass, n, hw, lab8, lab64, conf);

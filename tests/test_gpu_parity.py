@@ -39,6 +39,15 @@ def assert_normwise(got, want, rtol=RTOL, what=""):
     assert err <= rtol * max(scale, 1e-30), f"{what}: max|diff| {err:.3e} > {rtol} * max|ref| {scale:.3e}"
 
 
+def assert_same_bits(got, want, what=""):
+    """Bit-exact fp32 comparison (distinguishes -0.0 from 0.0); NaNs must coincide, their payload may differ
+    (x86 produces the negative quiet NaN for inf*0, the GPU the canonical 0x7fffffff)."""
+    got, want = np.asarray(got, dtype=np.float32), np.asarray(want, dtype=np.float32)
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w), f"{what}: NaN positions differ"
+    assert np.array_equal(got.view(np.uint32)[~nan_g], want.view(np.uint32)[~nan_w]), f"{what}: bits differ"
+
+
 def assert_rel(got, want, rtol=RTOL, what=""):
     got, want = float(got), float(want)
     assert abs(got - want) <= rtol * abs(want), f"{what}: {got!r} vs {want!r}"
@@ -247,7 +256,8 @@ def test_classmix_vs_oracle(D, b, h, w, block):
     mo, xo, lo = O.classmix(sl, a, bb, tl, rng=random.Random(5))
     mg, xg, lg = D.classmix(sl.to(dev()), a.to(dev()), bb.to(dev()), tl.to(dev()), rng=random.Random(5))
     assert torch.equal(mg.cpu(), mo)
-    assert np.array_equal(xg.cpu().numpy().view(np.uint32), xo.numpy().view(np.uint32))
+    assert_same_bits(xg.cpu().numpy(), xo.numpy(), "mix")
+    assert bool(torch.isnan(xg[0, 0, 0, 0]))            # inf * 0 propagates exactly as in the reference
     assert torch.equal(lg.cpu(), lo)
     # presence bitmap == torch.unique
     from diga_b200.classmix import present_classes
@@ -415,7 +425,16 @@ def test_proto_vs_oracle(D, n, d, h, w, c):
     d64 = d64.reshape(n, h, w, c).permute(0, 3, 1, 2)
     assert_normwise(dist_g, d64, what="dist vs fp64")
     assert_normwise(dist_g, dist_o, what="dist vs reference chain")
-    assert_normwise(w_g, w_o, what="weight")
+    # weight = softmax(-dist): d w = w * d(dist) (absolute), so a distance held to 1e-5 RELATIVE moves a weight by up
+    # to 1e-5 * max(dist) relative.  That conditioning bound is the bar (at D=2048, dist ~ 64, two fp32 evaluations of
+    # the reference's own formula already differ by more than 1e-5 * max|w|); on top, the kernel must be no further
+    # from the fp64 truth than a small multiple of the reference chain's own fp32 error.
+    w64 = torch.softmax(-d64, dim=1)
+    err_g = (w_g.double() - w64).abs().max().item()
+    err_o = (w_o.double() - w64).abs().max().item()
+    tol = 1e-5 * d64.max().item() * w64.max().item()
+    assert err_g <= tol, f"weight error {err_g:.3e} exceeds the conditioning bound {tol:.3e}"
+    assert err_g <= 4 * err_o + 1e-7, f"weight error {err_g:.3e} vs reference chain's own {err_o:.3e}"
     mism = dist_g.argmin(1) != d64.argmin(1)
     if mism.any():
         top2 = d64.topk(2, dim=1, largest=False).values

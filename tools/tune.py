@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Launch-shape sweep on the GPU: times each hot kernel for every tunable combination with CUDA events and prints
+one JSON line per measurement (gpurun_out/tune.jsonl).  Defaults in csrc/*.cu are set from these sweeps."""
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import diga_b200 as D  # noqa: E402
+from diga_b200 import _lib as L, synthetic as S  # noqa: E402
+
+dev = torch.device("cuda", 0)
+PEAK = 6530.3
+out_path = os.path.join(ROOT, "gpurun_out", "tune.jsonl")
+os.makedirs(os.path.dirname(out_path), exist_ok=True)
+fout = open(out_path, "a")
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(kernel, cfg, ms, nbytes):
+    rec = {"kernel": kernel, **cfg, "ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / PEAK, 3)}
+    print(json.dumps(rec), flush=True)
+    fout.write(json.dumps(rec) + "\n")
+    fout.flush()
+
+
+def sweep_kd():
+    g = S.gen(1, dev)
+    shape = (8, 19, 512, 1024)
+    sets = [(S.logits(shape, g), S.logits(shape, g)) for _ in range(2)]
+    px = 8 * 512 * 1024
+    ws = L.kd_workspace(dev)
+    loss = torch.empty((), device=dev)
+    ds = torch.empty(shape, device=dev)
+    up = torch.tensor(0.25, device=dev)
+    k = [0]
+
+    def fwd():
+        t, s = sets[k[0] % 2]; k[0] += 1
+        L.check(L.lib.diga_kd_fwd(t.data_ptr(), s.data_ptr(), 8, 19, 512 * 1024, 0.5, loss.data_ptr(), ws.data_ptr(), L.stream()))
+
+    def bwd():
+        t, s = sets[k[0] % 2]; k[0] += 1
+        L.check(L.lib.diga_kd_bwd(t.data_ptr(), s.data_ptr(), 8, 19, 512 * 1024, 0.5, up.data_ptr(), ds.data_ptr(), L.stream()))
+
+    def both():
+        t, s = sets[k[0] % 2]; k[0] += 1
+        L.check(L.lib.diga_kd_fwd_bwd(t.data_ptr(), s.data_ptr(), 8, 19, 512 * 1024, 0.5, 0.25, loss.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
+
+    for vec, block, waves in itertools.product((2, 1), (256, 128), (1, 2, 4, 8)):
+        L.set_tunable("kd_vec", vec); L.set_tunable("kd_block", block); L.set_tunable("kd_waves_fwd", waves); L.set_tunable("kd_waves_bwd", waves)
+        cfg = {"vec": vec, "block": block, "waves": waves}
+        report("kd_fwd", cfg, timeit(fwd), px * 152)
+        report("kd_bwd", cfg, timeit(bwd), px * 228)
+        report("kd_fwd_bwd", cfg, timeit(both), px * 228)
+    L.set_tunable("kd_vec", 2); L.set_tunable("kd_block", 256); L.set_tunable("kd_waves_fwd", 1); L.set_tunable("kd_waves_bwd", 8)
+
+
+def sweep_pl():
+    g = S.gen(2, dev)
+    n, hh, ww = 4, 1024, 2048
+    z, z2 = S.logits((n, 19, hh, ww), g), S.logits((n, 19, hh, ww), g)
+    px = n * hh * ww
+    for vec, waves in itertools.product((4, 2, 1), (1, 2, 4, 8)):
+        L.set_tunable("pl_vec", vec); L.set_tunable("pl_vec2", vec); L.set_tunable("pl_waves", waves); L.set_tunable("pl_waves2", waves)
+        cfg = {"vec": vec, "waves": waves}
+        report("pseudo_label_1", cfg, timeit(lambda: D.pseudo_label(z)), px * 81)
+        report("pseudo_label_2", cfg, timeit(lambda: D.pseudo_label(z, z2)), px * 157)
+    L.set_tunable("pl_vec", 4); L.set_tunable("pl_vec2", 2); L.set_tunable("pl_waves", 2); L.set_tunable("pl_waves2", 8)
+
+
+def sweep_accum():
+    g = S.gen(3, dev)
+    for (n, d, h, w) in ((8, 2048, 65, 129), (1, 2048, 65, 129), (8, 256, 65, 129), (8, 2048, 64, 128)):
+        feat = S.features((n, d, h, w), g)
+        cls = torch.randint(0, 19, (n, h * w), device=dev, dtype=torch.uint8)
+        sums = torch.empty((n, 19, d), device=dev)
+        for variant in range(5):
+            L.set_tunable("accum_variant", variant)
+            ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
+            report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "random"}, ms, feat.numel() * 4)
+        cls2 = (torch.arange(h * w, device=dev) // 200 % 19).to(torch.uint8).repeat(n, 1).contiguous()
+        L.set_tunable("accum_variant", 0)
+        ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls2.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
+        report("centroid_accum", {"variant": 0, "shape": [n, d, h, w], "labels": "runs of 200"}, ms, feat.numel() * 4)
+    L.set_tunable("accum_variant", 0)
+
+
+def sweep_cm():
+    import random
+    g = S.gen(4, dev)
+    b, hh, ww = 8, 512, 1024
+    sl = S.block_labels(b, hh, ww, g); tl = S.perturb_labels(sl, g)
+    xa, xb = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    from diga_b200.classmix import present_classes, select_classes
+    classes = select_classes(present_classes(sl), random.Random(1))
+    px = b * hh * ww
+    for vec, waves in itertools.product((4, 2, 1), (1, 2, 4)):
+        L.set_tunable("cm_vec", vec); L.set_tunable("cm_waves", waves)
+        report("classmix_blend_dacs", {"vec": vec, "waves": waves},
+               timeit(lambda: D.classmix(sl, xa, xb, tl, classes=classes, return_mask=False)), px * 60)
+    L.set_tunable("cm_vec", 4); L.set_tunable("cm_waves", 1)
+    bm = torch.empty((b, 8), dtype=torch.int32, device=dev); fl = torch.empty(1, dtype=torch.int32, device=dev)
+    report("class_presence", {}, timeit(lambda: L.check(L.lib.diga_class_presence(sl.data_ptr(), b, hh * ww, bm.data_ptr(), fl.data_ptr(), L.stream()))), px * 8)
+
+
+def sweep_misc():
+    g = S.gen(5, dev)
+    b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
+    feat = S.features((b, d, h, w), g)
+    cf = D.Class_Features(19, d); cf.objective_vectors = S.centroids(19, d, g)
+    report("proto_distance_fp32", {"shape": [b, d, h, w]}, timeit(lambda: cf.get_centroid_weight(feat)), feat.numel() * 4)
+    wl = cf.get_centroid_weight(feat)
+    tl = S.block_labels(b, hh, ww, g)
+    report("consensus_select", {}, timeit(lambda: D.consensus_select(tl, wl)), b * hh * ww * 24)
+    l1, l2 = S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g)
+    report("pseudo_label_fused_upsample", {}, timeit(lambda: D.pseudo_label_two_scale(l1, l2, (1024, 2048))), 4 * 1024 * 2048 * 5)
+    # reference-point: torch copy bandwidth on this box
+    a = torch.empty(1 << 28, device=dev); bb = torch.empty_like(a)
+    report("torch_copy_1GiB", {}, timeit(lambda: bb.copy_(a)), a.numel() * 8)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["kd", "pl", "accum", "cm", "misc"]
+    for name in which:
+        globals()["sweep_" + name]()
