@@ -66,7 +66,6 @@ def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=T
     lut_host = np.zeros((bsz, 256), dtype=np.uint8)
     for i, sel in enumerate(classes):
         lut_host[i, [c for c in sel if 0 <= c <= 255]] = 1
-    lut = torch.from_numpy(lut_host).to(lab.device, non_blocking=True)
     hw = lab[0].numel() if bsz else 0
     fa, fb = L.f32c(a), L.f32c(b)
     if fa.shape != fb.shape or fa.shape[0] != bsz or fa[0, 0].numel() != hw:
@@ -81,7 +80,7 @@ def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=T
     if tlabel is not None:
         tl = L.i64c(tlabel)
         mixlabel = torch.empty_like(tl)
-    L.check(L.lib.diga_classmix_blend(lab.data_ptr(), lut.data_ptr(), L.ptr(fa), L.ptr(fb), L.ptr(tl), bsz, fa.shape[1],
+    L.check(L.lib.diga_classmix_blend(lab.data_ptr(), lut_host.ctypes.data, L.ptr(fa), L.ptr(fb), L.ptr(tl), bsz, fa.shape[1],
                                       hw, L.ptr(mask), L.ptr(mix), L.ptr(mixlabel), L.stream()))
     if tlabel is None:
         return mask, mix

@@ -43,4 +43,51 @@ __device__ __forceinline__ float bilinear_col(const Tap& ty, float top, float bo
   return __fmaf_rn(ty.l0, top, __fmul_rn(ty.l1, bottom));
 }
 
+// Vertical-run evaluator.  A thread that walks down a column of output pixels keeps, for every class, the two
+// horizontally interpolated source rows (`top`, `bot`) of the current source cell in registers.  Moving to the
+// next output row inside the same cell costs one FMUL + FFMA per class; crossing into the next cell re-uses `bot`
+// as the new `top` (same inputs, same expression => bit-identical) and interpolates one new source row.  The
+// values are exactly those of ATen's per-pixel expression (common sub-expressions are merely not recomputed).
+template <int C, bool PAD, int PX>
+struct ColumnInterp {
+  float top[PX][C], bot[PX][C];
+  int i0 = -1, i1 = -1;
+
+  __device__ __forceinline__ void row(float (&dst)[PX][C], const float* __restrict__ base, int64_t plane, int w, int r,
+                                      const Tap (&tx)[PX], int nclass) {
+    const float* q = base + (int64_t)r * w;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
+#pragma unroll
+        for (int v = 0; v < PX; ++v) dst[v][c] = bilinear_row(tx[v], __ldg(q + c * plane + tx[v].i0), __ldg(q + c * plane + tx[v].i1));
+      }
+  }
+
+  __device__ __forceinline__ void seek(const Tap& ty, const float* __restrict__ base, int64_t plane, int w, const Tap (&tx)[PX],
+                                       int nclass) {
+    if (ty.i0 == i0 && ty.i1 == i1) return;
+    if (ty.i0 == i1 && i1 >= 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int v = 0; v < PX; ++v) top[v][c] = bot[v][c];
+    } else if (ty.i0 != i0) {
+      row(top, base, plane, w, ty.i0, tx, nclass);
+    }
+    if (ty.i1 == ty.i0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int v = 0; v < PX; ++v) bot[v][c] = top[v][c];
+    } else {
+      row(bot, base, plane, w, ty.i1, tx, nclass);
+    }
+    i0 = ty.i0;
+    i1 = ty.i1;
+  }
+
+  __device__ __forceinline__ float value(const Tap& ty, int v, int c) const { return bilinear_col(ty, top[v][c], bot[v][c]); }
+};
+
 }  // namespace diga

@@ -72,7 +72,46 @@ template <int R> struct AccT;
 template <> struct AccT<4> { using type = float4; };
 template <> struct AccT<2> { using type = float2; };
 
+// One batch = U pixel stripes x R rows of loads, all issued before any is consumed.
+template <int R, int U>
+struct AccumBatch {
+  float x[U][R];
+  int cid[U];
+};
+
 template <int R, int WARPS, int U>
+__device__ __forceinline__ void accum_load(AccumBatch<R, U>& b, const float* const (&rows)[R], const uint8_t* cl, int64_t base,
+                                           int64_t hw) {
+  constexpr int STRIPE = WARPS * 32;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t p = base + (int64_t)u * STRIPE;
+    const bool ok = p < hw;
+    b.cid[u] = ok ? (int)__ldg(cl + p) : 255;
+#pragma unroll
+    for (int r = 0; r < R; ++r) b.x[u][r] = ok ? ld_stream<1>(rows[r] + p).v[0] : 0.f;
+  }
+}
+
+template <int R, int U, typename acc_t>
+__device__ __forceinline__ void accum_apply(const AccumBatch<R, U>& b, acc_t* my, int nclass) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (b.cid[u] < nclass) {
+      acc_t v = my[b.cid[u] * 32];
+      if constexpr (R == 4) {
+        v.x += b.x[u][0]; v.y += b.x[u][1]; v.z += b.x[u][2]; v.w += b.x[u][3];
+      } else {
+        v.x += b.x[u][0]; v.y += b.x[u][1];
+      }
+      my[b.cid[u] * 32] = v;
+    }
+  }
+}
+
+// PIPE: software pipelining — the loads of batch i+1 are issued before the shared-memory updates of batch i, so a
+// warp keeps R*U..2*R*U 32-bit loads in flight instead of draining to zero every iteration.
+template <int R, int WARPS, int U, bool PIPE>
 __global__ void __launch_bounds__(WARPS * 32)
 centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ cls, int nclass, int64_t n, int64_t D,
                       int64_t hw, float* __restrict__ sums) {
@@ -83,6 +122,7 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
   const int64_t groups = (D + R - 1) / R;
   const int64_t items = n * groups;
   acc_t* my = acc + (size_t)warp * nclass * 32 + lane;
+  constexpr int64_t STEP = (int64_t)WARPS * 32 * U;
 
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int64_t img = item / groups;
@@ -95,34 +135,26 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
       row_ok[r] = d0 + r < D;
       rows[r] = feat + (img * D + (row_ok[r] ? d0 + r : d0)) * hw;
     }
+    const int64_t first = warp * 32 + lane;
+    AccumBatch<R, U> a, b;
+    accum_load<R, WARPS, U>(a, rows, cl, first, hw);          // in flight while the accumulators are cleared
     acc_t zero;
     if constexpr (R == 4) zero = make_float4(0.f, 0.f, 0.f, 0.f); else zero = make_float2(0.f, 0.f);
     for (int c = 0; c < nclass; ++c) my[c * 32] = zero;
     // (own lane-private cells only: no barrier needed before the main loop)
 
-    constexpr int STRIPE = WARPS * 32;
-    for (int64_t base = warp * 32 + lane; base < hw; base += (int64_t)STRIPE * U) {
-      float x[U][R];
-      int cid[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t p = base + (int64_t)u * STRIPE;
-        const bool ok = p < hw;
-        cid[u] = ok ? (int)__ldg(cl + p) : 255;
-#pragma unroll
-        for (int r = 0; r < R; ++r) x[u][r] = ok ? ld_stream<1>(rows[r] + p).v[0] : 0.f;
+    if constexpr (PIPE) {
+      // bases are warp-uniform up to +lane, so the loop trip count is uniform within a warp
+      for (int64_t base = first; base - lane < hw; base += 2 * STEP) {
+        accum_load<R, WARPS, U>(b, rows, cl, base + STEP, hw);
+        accum_apply<R, U>(a, my, nclass);
+        accum_load<R, WARPS, U>(a, rows, cl, base + 2 * STEP, hw);
+        accum_apply<R, U>(b, my, nclass);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (cid[u] < nclass) {
-          acc_t v = my[cid[u] * 32];
-          if constexpr (R == 4) {
-            v.x += x[u][0]; v.y += x[u][1]; v.z += x[u][2]; v.w += x[u][3];
-          } else {
-            v.x += x[u][0]; v.y += x[u][1];
-          }
-          my[cid[u] * 32] = v;
-        }
+    } else {
+      for (int64_t base = first; base - lane < hw; base += STEP) {
+        accum_apply<R, U>(a, my, nclass);
+        accum_load<R, WARPS, U>(a, rows, cl, base + STEP, hw);
       }
     }
     __syncthreads();
@@ -153,10 +185,10 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
   }
 }
 
-template <int R, int WARPS, int U>
+template <int R, int WARPS, int U, bool PIPE>
 static int launch_accum(const float* feat, const uint8_t* cls, int nclass, int64_t n, int64_t D, int64_t hw, float* sums,
                         cudaStream_t st) {
-  auto kern = centroid_accum_kernel<R, WARPS, U>;
+  auto kern = centroid_accum_kernel<R, WARPS, U, PIPE>;
   const size_t smem = (size_t)WARPS * nclass * 32 * sizeof(typename AccT<R>::type);
   static size_t configured = 0;
   static int blocks_per_sm = 0;
@@ -344,11 +376,14 @@ int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_
   cudaStream_t st = (cudaStream_t)stream;
   const int variant = tunable("accum_variant", 0);
   switch (variant) {
-    case 1: return launch_accum<4, 8, 4>(feat, cls, (int)C, n, D, hw, sums, st);
-    case 2: return launch_accum<2, 8, 4>(feat, cls, (int)C, n, D, hw, sums, st);
-    case 3: return launch_accum<4, 8, 2>(feat, cls, (int)C, n, D, hw, sums, st);
-    case 4: return launch_accum<2, 4, 8>(feat, cls, (int)C, n, D, hw, sums, st);
-    default: return launch_accum<4, 4, 4>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 1: return launch_accum<4, 4, 4, false>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 2: return launch_accum<4, 4, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 3: return launch_accum<4, 8, 4, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 4: return launch_accum<2, 4, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 5: return launch_accum<4, 2, 4, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 6: return launch_accum<4, 2, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    case 7: return launch_accum<2, 8, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    default: return launch_accum<4, 4, 4, true>(feat, cls, (int)C, n, D, hw, sums, st);
   }
 }
 

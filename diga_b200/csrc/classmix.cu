@@ -62,14 +62,22 @@ __device__ __forceinline__ float blend(float a, float b, float m) {
   return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, m)), __fmul_rn(b, m));
 }
 
+// The per-image class selection travels as a kernel argument (256-bit bitmap per image, up to 16 images per
+// launch): no device-side LUT buffer, no H2D copy.
+constexpr int kBlendImagesPerLaunch = 16;
+struct BlendSelection {
+  uint32_t bits[kBlendImagesPerLaunch][8];
+};
+
 template <int VEC, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-classmix_blend_kernel(const int64_t* __restrict__ slabel, const uint8_t* __restrict__ lut, const float* __restrict__ a,
-                      const float* __restrict__ b, const int64_t* __restrict__ tlabel, int channels, int64_t hw,
-                      float* __restrict__ mask, float* __restrict__ mix, int64_t* __restrict__ mixlabel) {
+classmix_blend_kernel(const int64_t* __restrict__ slabel, const __grid_constant__ BlendSelection sel, int64_t img0,
+                      const float* __restrict__ a, const float* __restrict__ b, const int64_t* __restrict__ tlabel,
+                      int channels, int64_t hw, float* __restrict__ mask, float* __restrict__ mix,
+                      int64_t* __restrict__ mixlabel) {
   __shared__ uint8_t s_lut[256];
-  const int64_t img = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += BLOCK) s_lut[i] = lut[img * 256 + i];
+  const int64_t img = img0 + blockIdx.y;
+  for (int i = threadIdx.x; i < 256; i += BLOCK) s_lut[i] = (sel.bits[blockIdx.y][i >> 5] >> (i & 31)) & 1u;
   __syncthreads();
   const int64_t groups = hw / VEC;
   const int64_t* sl = slabel + img * hw;
@@ -148,14 +156,14 @@ int diga_class_presence(const int64_t* slabel, int64_t B, int64_t hw, uint32_t* 
   return DIGA_OK;
 }
 
-int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut, const float* a, const float* b,
+int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const float* a, const float* b,
                         const int64_t* tlabel, int64_t B, int64_t channels, int64_t hw, float* mask, float* mix,
                         int64_t* mixlabel, diga_stream_t stream) {
   using namespace diga;
-  DIGA_REQUIRE(slabel && lut, DIGA_ERR_INVALID, "classmix_blend: null label/lut");
+  DIGA_REQUIRE(slabel && lut_host, DIGA_ERR_INVALID, "classmix_blend: null label/lut");
   DIGA_REQUIRE(!mix || (a && b), DIGA_ERR_INVALID, "classmix_blend: mix needs both images");
   DIGA_REQUIRE(!mixlabel || tlabel, DIGA_ERR_INVALID, "classmix_blend: mixlabel needs tlabel");
-  DIGA_REQUIRE(B >= 0 && hw >= 0 && channels >= 0 && B <= 65535, DIGA_ERR_INVALID, "classmix_blend: bad sizes");
+  DIGA_REQUIRE(B >= 0 && hw >= 0 && channels >= 0, DIGA_ERR_INVALID, "classmix_blend: bad sizes");
   DIGA_REQUIRE(aligned(slabel, 8) && aligned(tlabel, 8) && aligned(mixlabel, 8) && aligned(a, 4) && aligned(b, 4) &&
                    aligned(mix, 4) && aligned(mask, 4),
                DIGA_ERR_MISALIGNED, "classmix_blend: misaligned pointer");
@@ -164,20 +172,32 @@ int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut, const float* 
   constexpr int BLOCK = 256;
   const bool a16 = aligned(slabel, 16) && aligned(tlabel, 16) && aligned(mixlabel, 16) && aligned(a, 16) &&
                    aligned(b, 16) && aligned(mix, 16) && aligned(mask, 16);
-  const int vec = ((hw % 4) == 0 && a16) ? tunable("cm_vec", 4) : 1;
+  int vec = ((hw % 4) == 0 && a16) ? tunable("cm_vec", 4) : 1;
+  if (vec == 2 && (hw % 2) != 0) vec = 1;
   const int64_t groups = hw / vec;
-  int64_t gx = (groups + BLOCK - 1) / BLOCK;
-  const int64_t cap = ((int64_t)sm_count() * 8 * tunable("cm_waves", 1) + B - 1) / B;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)B);
-  if (vec == 4)
-    classmix_blend_kernel<4, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, lut, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
-  else if (vec == 2 && (hw % 2) == 0)
-    classmix_blend_kernel<2, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, lut, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
-  else
-    classmix_blend_kernel<1, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, lut, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
-  DIGA_CHECK_LAUNCH("classmix_blend_kernel");
+  for (int64_t img0 = 0; img0 < B; img0 += kBlendImagesPerLaunch) {
+    const int64_t nb = B - img0 < kBlendImagesPerLaunch ? B - img0 : kBlendImagesPerLaunch;
+    BlendSelection sel;
+    for (int i = 0; i < kBlendImagesPerLaunch; ++i)
+      for (int wd = 0; wd < 8; ++wd) {
+        uint32_t bits = 0;
+        if (i < nb)
+          for (int k = 0; k < 32; ++k) bits |= (lut_host[(img0 + i) * 256 + wd * 32 + k] ? 1u : 0u) << k;
+        sel.bits[i][wd] = bits;
+      }
+    int64_t gx = (groups + BLOCK - 1) / BLOCK;
+    const int64_t cap = ((int64_t)sm_count() * 8 * tunable("cm_waves", 2) + nb - 1) / nb;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)nb);
+    if (vec == 4)
+      classmix_blend_kernel<4, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, sel, img0, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
+    else if (vec == 2)
+      classmix_blend_kernel<2, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, sel, img0, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
+    else
+      classmix_blend_kernel<1, BLOCK><<<grid, BLOCK, 0, st>>>(slabel, sel, img0, a, b, tlabel, (int)channels, hw, mask, mix, mixlabel);
+    DIGA_CHECK_LAUNCH("classmix_blend_kernel");
+  }
   return DIGA_OK;
 }
 

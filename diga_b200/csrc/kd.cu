@@ -171,7 +171,7 @@ static int dispatch_kd(const float* tea, const float* stu, float* dstu, int64_t 
   int vec = tunable("kd_vec", 2);
   const bool a8 = aligned(tea, 8) && aligned(stu, 8) && (!GRAD || aligned(dstu, 8));
   if (vec != 1 && !((hw % 2) == 0 && a8)) vec = 1;
-  const int block = tunable("kd_block", (LOSS && GRAD) ? 128 : 256);
+  const int block = tunable((LOSS && GRAD) ? "kd_block_fused" : "kd_block", (LOSS && GRAD) ? 128 : 256);
   KdWorkspace* ws = reinterpret_cast<KdWorkspace*>(workspace);
 #define DIGA_KD_GO(V, BL) \
   return launch_kd<kC, kPad, V, BL, LOSS, GRAD>(tea, stu, dstu, (int)C, B, hw, scale, up_dev, up_host, loss_out, ws, st)

@@ -65,15 +65,20 @@ proto_distance_fp32_kernel(const float* __restrict__ feat, const float* __restri
     float x[DK];
 #pragma unroll
     for (int k = 0; k < DK; ++k) x[k] = (ok && d0 + k < D) ? ld_stream<1>(f + (d0 + k) * hw).v[0] : 0.f;
+    // two-level summation: a fresh partial per DK-channel step, then one add into the running sum.  A single
+    // 2048-term fp32 chain would be ~15x less accurate than torch's tree reduction (measured: weight error
+    // 1.2e-5 vs 8e-7 at D=2048).
 #pragma unroll
-    for (int k = 0; k < DK; ++k) {
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
+        float part = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        if (!PAD || c < nclass) {
+        for (int k = 0; k < DK; ++k) {
           const float df = s_cen[c][k] - x[k];
-          acc[c] = fmaf(df, df, acc[c]);
+          part = fmaf(df, df, part);
         }
-    }
+        acc[c] += part;
+      }
   }
   if (!ok) return;
 #pragma unroll

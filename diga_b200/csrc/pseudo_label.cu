@@ -119,62 +119,66 @@ static int launch_pl(const float* z1, const float* z2, int nclass, int64_t n, in
 // ------------------------------------------------------------------------------------------------
 // Fused two-scale variant: the bilinear up-samplings of pseudolabel_generator.py:77-78 are evaluated
 // on the fly from the stride-8 logits (L1/L2 resident), so HBM traffic drops from 8C+5 to ~5 B/px.
-// One thread = one output pixel; interpolation mirrors ATen (bilinear.cuh).
+// Interpolation mirrors ATen (bilinear.cuh).
 // ------------------------------------------------------------------------------------------------
-template <int C, bool PAD, int BLOCK, bool HAS2>
+// One thread = one output column x RY consecutive rows; both scales are walked with a ColumnInterp each.
+template <int C, bool PAD, int RY, int BLOCK, bool HAS2>
 __global__ void __launch_bounds__(BLOCK)
 pseudo_label_upsampled_kernel(const float* __restrict__ z1, int h1, int w1, float sh1, float sw1,
                               const float* __restrict__ z2, int h2, int w2, float sh2, float sw2, int nclass, int H, int W,
                               uint8_t* __restrict__ lab8, int64_t* __restrict__ lab64, float* __restrict__ conf) {
   const int64_t img = blockIdx.z;
-  const int Y = blockIdx.y;
+  const int Y0 = blockIdx.y * RY;
   const int X = blockIdx.x * BLOCK + threadIdx.x;
   if (X >= W) return;
-  const Tap ty1 = bilinear_tap(sh1, Y, h1), tx1 = bilinear_tap(sw1, X, w1);
   const float* b1 = z1 + img * nclass * h1 * w1;
   const int64_t pl1 = (int64_t)h1 * w1;
-  Tap ty2 = ty1, tx2 = tx1;
+  const Tap tx1[1] = {bilinear_tap(sw1, X, w1)};
+  ColumnInterp<C, PAD, 1> c1;
   const float* b2 = nullptr;
   int64_t pl2 = 0;
+  Tap tx2[1] = {tx1[0]};
+  ColumnInterp<HAS2 ? C : 1, PAD, 1> c2;
   if constexpr (HAS2) {
-    ty2 = bilinear_tap(sh2, Y, h2);
-    tx2 = bilinear_tap(sw2, X, w2);
     b2 = z2 + img * nclass * h2 * w2;
     pl2 = (int64_t)h2 * w2;
+    tx2[0] = bilinear_tap(sw2, X, w2);
   }
-  float z[C];
+  const int Yend = min(Y0 + RY, H);
+  for (int Y = Y0; Y < Yend; ++Y) {
+    const Tap ty1 = bilinear_tap(sh1, Y, h1);
+    c1.seek(ty1, b1, pl1, w1, tx1, nclass);
+    Tap ty2 = ty1;
+    if constexpr (HAS2) {
+      ty2 = bilinear_tap(sh2, Y, h2);
+      c2.seek(ty2, b2, pl2, w2, tx2, nclass);
+    }
+    float z[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c)
-    if (!PAD || c < nclass) {
-      const float* q = b1 + c * pl1;
-      const float top = bilinear_row(tx1, __ldg(q + (int64_t)ty1.i0 * w1 + tx1.i0), __ldg(q + (int64_t)ty1.i0 * w1 + tx1.i1));
-      const float bot = bilinear_row(tx1, __ldg(q + (int64_t)ty1.i1 * w1 + tx1.i0), __ldg(q + (int64_t)ty1.i1 * w1 + tx1.i1));
-      float val = bilinear_col(ty1, top, bot);
-      if constexpr (HAS2) {
-        const float* r = b2 + c * pl2;
-        const float t2 = bilinear_row(tx2, __ldg(r + (int64_t)ty2.i0 * w2 + tx2.i0), __ldg(r + (int64_t)ty2.i0 * w2 + tx2.i1));
-        const float o2 = bilinear_row(tx2, __ldg(r + (int64_t)ty2.i1 * w2 + tx2.i0), __ldg(r + (int64_t)ty2.i1 * w2 + tx2.i1));
-        val = fmaxf(val, bilinear_col(ty2, t2, o2));
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
+        float val = c1.value(ty1, 0, c);
+        if constexpr (HAS2) val = fmaxf(val, c2.value(ty2, 0, c));   // torch.max(output_ds, output), :80
+        z[c] = val;
       }
-      z[c] = val;
-    }
-  float m = z[0];
-  int am = 0;
+    float m = z[0];
+    int am = 0;
 #pragma unroll
-  for (int c = 1; c < C; ++c)
-    if (!PAD || c < nclass) {
-      const bool gt = z[c] > m;
-      m = gt ? z[c] : m;
-      am = gt ? c : am;
-    }
-  float S = 0.f;
+    for (int c = 1; c < C; ++c)
+      if (!PAD || c < nclass) {
+        const bool gt = z[c] > m;
+        m = gt ? z[c] : m;
+        am = gt ? c : am;
+      }
+    float S = 0.f;
 #pragma unroll
-  for (int c = 0; c < C; ++c)
-    if (!PAD || c < nclass) S += fast_exp(z[c] - m);
-  const int64_t o = (img * H + Y) * W + X;
-  if (lab8) lab8[o] = (uint8_t)am;
-  if (lab64) lab64[o] = am;
-  if (conf) conf[o] = 1.0f / S;
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) S += fast_exp(z[c] - m);
+    const int64_t o = (img * H + Y) * W + X;
+    if (lab8) lab8[o] = (uint8_t)am;
+    if (lab64) lab64[o] = am;
+    if (conf) conf[o] = 1.0f / S;
+  }
 }
 
 }  // namespace diga
@@ -195,17 +199,17 @@ extern "C" int diga_pseudo_label_upsampled(const float* logits, int64_t h1, int6
                "pseudo_label_upsampled: misaligned pointer");
   if (n == 0) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  constexpr int BLOCK = 128;
-  dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), (unsigned)H, (unsigned)n);
+  constexpr int BLOCK = 128, RY = 16;
+  dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), (unsigned)((H + RY - 1) / RY), (unsigned)n);
   const float sh1 = bilinear_scale_host(h1, H), sw1 = bilinear_scale_host(w1, W);
   const float sh2 = logits_ds ? bilinear_scale_host(h2, H) : 0.f, sw2 = logits_ds ? bilinear_scale_host(w2, W) : 0.f;
   DIGA_DISPATCH_C(C, {
     if (logits_ds)
-      pseudo_label_upsampled_kernel<kC, kPad, BLOCK, true><<<grid, BLOCK, 0, st>>>(
+      pseudo_label_upsampled_kernel<kC, kPad, RY, BLOCK, true><<<grid, BLOCK, 0, st>>>(
           logits, (int)h1, (int)w1, sh1, sw1, logits_ds, (int)h2, (int)w2, sh2, sw2, (int)C, (int)H, (int)W, label_u8,
           label_i64, conf);
     else
-      pseudo_label_upsampled_kernel<kC, kPad, BLOCK, false><<<grid, BLOCK, 0, st>>>(
+      pseudo_label_upsampled_kernel<kC, kPad, RY, BLOCK, false><<<grid, BLOCK, 0, st>>>(
           logits, (int)h1, (int)w1, sh1, sw1, nullptr, 0, 0, 0.f, 0.f, (int)C, (int)H, (int)W, label_u8, label_i64, conf);
   });
   DIGA_CHECK_LAUNCH("pseudo_label_upsampled_kernel");

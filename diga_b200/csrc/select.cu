@@ -31,60 +31,67 @@ upsample_bilinear_kernel(const float* __restrict__ in, int64_t planes, int h, in
   }
 }
 
-// One thread = PX adjacent output pixels of one row.  torch.max(dim=1) semantics: first index on ties.
-template <int C, bool PAD, int PX, int BLOCK>
+// One thread = PX adjacent output pixels x RY consecutive output rows (ColumnInterp keeps the horizontally
+// interpolated source rows of all classes in registers while it walks down).  A warp covers 32*PX adjacent
+// pixels of a row, so the int64 accesses are 128-bit and fully coalesced.  torch.max(dim=1): first index on ties.
+template <int C, bool PAD, int PX, int RY, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict__ pseudo, int nclass, int h, int w, int H,
                         int W, float sh, float sw, int64_t* __restrict__ kept, int64_t* __restrict__ feat_pseudo) {
   const int64_t img = blockIdx.z;
-  const int Y = blockIdx.y;
-  const int gx = blockIdx.x * BLOCK + threadIdx.x;
-  const int X0 = gx * PX;
+  const int Y0 = blockIdx.y * RY;
+  const int X0 = (blockIdx.x * BLOCK + threadIdx.x) * PX;
   if (X0 >= W) return;
-  const Tap ty = bilinear_tap(sh, Y, h);
   const float* base = wl + img * nclass * h * w;
   const int64_t plane = (int64_t)h * w;
-  int64_t lab[PX];
-  const int64_t o = (img * H + Y) * W + X0;
-  if constexpr (PX == 2) {
-    const longlong2 t = ld_stream_i64x2(pseudo + o);
-    lab[0] = t.x;
-    lab[1] = t.y;
-  } else {
-    lab[0] = ld_stream_i64(pseudo + o);
-  }
-  int64_t am[PX];
+  Tap tx[PX];
 #pragma unroll
-  for (int v = 0; v < PX; ++v) {
-    const Tap tx = bilinear_tap(sw, X0 + v, w);
-    const float* r0 = base + (int64_t)ty.i0 * w;
-    const float* r1 = base + (int64_t)ty.i1 * w;
-    float best = 0.f;
-    int arg = 0;
+  for (int v = 0; v < PX; ++v) tx[v] = bilinear_tap(sw, X0 + v, w);
+  ColumnInterp<C, PAD, PX> ci;
+  const int Yend = min(Y0 + RY, H);
+  // software prefetch of the label loads: one row ahead
+  int64_t lab[PX], nxt[PX];
+  auto load_labels = [&](int64_t (&dst)[PX], int Y) {
+    const int64_t o = (img * H + Y) * W + X0;
+    if constexpr (PX == 2) {
+      const longlong2 t = ld_stream_i64x2(pseudo + o);
+      dst[0] = t.x;
+      dst[1] = t.y;
+    } else {
+      dst[0] = ld_stream_i64(pseudo + o);
+    }
+  };
+  load_labels(lab, Y0);
+  for (int Y = Y0; Y < Yend; ++Y) {
+    if (Y + 1 < Yend) load_labels(nxt, Y + 1);
+    const Tap ty = bilinear_tap(sh, Y, h);
+    ci.seek(ty, base, plane, w, tx, nclass);
+    int64_t am[PX];
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) {
-        const float* q0 = r0 + c * plane;
-        const float* q1 = r1 + c * plane;
-        const float top = bilinear_row(tx, __ldg(q0 + tx.i0), __ldg(q0 + tx.i1));
-        const float bot = bilinear_row(tx, __ldg(q1 + tx.i0), __ldg(q1 + tx.i1));
-        const float val = bilinear_col(ty, top, bot);
-        if (c == 0 || val > best) {
-          best = val;
-          arg = c;
+    for (int v = 0; v < PX; ++v) {
+      float best = ci.value(ty, v, 0);
+      int arg = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c)
+        if (!PAD || c < nclass) {
+          const float val = ci.value(ty, v, c);
+          const bool gt = val > best;
+          best = gt ? val : best;
+          arg = gt ? c : arg;
         }
-      }
-    am[v] = arg;
-  }
-  int64_t kp[PX];
+      am[v] = arg;
+    }
+    const int64_t o = (img * H + Y) * W + X0;
+    if constexpr (PX == 2) {
+      st_stream_i64x2(kept + o, lab[0] == am[0] ? lab[0] : (int64_t)DIGA_IGNORE_LABEL,           // :304
+                      lab[1] == am[1] ? lab[1] : (int64_t)DIGA_IGNORE_LABEL);
+      if (feat_pseudo) st_stream_i64x2(feat_pseudo + o, am[0], am[1]);
+    } else {
+      st_stream_i64(kept + o, lab[0] == am[0] ? lab[0] : (int64_t)DIGA_IGNORE_LABEL);
+      if (feat_pseudo) st_stream_i64(feat_pseudo + o, am[0]);
+    }
 #pragma unroll
-  for (int v = 0; v < PX; ++v) kp[v] = (lab[v] == am[v]) ? lab[v] : (int64_t)DIGA_IGNORE_LABEL;   // :304
-  if constexpr (PX == 2) {
-    st_stream_i64x2(kept + o, kp[0], kp[1]);
-    if (feat_pseudo) st_stream_i64x2(feat_pseudo + o, am[0], am[1]);
-  } else {
-    st_stream_i64(kept + o, kp[0]);
-    if (feat_pseudo) st_stream_i64(feat_pseudo + o, am[0]);
+    for (int v = 0; v < PX; ++v) lab[v] = nxt[v];
   }
 }
 
@@ -125,16 +132,17 @@ int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, in
   cudaStream_t st = (cudaStream_t)stream;
   const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
   const bool pair = (W % 2) == 0 && aligned(pseudo, 16) && aligned(kept, 16) && aligned(feat_pseudo, 16);
-  constexpr int BLOCK = 128;
+  constexpr int BLOCK = 128, RY = 8;
+  const unsigned gy = (unsigned)((H + RY - 1) / RY);
   DIGA_DISPATCH_C(C, {
     if (pair) {
-      dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), (unsigned)H, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 2, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
-                                                                         (int)H, (int)W, sh, sw, kept, feat_pseudo);
+      dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), gy, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 2, RY, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
+                                                                             (int)H, (int)W, sh, sw, kept, feat_pseudo);
     } else {
-      dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), (unsigned)H, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 1, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
-                                                                         (int)H, (int)W, sh, sw, kept, feat_pseudo);
+      dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), gy, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 1, RY, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
+                                                                             (int)H, (int)W, sh, sw, kept, feat_pseudo);
     }
   });
   DIGA_CHECK_LAUNCH("consensus_select_kernel");

@@ -82,14 +82,15 @@ int diga_pseudo_label(const float* logits, const float* logits_ds, int64_t n, in
  *   class_presence: bitmap[b][8] (256 bits) of label values present in image b — the device half
  *     of torch.unique(slabel[b]); flags[0] |= 1 if a label lies outside [0,255].
  *     bitmap and flags are cleared by the call.
- *   classmix_blend: lut[b][256] (uint8, 1 = class selected for image b) ->
- *     mask[b,p] = lut[b][slabel[b,p]]  (fp32 0/1, may be NULL)
+ *   classmix_blend: lut_host[b][256] (uint8 in HOST memory, 1 = class selected for image b; it is consumed
+ *     before the call returns and travels to the GPU as a kernel argument) ->
+ *     mask[b,p] = lut_host[b][slabel[b,p]]  (fp32 0/1, may be NULL)
  *     mix[b,c,p] = a*(1-mask) + b*mask  (evaluated exactly as written, no FMA contraction)
  *     mixlabel[b,p] = mask ? slabel : tlabel   (only if tlabel != NULL)
  * ------------------------------------------------------------------------------------------ */
 int diga_class_presence(const int64_t* slabel, int64_t B, int64_t hw, uint32_t* bitmap, uint32_t* flags,
                         diga_stream_t stream);
-int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut, const float* a, const float* b,
+int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const float* a, const float* b,
                         const int64_t* tlabel, int64_t B, int64_t channels, int64_t hw,
                         float* mask, float* mix, int64_t* mixlabel, diga_stream_t stream);
 

@@ -377,7 +377,7 @@ def test_centroid_accum_variants_and_determinism(D):
     out = S.logits((2, 19, 65, 129), g)
     ref = None
     try:
-        for variant in range(5):
+        for variant in range(8):
             L.set_tunable("accum_variant", variant)
             cf = D.Class_Features(19, 256)
             v1, s1, ok1 = cf._masked_means(feat, out, None)
@@ -434,7 +434,7 @@ def test_proto_vs_oracle(D, n, d, h, w, c):
     err_o = (w_o.double() - w64).abs().max().item()
     tol = 1e-5 * d64.max().item() * w64.max().item()
     assert err_g <= tol, f"weight error {err_g:.3e} exceeds the conditioning bound {tol:.3e}"
-    assert err_g <= 4 * err_o + 1e-7, f"weight error {err_g:.3e} vs reference chain's own {err_o:.3e}"
+    assert err_g <= max(0.1 * tol, 4 * err_o), f"weight error {err_g:.3e} vs reference chain's own {err_o:.3e}"
     mism = dist_g.argmin(1) != d64.argmin(1)
     if mism.any():
         top2 = d64.topk(2, dim=1, largest=False).values

@@ -91,7 +91,7 @@ def sweep_accum():
         feat = S.features((n, d, h, w), g)
         cls = torch.randint(0, 19, (n, h * w), device=dev, dtype=torch.uint8)
         sums = torch.empty((n, 19, d), device=dev)
-        for variant in range(5):
+        for variant in range(8):
             L.set_tunable("accum_variant", variant)
             ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
             report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "random"}, ms, feat.numel() * 4)
@@ -111,11 +111,21 @@ def sweep_cm():
     from diga_b200.classmix import present_classes, select_classes
     classes = select_classes(present_classes(sl), random.Random(1))
     px = b * hh * ww
-    for vec, waves in itertools.product((4, 2, 1), (1, 2, 4)):
+    import numpy as np
+    lut = np.zeros((b, 256), dtype=np.uint8)
+    for i, sel in enumerate(classes):
+        lut[i, sel] = 1
+    mix = torch.empty_like(xa); ml = torch.empty_like(tl); mask = torch.empty((b, hh, ww), device=dev)
+    for vec, waves in itertools.product((4, 2, 1), (1, 2, 4, 8)):
         L.set_tunable("cm_vec", vec); L.set_tunable("cm_waves", waves)
-        report("classmix_blend_dacs", {"vec": vec, "waves": waves},
-               timeit(lambda: D.classmix(sl, xa, xb, tl, classes=classes, return_mask=False)), px * 60)
-    L.set_tunable("cm_vec", 4); L.set_tunable("cm_waves", 1)
+        fn = lambda: L.check(L.lib.diga_classmix_blend(sl.data_ptr(), lut.ctypes.data, xa.data_ptr(), xb.data_ptr(), tl.data_ptr(),
+                                                       b, 3, hh * ww, None, mix.data_ptr(), ml.data_ptr(), L.stream()))
+        report("classmix_blend_dacs_kernel", {"vec": vec, "waves": waves}, timeit(fn), px * 60)
+        fn2 = lambda: L.check(L.lib.diga_classmix_blend(sl.data_ptr(), lut.ctypes.data, xa.data_ptr(), xb.data_ptr(), None,
+                                                        b, 3, hh * ww, mask.data_ptr(), mix.data_ptr(), None, L.stream()))
+        report("classmix_blend_img_mask_kernel", {"vec": vec, "waves": waves}, timeit(fn2), px * 48)
+    L.set_tunable("cm_vec", 4); L.set_tunable("cm_waves", 2)
+    report("classmix_python_total", {}, timeit(lambda: D.classmix(sl, xa, xb, tl, rng=random.Random(1), return_mask=False)), px * 68)
     bm = torch.empty((b, 8), dtype=torch.int32, device=dev); fl = torch.empty(1, dtype=torch.int32, device=dev)
     report("class_presence", {}, timeit(lambda: L.check(L.lib.diga_class_presence(sl.data_ptr(), b, hh * ww, bm.data_ptr(), fl.data_ptr(), L.stream()))), px * 8)
 
