@@ -1,0 +1,29 @@
+"""Run one hot kernel a few times (for ncu captures):  python tools/prof_one.py proto|accum|select|plup"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import diga_b200 as D
+from diga_b200 import _lib as L, synthetic as S
+dev = torch.device("cuda", 0)
+g = S.gen(17, dev)
+which = sys.argv[1]
+n, d, h, w, c = 8, 2048, 65, 129, 19
+if which in ("proto", "accum"):
+    feat = S.features((n, d, h, w), g)
+    cf = D.Class_Features(c, d); cf.objective_vectors = S.centroids(c, d, g)
+    out = S.logits((n, c, h, w), g)
+    for _ in range(3):
+        if which == "proto":
+            cf.get_centroid_weight(feat)
+        else:
+            cf.update_from_features(feat, out, None, "mean")
+elif which == "select":
+    wl = torch.softmax(S.logits((8, 19, 65, 129), g), 1)
+    tl = S.block_labels(8, 512, 1024, g)
+    for _ in range(3):
+        D.consensus_select(tl, wl)
+elif which == "plup":
+    l1, l2 = S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g)
+    for _ in range(3):
+        D.pseudo_label_two_scale(l1, l2, (1024, 2048))
+torch.cuda.synchronize()
