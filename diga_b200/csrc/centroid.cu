@@ -68,6 +68,25 @@ centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // accum
 // ------------------------------------------------------------------------------------------------
+// Persistent grid for `items` equal work items: among 3..max resident CTAs per SM pick the count whose last round is
+// fullest (4096 items on 148 SMs: 5 CTAs/SM leaves a 5.53 -> 6 round, 8 % idle; 4 CTAs/SM gives 6.92 -> 7, 1 %).
+static int64_t balanced_grid(int64_t items, int blocks_per_sm) {
+  const int64_t sms = sm_count();
+  if (items <= sms * blocks_per_sm) return items < 1 ? 1 : items;
+  int64_t best = sms * blocks_per_sm;
+  double best_eff = 0.0;
+  for (int k = blocks_per_sm; k >= (blocks_per_sm > 3 ? 3 : 1); --k) {
+    const int64_t g = sms * k;
+    const int64_t rounds = (items + g - 1) / g;
+    const double eff = (double)items / (double)(rounds * g);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = g;
+    }
+  }
+  return best;
+}
+
 template <int R> struct AccT;
 template <> struct AccT<4> { using type = float4; };
 template <> struct AccT<2> { using type = float2; };
@@ -93,18 +112,40 @@ __device__ __forceinline__ void accum_load(AccumBatch<R, U>& b, const float* con
   }
 }
 
+// Run combining: the pixels one lane visits (p, p+STRIPE, p+2*STRIPE, ...) are vertical neighbours in the image, and
+// segmentation maps are piecewise constant, so consecutive visits usually hit the same class.  The values of a run are
+// summed in registers and flushed to the lane-private shared-memory cell only when the class changes: on realistic
+// maps that removes most of the shared-memory read-modify-writes (the L1/shared data pipe is this kernel's busiest
+// unit, 65 % in ncu), on i.i.d. random classes it degenerates to one RMW per pixel as before.
+template <int R, typename acc_t>
+struct AccumRun {
+  int cls = 255;
+  float v[R];
+  __device__ __forceinline__ void flush(acc_t* my, int nclass) {
+    if (cls < nclass) {
+      acc_t a = my[cls * 32];
+      if constexpr (R == 4) {
+        a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+      } else {
+        a.x += v[0]; a.y += v[1];
+      }
+      my[cls * 32] = a;
+    }
+  }
+};
+
 template <int R, int U, typename acc_t>
-__device__ __forceinline__ void accum_apply(const AccumBatch<R, U>& b, acc_t* my, int nclass) {
+__device__ __forceinline__ void accum_apply(const AccumBatch<R, U>& b, acc_t* my, int nclass, AccumRun<R, acc_t>& run) {
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    if (b.cid[u] < nclass) {
-      acc_t v = my[b.cid[u] * 32];
-      if constexpr (R == 4) {
-        v.x += b.x[u][0]; v.y += b.x[u][1]; v.z += b.x[u][2]; v.w += b.x[u][3];
-      } else {
-        v.x += b.x[u][0]; v.y += b.x[u][1];
-      }
-      my[b.cid[u] * 32] = v;
+    if (b.cid[u] == run.cls) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) run.v[r] += b.x[u][r];
+    } else {
+      run.flush(my, nclass);
+      run.cls = b.cid[u];
+#pragma unroll
+      for (int r = 0; r < R; ++r) run.v[r] = b.x[u][r];
     }
   }
 }
@@ -143,20 +184,22 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
     for (int c = 0; c < nclass; ++c) my[c * 32] = zero;
     // (own lane-private cells only: no barrier needed before the main loop)
 
+    AccumRun<R, acc_t> run;
     if constexpr (PIPE) {
       // bases are warp-uniform up to +lane, so the loop trip count is uniform within a warp
       for (int64_t base = first; base - lane < hw; base += 2 * STEP) {
         accum_load<R, WARPS, U>(b, rows, cl, base + STEP, hw);
-        accum_apply<R, U>(a, my, nclass);
+        accum_apply<R, U>(a, my, nclass, run);
         accum_load<R, WARPS, U>(a, rows, cl, base + 2 * STEP, hw);
-        accum_apply<R, U>(b, my, nclass);
+        accum_apply<R, U>(b, my, nclass, run);
       }
     } else {
       for (int64_t base = first; base - lane < hw; base += STEP) {
-        accum_apply<R, U>(a, my, nclass);
+        accum_apply<R, U>(a, my, nclass, run);
         accum_load<R, WARPS, U>(a, rows, cl, base + STEP, hw);
       }
     }
+    run.flush(my, nclass);
     __syncthreads();
     // cross-warp then cross-lane reduction; classes are dealt round-robin to warps
     for (int c = warp; c < nclass; c += WARPS) {
@@ -185,6 +228,175 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// accum, 128-bit variant.  A lane owns 4 ADJACENT pixels of 4 channel rows (four aligned LDG.128).  The four rows
+// are chosen RS apart so that they share one alignment: with hw odd (65x129) row d starts (d*hw) mod 32 floats past a
+// 128-byte line, rows d, d+32, d+64, d+96 start at the same phase s, and the aligned quad t of every row covers
+// pixels 4t-s .. 4t-s+3, so every warp request is exactly four whole cache lines.  Adjacent pixels usually carry the same class (segmentation maps are piecewise constant):
+// when all four agree their values are summed in registers and ONE shared-memory read-modify-write is issued instead
+// of four, which takes the kernel off the shared-memory pipe on realistic label maps.
+// ------------------------------------------------------------------------------------------------
+// Row stride RS (a power of two) such that rows d and d+RS start at the same phase within a 128-byte line
+// (RS*hw % 32 == 0), falling back to 16-byte phase equality (RS*hw % 4 == 0); 0 if D cannot be tiled by 4*RS rows.
+static int quad_row_stride(int64_t hw, int64_t D) {
+  for (int unit = 32; unit >= 4; unit /= 8) {       // 32 floats = one line, then 4 floats = one 128-bit access
+    int rs = unit;
+    while (rs > 1 && ((rs / 2) * hw) % unit == 0) rs /= 2;
+    if (D % (4 * rs) == 0) return rs;
+  }
+  return 0;
+}
+
+template <int U>
+struct QuadBatch {
+  float4 x[U][4];
+  uint32_t cls4[U];   // 4 class bytes, 0xff = skip
+};
+
+template <int WARPS, int U>
+__device__ __forceinline__ void quad_load(QuadBatch<U>& b, const float* const (&rows)[4], const uint8_t* cl, int64_t t0,
+                                          int64_t T, int s, int64_t hw) {
+  constexpr int STRIPE = WARPS * 32;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t t = t0 + (int64_t)u * STRIPE;
+    const bool ok = t < T;
+    uint32_t c4 = 0xffffffffu;
+    if (ok) {
+      const int64_t p0 = 4 * t - s;
+      c4 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t p = p0 + i;
+        const uint32_t c = (p >= 0 && p < hw) ? (uint32_t)__ldg(cl + p) : 0xffu;
+        c4 |= c << (8 * i);
+      }
+    }
+    b.cls4[u] = c4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (ok) {
+        const Vec<4> v = ld_stream<4>(rows[r] + 4 * t);
+        b.x[u][r] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+      } else {
+        b.x[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float f4_get(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <int U>
+__device__ __forceinline__ void quad_apply(const QuadBatch<U>& b, float4* my, int nclass) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t c4 = b.cls4[u];
+    const uint32_t c0 = c4 & 0xffu;
+    if (c4 == c0 * 0x01010101u) {            // all four pixels in one class (or all skipped)
+      if ((int)c0 < nclass) {
+        float4 v = my[c0 * 32];
+        v.x += (b.x[u][0].x + b.x[u][0].y) + (b.x[u][0].z + b.x[u][0].w);
+        v.y += (b.x[u][1].x + b.x[u][1].y) + (b.x[u][1].z + b.x[u][1].w);
+        v.z += (b.x[u][2].x + b.x[u][2].y) + (b.x[u][2].z + b.x[u][2].w);
+        v.w += (b.x[u][3].x + b.x[u][3].y) + (b.x[u][3].z + b.x[u][3].w);
+        my[c0 * 32] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (int)((c4 >> (8 * i)) & 0xffu);
+        if (c < nclass) {
+          float4 v = my[c * 32];
+          v.x += f4_get(b.x[u][0], i);
+          v.y += f4_get(b.x[u][1], i);
+          v.z += f4_get(b.x[u][2], i);
+          v.w += f4_get(b.x[u][3], i);
+          my[c * 32] = v;
+        }
+      }
+    }
+  }
+}
+
+template <int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32)
+centroid_accum_quad_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ cls, int nclass, int64_t n, int64_t D,
+                           int64_t hw, int RS, float* __restrict__ sums) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* acc = reinterpret_cast<float4*>(smem_raw);   // [WARPS][nclass][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t groups = D / 4;
+  const int64_t items = n * groups;
+  float4* my = acc + (size_t)warp * nclass * 32 + lane;
+  constexpr int64_t STEP = (int64_t)WARPS * 32 * U;
+
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t img = item / groups;
+    const int64_t g = item - img * groups;
+    const int64_t blk = g / RS, q = g - blk * RS;        // rows blk*4*RS + q + j*RS, j = 0..3
+    const int64_t d0 = blk * 4 * RS + q;
+    const int s = (int)((q * hw) & (RS - 1));             // common alignment phase (floats) of the four rows
+    const int64_t T = (hw + s + 3) >> 2;
+    const uint8_t* cl = cls + img * hw;
+    const float* rows[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rows[j] = feat + (img * D + d0 + (int64_t)j * RS) * hw - s;
+    const int64_t first = warp * 32 + lane;
+    QuadBatch<U> a, b;
+    quad_load<WARPS, U>(a, rows, cl, first, T, s, hw);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < nclass; ++c) my[c * 32] = zero;
+    for (int64_t t0 = first; t0 - lane < T; t0 += 2 * STEP) {
+      quad_load<WARPS, U>(b, rows, cl, t0 + STEP, T, s, hw);
+      quad_apply<U>(a, my, nclass);
+      quad_load<WARPS, U>(a, rows, cl, t0 + 2 * STEP, T, s, hw);
+      quad_apply<U>(b, my, nclass);
+    }
+    __syncthreads();
+    for (int c = warp; c < nclass; c += WARPS) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const float4 v = acc[((size_t)w * nclass + c) * 32 + lane];
+        sx += v.x; sy += v.y; sz += v.z; sw += v.w;
+      }
+      sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sw = warp_sum(sw);
+      if (lane == 0) {
+        float* o = sums + (img * nclass + c) * D + d0;
+        o[0] = sx; o[RS] = sy; o[2 * RS] = sz; o[3 * RS] = sw;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int WARPS, int U>
+static int launch_accum_quad(const float* feat, const uint8_t* cls, int nclass, int64_t n, int64_t D, int64_t hw, float* sums,
+                             cudaStream_t st) {
+  auto kern = centroid_accum_quad_kernel<WARPS, U>;
+  const size_t smem = (size_t)WARPS * nclass * 32 * sizeof(float4);
+  static size_t configured = 0;
+  static int blocks_per_sm = 0;
+  if (configured != smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("centroid_accum: cannot reserve %zu bytes of shared memory", smem);
+      return DIGA_ERR_CUDA;
+    }
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, WARPS * 32, smem);
+    blocks_per_sm = b > 0 ? b : 1;
+    configured = smem;
+  }
+  const int RS = quad_row_stride(hw, D);
+  const int64_t items = n * (D / 4);
+  const int64_t grid = tunable("accum_balance", 1) ? balanced_grid(items, blocks_per_sm) : (items < (int64_t)sm_count() * blocks_per_sm ? items : (int64_t)sm_count() * blocks_per_sm);
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, cls, nclass, n, D, hw, RS, sums);
+  DIGA_CHECK_LAUNCH("centroid_accum_quad_kernel");
+  return DIGA_OK;
+}
+
 template <int R, int WARPS, int U, bool PIPE>
 static int launch_accum(const float* feat, const uint8_t* cls, int nclass, int64_t n, int64_t D, int64_t hw, float* sums,
                         cudaStream_t st) {
@@ -204,9 +416,7 @@ static int launch_accum(const float* feat, const uint8_t* cls, int nclass, int64
     configured = smem;
   }
   const int64_t items = n * ((D + R - 1) / R);
-  int64_t grid = (int64_t)sm_count() * blocks_per_sm;
-  if (grid > items) grid = items;
-  if (grid < 1) grid = 1;
+  const int64_t grid = tunable("accum_balance", 1) ? balanced_grid(items, blocks_per_sm) : (items < (int64_t)sm_count() * blocks_per_sm ? items : (int64_t)sm_count() * blocks_per_sm);
   kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, cls, nclass, n, D, hw, sums);
   DIGA_CHECK_LAUNCH("centroid_accum_kernel");
   return DIGA_OK;
@@ -258,23 +468,45 @@ __device__ __forceinline__ float rule_apply(const UpdateRule& r, bool mean, floa
   return __fadd_rn(__fmul_rn(obj, r.one_minus_m), __fmul_rn(r.m, v));   // :153-154
 }
 
+// grid (C, ceil(D / BLOCK)): one thread per (class, channel).  The sequential recurrence over images runs in
+// registers (the centroid element is read once and written once); every block of a class replays the same scalar
+// `num` recurrence, block y == 0 stores it.  (A first version with one block per class and global read-modify-writes
+// per image took 37 us for N=8, D=2048 — a third of the accumulation kernel it follows.)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_update_kernel(const float* __restrict__ vec, const float* __restrict__ vecsum, const uint8_t* __restrict__ valid,
                        int64_t n, int64_t C, int64_t D, float* __restrict__ obj, float* __restrict__ objnum, UpdateRule rule) {
   const int64_t c = blockIdx.x;
+  const int64_t d = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
+  const bool live = d < D;
   float num = objnum[c];
-  float* o = obj + c * D;
+  float o = live ? obj[c * D + d] : 0.f;
   for (int64_t i = 0; i < n; ++i) {
     const int64_t nc = i * C + c;
     if (valid != nullptr && !valid[nc]) continue;
     if (vecsum[nc] == 0.f) continue;                                    // :148
     const bool mean = rule_is_mean(rule, num);
-    const float* v = vec + nc * D;
-    for (int64_t d = threadIdx.x; d < D; d += BLOCK) o[d] = rule_apply(rule, mean, o[d], num, v[d]);
+    const float v = live ? vec[nc * D + d] : 0.f;
+    o = rule_apply(rule, mean, o, num, v);
     num = fminf(__fadd_rn(num, 1.f), 3000.f);                           // :155-156 / :159,161
   }
-  if (threadIdx.x == 0) objnum[c] = num;
+  if (live) obj[c * D + d] = o;
+}
+
+// The counts are advanced by a second, tiny launch so that no block of the kernel above can observe a count that
+// another block of the same class has already updated.
+__global__ void centroid_update_num_kernel(const float* __restrict__ vecsum, const uint8_t* __restrict__ valid, int64_t n,
+                                           int64_t C, float* __restrict__ objnum) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float num = objnum[c];
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t nc = i * C + c;
+    if (valid != nullptr && !valid[nc]) continue;
+    if (vecsum[nc] == 0.f) continue;
+    num = fminf(__fadd_rn(num, 1.f), 3000.f);
+  }
+  objnum[c] = num;
 }
 
 template <int BLOCK>
@@ -303,17 +535,16 @@ __global__ void __launch_bounds__(BLOCK)
 centroid_reduce_images_kernel(const float* __restrict__ vec, const float* __restrict__ vecsum,
                               const uint8_t* __restrict__ valid, int64_t n, int64_t C, int64_t D, float* __restrict__ acc) {
   const int64_t c = blockIdx.x;
-  float* a = acc + c * (D + 1);
-  int used = 0;
+  const int64_t d = (int64_t)blockIdx.y * BLOCK + threadIdx.x;   // d == D is the image-count column
+  if (d > D) return;
+  float a = acc[c * (D + 1) + d];
   for (int64_t i = 0; i < n; ++i) {
     const int64_t nc = i * C + c;
     if (valid != nullptr && !valid[nc]) continue;
     if (vecsum[nc] == 0.f) continue;
-    ++used;
-    const float* v = vec + nc * D;
-    for (int64_t d = threadIdx.x; d < D; d += BLOCK) a[d] += v[d];
+    a += d < D ? vec[nc * D + d] : 1.f;
   }
-  if (threadIdx.x == 0) a[D] += (float)used;
+  acc[c * (D + 1) + d] = a;
 }
 
 // process_label (util/utils.py:158-163): onehot[b][k][p] = (k == (label < C ? long(label) : C)), k in [0, C].
@@ -375,6 +606,19 @@ int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_
   if (n == 0 || D == 0) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int variant = tunable("accum_variant", 0);
+  const int RS = quad_row_stride(hw, D);
+  const bool quad_ok = RS > 0 && aligned(feat, 128) && hw >= 4;
+  // Default: the 128-bit kernel (4 warps, 2 quads in flight twice) — the best all-round shape in the sweeps
+  // (profiles/r01_tune_accum.jsonl); the scalar kernels take the shapes it cannot tile (variants 1..7 force them).
+  if (quad_ok && (variant == 0 || variant >= 8)) {
+    switch (variant) {
+      case 8: return launch_accum_quad<4, 1>(feat, cls, (int)C, n, D, hw, sums, st);
+      case 10: return launch_accum_quad<2, 1>(feat, cls, (int)C, n, D, hw, sums, st);
+      case 11: return launch_accum_quad<2, 2>(feat, cls, (int)C, n, D, hw, sums, st);
+      case 12: return launch_accum_quad<8, 1>(feat, cls, (int)C, n, D, hw, sums, st);
+      default: return launch_accum_quad<4, 2>(feat, cls, (int)C, n, D, hw, sums, st);
+    }
+  }
   switch (variant) {
     case 1: return launch_accum<4, 4, 4, false>(feat, cls, (int)C, n, D, hw, sums, st);
     case 2: return launch_accum<4, 4, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
@@ -383,7 +627,7 @@ int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_
     case 5: return launch_accum<4, 2, 4, true>(feat, cls, (int)C, n, D, hw, sums, st);
     case 6: return launch_accum<4, 2, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
     case 7: return launch_accum<2, 8, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
-    default: return launch_accum<4, 4, 4, true>(feat, cls, (int)C, n, D, hw, sums, st);
+    default: return launch_accum<4, 4, 8, true>(feat, cls, (int)C, n, D, hw, sums, st);
   }
 }
 
@@ -409,9 +653,13 @@ int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* v
                "no such updating way of objective vectors %d", mode);
   DIGA_REQUIRE(C >= 1 && n >= 0 && D >= 0, DIGA_ERR_INVALID, "centroid_update: bad sizes");
   if (n == 0) return DIGA_OK;
-  centroid_update_kernel<256><<<(unsigned)C, 256, 0, (cudaStream_t)stream>>>(
-      vec, vecsum, valid, n, C, D, objective_vectors, objective_num, make_rule(mode, start_mean, momentum));
-  DIGA_CHECK_LAUNCH("centroid_update_kernel");
+  if (D > 0) {
+    centroid_update_kernel<256><<<dim3((unsigned)C, (unsigned)((D + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(
+        vec, vecsum, valid, n, C, D, objective_vectors, objective_num, make_rule(mode, start_mean, momentum));
+    DIGA_CHECK_LAUNCH("centroid_update_kernel");
+  }
+  centroid_update_num_kernel<<<(unsigned)((C + 31) / 32), 32, 0, (cudaStream_t)stream>>>(vecsum, valid, n, C, objective_num);
+  DIGA_CHECK_LAUNCH("centroid_update_num_kernel");
   return DIGA_OK;
 }
 
@@ -448,7 +696,8 @@ int diga_centroid_reduce_images(const float* vec, const float* vecsum, const uin
   DIGA_REQUIRE(vec && vecsum && acc, DIGA_ERR_INVALID, "centroid_reduce_images: null pointer");
   DIGA_REQUIRE(C >= 1 && n >= 0 && D >= 0, DIGA_ERR_INVALID, "centroid_reduce_images: bad sizes");
   if (n == 0) return DIGA_OK;
-  centroid_reduce_images_kernel<256><<<(unsigned)C, 256, 0, (cudaStream_t)stream>>>(vec, vecsum, valid, n, C, D, acc);
+  centroid_reduce_images_kernel<256><<<dim3((unsigned)C, (unsigned)((D + 1 + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(
+      vec, vecsum, valid, n, C, D, acc);
   DIGA_CHECK_LAUNCH("centroid_reduce_images_kernel");
   return DIGA_OK;
 }

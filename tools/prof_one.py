@@ -22,6 +22,17 @@ elif which == "select":
     tl = S.block_labels(8, 512, 1024, g)
     for _ in range(3):
         D.consensus_select(tl, wl)
+elif which == "pl":
+    z, z2 = S.logits((4, 19, 1024, 2048), g), S.logits((4, 19, 1024, 2048), g)
+    for _ in range(3):
+        D.pseudo_label(z)
+        D.pseudo_label(z, z2)
+elif which == "cm":
+    import random
+    sl = S.block_labels(8, 512, 1024, g); tl = S.perturb_labels(sl, g)
+    xa, xb = S.images((8, 3, 512, 1024), g), S.images((8, 3, 512, 1024), g)
+    for _ in range(3):
+        D.classmix(sl, xa, xb, tl, rng=random.Random(1), return_mask=False)
 elif which == "plup":
     l1, l2 = S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g)
     for _ in range(3):

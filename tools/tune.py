@@ -87,18 +87,20 @@ def sweep_pl():
 
 def sweep_accum():
     g = S.gen(3, dev)
-    for (n, d, h, w) in ((8, 2048, 65, 129), (1, 2048, 65, 129), (8, 256, 65, 129), (8, 2048, 64, 128)):
+    for (n, d, h, w) in ((8, 2048, 65, 129), (8, 2048, 64, 128), (1, 2048, 65, 129)):
         feat = S.features((n, d, h, w), g)
         cls = torch.randint(0, 19, (n, h * w), device=dev, dtype=torch.uint8)
         sums = torch.empty((n, 19, d), device=dev)
-        for variant in range(8):
+        for variant in (0, 2, 6, 9):
             L.set_tunable("accum_variant", variant)
             ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
             report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "random"}, ms, feat.numel() * 4)
-        cls2 = (torch.arange(h * w, device=dev) // 200 % 19).to(torch.uint8).repeat(n, 1).contiguous()
-        L.set_tunable("accum_variant", 0)
-        ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls2.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
-        report("centroid_accum", {"variant": 0, "shape": [n, d, h, w], "labels": "runs of 200"}, ms, feat.numel() * 4)
+        blk = S.block_labels(n, h, w, S.gen(9, dev), 4, 19, 0.1)           # 32x32 image blocks at stride 8
+        cls2 = blk.reshape(n, h * w).to(torch.uint8).contiguous()
+        for variant in (0, 2, 6, 9):
+            L.set_tunable("accum_variant", variant)
+            ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls2.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
+            report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "4x4 blocks"}, ms, feat.numel() * 4)
     L.set_tunable("accum_variant", 0)
 
 
