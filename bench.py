@@ -120,16 +120,34 @@ def max_over_ranks(x: float, world: int, device) -> float:
     return float(t.item())
 
 
-def time_loop(fn, iters, warmup, world=1, device=None):
-    """CUDA-event timing of ``iters`` calls, barrier + synchronize on both sides, max over ranks -> ms per call."""
+def time_loop(fn, iters, warmup, world=1, device=None, graph=False):
+    """CUDA-event timing of ``iters`` calls, barrier + synchronize on both sides, max over ranks -> ms per call.
+    ``graph=True`` captures one call (a sync-free public-API call) in a CUDA graph and times its replays, which removes
+    the host-side launch gaps of the Python call chain; the eager figure is reported next to it by the caller."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                keep = fn()                                    # noqa: F841  (outputs stay alive with the graph)
+        torch.cuda.current_stream().wait_stream(side)
+        call = gph.replay
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+    else:
+        call = fn
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        fn()
+        call()
     e1.record()
     torch.cuda.synchronize()
     barrier(world)
@@ -231,24 +249,28 @@ def bench_stages(D, S, dev, peak, world, quick):
     iters, warm = (10, 3) if quick else (30, 5)
     out = {}
 
-    def add(name, px, bytes_per_px, ms, unit="px", extra=None):
+    def add(name, px, bytes_per_px, fn, unit="px", extra=None, sync_free=True):
+        """Times the public-API call ``fn``: replayed from a CUDA graph when it is sync-free (``ms``), eagerly otherwise;
+        the eager figure (Python launch chain included) is always reported as ``eager_ms``."""
+        eager = time_loop(fn, iters, warm, world, dev)
+        ms = time_loop(fn, iters, warm, world, dev, graph=True) if sync_free else eager
         gbs = px * bytes_per_px / (ms * 1e-3) / 1e9
-        out[name] = {"px_per_s": px / (ms * 1e-3) * world, "unit": f"{unit}/s (all ranks)", "ms": ms,
+        out[name] = {"px_per_s": px / (ms * 1e-3) * world, "unit": f"{unit}/s (all ranks)", "ms": ms, "eager_ms": eager,
                      "algo_bytes_per_px": bytes_per_px, "gbs_per_gpu": gbs, "frac_hbm": gbs / peak}
         if extra:
-            out[name].update(extra)
+            out[name].update(extra(ms) if callable(extra) else extra)
 
     # a3 pseudo-label at 2048x1024, one and two scales (config 5 resolution), 4 images per call
     n, hh, ww = 4, 1024, 2048
     z = S.logits((n, C, hh, ww), g)
     z2 = S.logits((n, C, hh, ww), g)
-    add("pseudo_label_1scale", n * hh * ww, 4 * C + 5, time_loop(lambda: D.pseudo_label(z), iters, warm, world, dev))
-    add("pseudo_label_2scale", n * hh * ww, 8 * C + 5, time_loop(lambda: D.pseudo_label(z, z2), iters, warm, world, dev))
+    add("pseudo_label_1scale", n * hh * ww, 4 * C + 5, lambda: D.pseudo_label(z))
+    add("pseudo_label_2scale", n * hh * ww, 8 * C + 5, lambda: D.pseudo_label(z, z2))
     del z, z2
-    # fused two-scale from stride-8 logits (next row f1): 5 B/px of HBM writes only
+    # fused two-scale from stride-8 logits (next row f1): 5 B/px of HBM writes only, ALU-bound
     l1, l2 = S.logits((n, C, 129, 257), g), S.logits((n, C, 65, 129), g)
-    add("pseudo_label_fused_upsample", n * hh * ww, 5,
-        time_loop(lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww)), iters, warm, world, dev))
+    add("pseudo_label_fused_upsample", n * hh * ww, 5, lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww)),
+        extra={"note": "replaces two bilinear up-samplings (2 x 76 B/px written + read) and the 157 B/px kernel; ALU-bound"})
 
     # config 3 pieces: B=8 @512x1024, features [8,2048,65,129]
     b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
@@ -256,39 +278,43 @@ def bench_stages(D, S, dev, peak, world, quick):
     tl = S.perturb_labels(sl, g)
     xa, xb = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
     rng = random.Random(1234)
-    add("classmix_dacs_total", b * hh * ww, 72,
-        time_loop(lambda: D.classmix(sl, xa, xb, tl, rng=rng, return_mask=False), iters, warm, world, dev),
-        extra={"note": "presence kernel (8 B/px) + host class choice + blend (64 B/px); includes the one D2H sync"})
+    add("classmix_dacs_total", b * hh * ww, 68, lambda: D.classmix(sl, xa, xb, tl, rng=rng, return_mask=False), sync_free=False,
+        extra={"note": "presence kernel (8 B/px) + D2H of 32 B/image + host random.sample + blend (60 B/px); one host sync"})
     from diga_b200.classmix import present_classes, select_classes
     classes = select_classes(present_classes(sl), rng)
     add("classmix_dacs_blend_kernel", b * hh * ww, 60,
-        time_loop(lambda: D.classmix(sl, xa, xb, tl, classes=classes, return_mask=False), iters, warm, world, dev))
+        lambda: D.classmix(sl, xa, xb, tl, classes=classes, return_mask=False, assume_labelled=True))
     del xa, xb
 
     feat = S.features((b, d, h, w), g)
     cf = D.Class_Features(C, d)
     cf.objective_vectors = S.centroids(C, d, g)
-    add("proto_distance_softmax_d2048", b * h * w, d * 4 + C * 4,
-        time_loop(lambda: cf.get_centroid_weight(feat), iters, warm, world, dev), unit="feature-px")
+    add("proto_distance_softmax_d2048", b * h * w, d * 4 + C * 4, lambda: cf.get_centroid_weight(feat), unit="feature-px")
     wl = cf.get_centroid_weight(feat)
-    add("consensus_select", b * hh * ww, 24, time_loop(lambda: D.consensus_select(tl, wl), iters, warm, world, dev))
+    add("consensus_select", b * hh * ww, 24, lambda: D.consensus_select(tl, wl),
+        extra={"note": "ALU-bound: 19 classes x (FMUL+FFMA+compare) per pixel on bit-exact interpolated weights"})
 
-    logits_lo = S.logits((b, C, h, w), g)
-    ms = time_loop(lambda: cf.update_from_features(feat, logits_lo, None, "mean"), iters, warm, world, dev)
-    add("centroid_accumulate_update_d2048", b * h * w, d * 4 + C * 4 + 1, ms, unit="feature-px",
-        extra={"images_per_s": b / (ms * 1e-3) * world})
+    # centroid accumulation + running update: i.i.d. random classes (worst case for the shared-memory accumulators)
+    # and segmentation-like maps (4x4 feature-pixel blocks = 32x32 image blocks)
+    logits_iid = S.logits((b, C, h, w), g)
+    blocks = S.block_labels(b, h, w, g, 4, C, 0.0)
+    logits_blk = S.logits((b, C, h, w), g) + 12.0 * torch.nn.functional.one_hot(blocks, C).permute(0, 3, 1, 2).float()
+    per_img = lambda ms: {"images_per_s": b / (ms * 1e-3) * world}
+    add("centroid_accumulate_update_d2048_iid_classes", b * h * w, d * 4 + C * 4 + 1,
+        lambda: cf.update_from_features(feat, logits_iid, None, "mean"), unit="feature-px", extra=per_img)
+    add("centroid_accumulate_update_d2048_blocky_classes", b * h * w, d * 4 + C * 4 + 1,
+        lambda: cf.update_from_features(feat, logits_blk, None, "mean"), unit="feature-px", extra=per_img)
 
     # config 4 shape of the exchange: mean pass + ONE all-reduce of [19, D+1] (NCCL over NVLink when world > 1)
     acc = P.new_mean_accumulator(C, d, dev)
 
     def mean_pass():
         acc.zero_()
-        cf.accumulate_mean_pass(acc, feat, logits_lo)
+        cf.accumulate_mean_pass(acc, feat, logits_iid)
         return P.finish_mean_pass(acc)
 
-    ms = time_loop(mean_pass, iters, warm, world, dev)
-    add("centroid_mean_pass_allreduce_d2048", b * h * w, d * 4 + C * 4 + 1, ms, unit="feature-px",
-        extra={"images_per_s": b / (ms * 1e-3) * world, "allreduce_bytes": C * (d + 1) * 4})
+    add("centroid_mean_pass_allreduce_d2048", b * h * w, d * 4 + C * 4 + 1, mean_pass, unit="feature-px", sync_free=(world == 1),
+        extra=lambda ms: {"images_per_s": b / (ms * 1e-3) * world, "allreduce_bytes": C * (d + 1) * 4})
     return out
 
 

@@ -4,6 +4,8 @@ Host side mirrors the reference's interface for this path:
 
 * ``diga_b200.util.loss.distillation_loss``          <- ``util/loss.py:125``
 * ``diga_b200.util.utils.process_label``             <- ``util/utils.py:158``
+* ``diga_b200.util.loss.cross_entropy2d``            <- ``util/loss.py:48``   (next row f2)
+* ``diga_b200.util.utils.update_teacher_params``     <- ``util/utils.py:103`` (next row f4)
 * ``diga_b200.calc_centroids.Class_Features`` / ``calc_centroids`` <- ``calc_centroids.py:84`` / ``:17``
 * ``diga_b200.classmix.classmix``                    <- inline block ``train_DiGA_gta2city_self_training.py:259-275, 306-325``
 * ``diga_b200.selection.consensus_select``           <- inline block ``:298-304``
@@ -17,9 +19,10 @@ from .calc_centroids import Class_Features, calc_centroids
 from .classmix import classmix
 from .pseudolabel import pseudo_label, pseudo_label_two_scale
 from .selection import consensus_select
-from .util.loss import distillation_loss, distillation_loss_and_grad
-from .util.utils import process_label
+from .util.loss import cross_entropy2d, distillation_loss, distillation_loss_and_grad
+from .util.utils import process_label, update_teacher_params
 
 __all__ = ["Class_Features", "calc_centroids", "classmix", "pseudo_label", "pseudo_label_two_scale",
-           "consensus_select", "distillation_loss", "distillation_loss_and_grad", "process_label"]
+           "consensus_select", "distillation_loss", "distillation_loss_and_grad", "process_label", "cross_entropy2d",
+           "update_teacher_params"]
 __version__ = "0.1.0"

@@ -1,7 +1,7 @@
 """ctypes binding of ``libdiga_b200.so`` (the C ABI declared in ``include/diga_b200.h``).
 
 There is no CPU fallback and no alternative backend: if the shared library has not been built
-(``python -m diga_b200.build``) importing this module raises, and every wrapper refuses non-CUDA tensors.
+(``python diga_b200/build.py``) importing this module raises, and every wrapper refuses non-CUDA tensors.
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdiga_b200.so")
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m diga_b200.build` "
+        f"{LIB_PATH} not found: the CUDA extension is not built. Run `python diga_b200/build.py` "
         "(nvcc, sm_100a). diga_b200 has no CPU or PyTorch fallback.")
 
 lib = C.CDLL(LIB_PATH)
@@ -51,6 +51,10 @@ SIGNATURES = {
     "diga_consensus_select": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "diga_upsample_bilinear": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "diga_pseudo_label_upsampled": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_ce_workspace_bytes": (C.c_size_t, []),
+    "diga_cross_entropy2d_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
+    "diga_cross_entropy2d_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
+    "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -110,11 +114,20 @@ def i64c(t):
 _workspaces = {}
 
 
-def kd_workspace(device: torch.device) -> torch.Tensor:
-    """Zero-initialised KD reduction workspace, one per (device, stream)."""
-    key = (device.index, stream())
+def _workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (kind, device.index, stream())
     ws = _workspaces.get(key)
     if ws is None:
-        ws = torch.zeros(int(lib.diga_kd_workspace_bytes()), dtype=torch.uint8, device=device)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def kd_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised KD reduction workspace, one per (device, stream)."""
+    return _workspace("kd", int(lib.diga_kd_workspace_bytes()), device)
+
+
+def ce_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised cross-entropy reduction workspace, one per (device, stream)."""
+    return _workspace("ce", int(lib.diga_ce_workspace_bytes()), device)

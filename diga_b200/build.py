@@ -1,6 +1,7 @@
 """Build ``libdiga_b200.so`` in-tree with nvcc for sm_100a.
 
-``python -m diga_b200.build`` (or ``__graft_entry__.build()``).  One nvcc process per ``.cu`` file in
+``python diga_b200/build.py`` (or ``__graft_entry__.build()``; run it by path — ``python -m diga_b200.build`` imports the
+package first, which refuses to load when the library is missing or stale).  One nvcc process per ``.cu`` file in
 parallel, then one link step.  Objects are rebuilt only when the source (or a header) is newer.
 nvcc cross-compiles without a GPU, so this runs in the build container and the resulting ``.so``
 travels to the GPU box with the repo snapshot.

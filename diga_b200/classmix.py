@@ -47,7 +47,7 @@ def select_classes(present, rng=_random):
     return chosen
 
 
-def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True):
+def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True, assume_labelled=False):
     """ClassMix mask build + blend.
 
     ``slabel [B,H,W]`` int64 source labels; ``a``, ``b`` ``[B,CH,H,W]`` fp32; optional ``tlabel [B,H,W]`` int64.
@@ -55,6 +55,9 @@ def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=T
     the reference expression); with ``tlabel``: ``mixlabel = where(mask, slabel, tlabel)``.
     Returns ``(mask, mix)`` or ``(mask, mix, mixlabel)``; ``mix`` is ``None`` when every label is 255, the case
     in which the reference never creates the tensor (:271 / :321).
+
+    ``classes`` (per-image lists) skips the presence pass and the host draw; the all-255 test then needs its own
+    device reduction + sync unless ``assume_labelled=True`` promises that some label differs from 255.
     """
     L.require_cuda(slabel, a, b, tlabel, what="classmix input")
     lab = L.i64c(slabel)
@@ -71,7 +74,7 @@ def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=T
     if fa.shape != fb.shape or fa.shape[0] != bsz or fa[0, 0].numel() != hw:
         raise ValueError("classmix: image / label shapes do not match")
     if present is None:
-        all_ignore = bool(torch.all(torch.eq(lab, IGNORE)))
+        all_ignore = False if assume_labelled else bool(torch.all(torch.eq(lab, IGNORE)))
     else:
         all_ignore = all(p == [IGNORE] for p in present)
     mask = torch.empty(lab.shape, dtype=torch.float32, device=lab.device) if return_mask else None

@@ -68,3 +68,42 @@ def distillation_loss_and_grad(teacher_out, student_out, scale=0.5, grad_scale=1
     L.check(L.lib.diga_kd_fwd_bwd(t.data_ptr(), s.data_ptr(), n2, c, h * w, float(scale), float(grad_scale),
                                   loss.data_ptr(), ds.data_ptr(), L.kd_workspace(s.device).data_ptr(), L.stream()))
     return loss, ds
+
+
+class _CrossEntropy2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, target, weight, size_average):
+        x = L.f32c(input.detach())
+        t = L.i64c(target)
+        wt = None if weight is None else L.f32c(weight.detach()).to(x.device)
+        n, c, h, w = x.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        denom = torch.empty((), dtype=torch.float32, device=x.device)
+        L.check(L.lib.diga_cross_entropy2d_fwd(x.data_ptr(), t.data_ptr(), L.ptr(wt), n, c, h * w, int(bool(size_average)),
+                                               loss.data_ptr(), denom.data_ptr(), L.ce_workspace(x.device).data_ptr(),
+                                               L.stream()))
+        ctx.save_for_backward(x, t, denom)
+        ctx.weight = wt
+        ctx.size_average = int(bool(size_average))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, t, denom = ctx.saved_tensors
+        n, c, h, w = x.shape
+        g = grad_out.to(dtype=torch.float32, device=x.device).contiguous()
+        dx = torch.empty_like(x)
+        L.check(L.lib.diga_cross_entropy2d_bwd(x.data_ptr(), t.data_ptr(), L.ptr(ctx.weight), n, c, h * w, ctx.size_average,
+                                               g.data_ptr(), denom.data_ptr(), dx.data_ptr(), L.stream()))
+        return dx, None, None, None
+
+
+def cross_entropy2d(input, target, weight=None, size_average=True):
+    """``util.loss.cross_entropy2d`` (G/util/loss.py:48-62): pixel-wise cross entropy with ``ignore_index=255``;
+    pixels with a negative target are dropped; ``size_average`` divides by the number of pixels with target >= 0
+    (ignore-255 pixels included, exactly like the reference).  ``input [N,C,H,W]`` fp32, ``target [N,H,W]`` int64."""
+    L.require_cuda(input, target, weight, what="cross_entropy2d input")
+    if input.dim() != 4 or target.dim() != 3 or input.shape[0] != target.shape[0] or input.shape[2:] != target.shape[1:]:
+        raise ValueError(f"cross_entropy2d: expected [N,C,H,W] logits and [N,H,W] targets, got {tuple(input.shape)} and "
+                         f"{tuple(target.shape)}")
+    return _CrossEntropy2d.apply(input, target, weight, size_average)

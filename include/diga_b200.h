@@ -166,6 +166,31 @@ int diga_pseudo_label_upsampled(const float* logits, int64_t h1, int64_t w1, con
                                 int64_t w2, int64_t n, int64_t C, int64_t H, int64_t W, uint8_t* label_u8,
                                 int64_t* label_i64, float* conf, diga_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2 (next row)  cross_entropy2d — util/loss.py:48-62
+ *   logits [n, C, hw] fp32, target [n, hw] int64 (255 = ignore, negative = dropped), weight [C] fp32 or NULL.
+ *   fwd: loss_out[0] = sum_{valid} -w[t] log_softmax(logits)[t]  (/ #(target >= 0) if size_average);
+ *        denom_out[0] = #(target >= 0) (kept for the backward).  workspace: diga_ce_workspace_bytes(), zero-filled
+ *        once by the caller (the kernel leaves it zeroed).
+ *   bwd: dlogits = upstream[0] * dloss/dlogits; `upstream` and `denom` are DEVICE scalars.
+ * ------------------------------------------------------------------------------------------ */
+size_t diga_ce_workspace_bytes(void);
+int diga_cross_entropy2d_fwd(const float* logits, const int64_t* target, const float* weight, int64_t n, int64_t C,
+                             int64_t hw, int size_average, float* loss_out, float* denom_out, void* workspace,
+                             diga_stream_t stream);
+int diga_cross_entropy2d_bwd(const float* logits, const int64_t* target, const float* weight, int64_t n, int64_t C,
+                             int64_t hw, int size_average, const float* upstream, const float* denom, float* dlogits,
+                             diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f4 (next row)  EMA teacher update — util/utils.py:103-116
+ *   For each of `count` parameter tensors: teacher = alpha * teacher + (1 - alpha) * student (fp32, in place,
+ *   separately rounded like the torch expression).  The three tables live in HOST memory (device pointers and
+ *   element counts) and are consumed before the call returns; 48 tensors per launch.
+ * ------------------------------------------------------------------------------------------ */
+int diga_ema_update(float* const* teacher_host, const float* const* student_host, const int64_t* numel_host,
+                    int64_t count, double alpha, diga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

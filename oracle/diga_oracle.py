@@ -294,6 +294,43 @@ def classmix(slabel: torch.Tensor, a: torch.Tensor, b: torch.Tensor, tlabel: Opt
 
 
 # --------------------------------------------------------------------------------------
+# f2  cross_entropy2d   (G/util/loss.py:48-62)        f4  EMA teacher   (G/util/utils.py:103-116)
+# --------------------------------------------------------------------------------------
+def cross_entropy2d(input, target, weight=None, size_average=True):
+    """Pixel-wise CE with ignore_index 255; negative targets dropped; the mean divides by #(target >= 0).
+    G/util/loss.py:48-62."""
+    n, c, h, w = input.size()
+    log_p = F.log_softmax(input, dim=1)                                               # :50
+    log_p = log_p.transpose(1, 2).transpose(2, 3).contiguous().view(-1, c)            # :51
+    keep = target.contiguous().view(n * h * w, 1).repeat(1, c) >= 0                   # :52
+    log_p = log_p[keep].view(-1, c)                                                   # :52-54
+    mask = target >= 0                                                                # :56
+    loss = F.nll_loss(log_p, target[mask], ignore_index=IGNORE, weight=weight, reduction="sum")   # :58-59
+    if size_average:                                                                  # :60-61
+        loss = loss / mask.data.sum()
+    return loss
+
+
+def ema_alpha(iteration, stage0=True, mean=False, replace=False):
+    """G/util/utils.py:105-112."""
+    if stage0 == True:      # noqa: E712
+        return min(1 - 1 / (iteration + 1), 0.999)
+    if mean == True:        # noqa: E712
+        return 0.9
+    if replace == True:     # noqa: E712
+        return 0.0
+    return 0.999
+
+
+def update_teacher_params(teacher, student, iteration, stage0=True, mean=False, replace=False):
+    """EMA of the student's parameters into the teacher; G/util/utils.py:103-116."""
+    alpha = ema_alpha(iteration, stage0, mean, replace)
+    for tp, sp in zip(teacher.parameters(), student.parameters()):                     # :113
+        tp.data[:] = alpha * tp[:].data[:] + (1 - alpha) * sp[:].data[:]               # :115
+    return teacher
+
+
+# --------------------------------------------------------------------------------------
 # drivers used as CPU baseline / multi-rank checks
 # --------------------------------------------------------------------------------------
 def centroid_pass(feats: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], numbers=19, feat_dim=256,

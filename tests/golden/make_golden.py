@@ -74,6 +74,33 @@ def main():
         (loss * 0.25).backward()                       # upstream grad 0.25 (lambda_distil-like)
         save(tag, teacher=t, student=s, scale=scale, upstream=0.25, loss=loss, grad=s.grad)
 
+    # ---- f2 cross_entropy2d (G/util/loss.py:48-62) ---------------------------------------------
+    for tag, shape, use_w, avg in (("ce_c19", (3, 19, 7, 10), False, True), ("ce_weighted_sum", (2, 16, 5, 6), True, False)):
+        x = (3.0 * torch.randn(shape, generator=gen)).requires_grad_(True)
+        tgt = torch.randint(0, shape[1], (shape[0], shape[2], shape[3]), generator=gen)
+        tgt[torch.rand(tgt.shape, generator=gen) < 0.2] = 255
+        tgt[0, 0, :3] = -1                                   # dropped pixels (target >= 0 mask, :52,:56)
+        wt = (0.5 + torch.rand(shape[1], generator=gen)) if use_w else None
+        loss = ref.cross_entropy2d(x, tgt, weight=wt, size_average=avg)
+        (loss * 0.7).backward()
+        save(tag, input=x, target=tgt, weight=(wt if use_w else torch.zeros(0)), size_average=avg, upstream=0.7,
+             loss=loss, grad=x.grad)
+
+    # ---- f4 EMA teacher update (G/util/utils.py:103-116) ---------------------------------------
+    def small_net(seed):
+        torch.manual_seed(seed)
+        return nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Conv2d(8, 5, 1), nn.Linear(7, 3))
+    teacher, student = small_net(1), small_net(2)
+    before = [p.detach().clone().reshape(-1) for p in teacher.parameters()]
+    stud = [p.detach().clone().reshape(-1) for p in student.parameters()]
+    after = {}
+    for it, kw in ((0, {}), (7, {}), (5000, {}), (3, {"stage0": False, "mean": True}), (3, {"stage0": False})):
+        t2 = small_net(1)
+        ref.update_teacher_params(t2, student, it, **kw)
+        after[f"after_it{it}_{'_'.join(k for k in kw) or 'stage0'}"] = torch.cat([p.detach().reshape(-1) for p in t2.parameters()])
+    save("ema", teacher=torch.cat(before), student=torch.cat(stud),
+         sizes=np.array([p.numel() for p in teacher.parameters()]), **after)
+
     # ---- process_label (G/util/utils.py:158-163) -------------------------------------------
     lab = torch.randint(0, 19, (2, 1, 5, 7), generator=gen).float()
     lab[0, 0, 0, :3] = 255.0

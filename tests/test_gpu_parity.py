@@ -475,6 +475,73 @@ def test_consensus_golden(D, golden):
     assert mism.sum() <= 2
 
 
+# ------------------------------------------------------------------------------------------------ next rows f2 / f4
+@pytest.mark.parametrize("name", ["ce_c19", "ce_weighted_sum"])
+def test_cross_entropy2d_golden(D, golden, name):
+    g = golden(name)
+    x = T(g["input"], dev()).requires_grad_(True)
+    wt = T(g["weight"], dev()) if g["weight"].size else None
+    loss = D.cross_entropy2d(x, T(g["target"], dev()), weight=wt, size_average=bool(g["size_average"]))
+    (loss * float(g["upstream"])).backward()
+    assert_rel(loss.item(), g["loss"], what="loss")
+    assert_normwise(x.grad, g["grad"], what="grad")
+    # ignored / dropped pixels receive exactly zero gradient
+    dead = (g["target"] < 0) | (g["target"] == 255)
+    assert float(x.grad.permute(0, 2, 3, 1)[T(dead, dev())].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(8, 19, 512, 1024), (2, 19, 33, 65), (1, 16, 7, 9), (2, 5, 4, 6)])
+def test_cross_entropy2d_vs_oracle_on_gpu(D, shape):
+    from diga_b200 import synthetic as S
+    g = S.gen(31, "cuda")
+    x = S.logits(shape, g)
+    tgt = S.block_labels(shape[0], shape[2], shape[3], g, 8, shape[1], 0.15)
+    xo = x.clone().requires_grad_(True)
+    lo = O.cross_entropy2d(xo, tgt)
+    (lo * 1.5).backward()
+    xg = x.clone().requires_grad_(True)
+    lg = D.cross_entropy2d(xg, tgt)
+    (lg * 1.5).backward()
+    assert_rel(lg.item(), lo.item(), what="loss")
+    assert_normwise(xg.grad, xo.grad, what="grad")
+    assert D.cross_entropy2d(x, tgt).item() == lg.item()           # deterministic reduction
+
+
+def test_ema_teacher_update_golden_bit_exact(D, golden):
+    import torch.nn as nn
+    g = golden("ema")
+
+    def build(flat):
+        net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Conv2d(8, 5, 1), nn.Linear(7, 3))
+        off = 0
+        for p, n in zip(net.parameters(), g["sizes"]):
+            p.data.copy_(T(flat[off:off + n]).reshape(p.shape))
+            off += int(n)
+        return net.to(dev())
+    for it, kw in ((0, {}), (7, {}), (5000, {}), (3, {"stage0": False, "mean": True}), (3, {"stage0": False})):
+        key = f"after_it{it}_{'_'.join(k for k in kw) or 'stage0'}"
+        teacher, student = build(g["teacher"]), build(g["student"])
+        out = D.update_teacher_params(teacher, student, it, **kw)
+        assert out is teacher
+        got = torch.cat([p.detach().reshape(-1) for p in teacher.parameters()]).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32)), key
+
+
+def test_ema_many_tensors_vs_oracle(D):
+    """More tensors than fit one launch (48), odd sizes, unaligned tails."""
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 3, 4, 5, 63, 64, 65, 1000, 4097, 300000] * 11            # 110 tensors
+    ts = [torch.randn(n, generator=g) for n in sizes]
+    ss = [torch.randn(n, generator=g) for n in sizes]
+    alpha = min(1 - 1 / (123 + 1), 0.999)
+    want = [alpha * t + (1 - alpha) * s for t, s in zip(ts, ss)]
+    from diga_b200.util.utils import ema_update_tensors
+    tg, sg = [t.to(dev()) for t in ts], [s.to(dev()) for s in ss]
+    ema_update_tensors(tg, sg, alpha)
+    for a, b in zip(tg, want):
+        assert np.array_equal(a.cpu().numpy().view(np.uint32), b.numpy().view(np.uint32))
+
+
 # ------------------------------------------------------------------------------------------------ boundary behaviour
 def test_no_cpu_fallback(D):
     with pytest.raises(RuntimeError):

@@ -31,6 +31,45 @@ def test_kd_matches_reference_bitwise(golden, name):
     assert np.abs(cf - g["grad"]).max() <= 1e-5 * np.abs(g["grad"]).max()
 
 
+@pytest.mark.parametrize("name", ["ce_c19", "ce_weighted_sum"])
+def test_cross_entropy2d_matches_reference_bitwise(golden, name):
+    g = golden(name)
+    x = T(g["input"]).requires_grad_(True)
+    wt = T(g["weight"]) if g["weight"].size else None
+    loss = O.cross_entropy2d(x, T(g["target"]), weight=wt, size_average=bool(g["size_average"]))
+    (loss * float(g["upstream"])).backward()
+    assert np.array_equal(loss.detach().numpy(), g["loss"])
+    assert np.array_equal(x.grad.numpy(), g["grad"])
+    assert (g["target"] < 0).any() and (g["target"] == 255).any()
+
+
+def ema_nets(g):
+    import torch.nn as nn
+
+    def build(flat):
+        net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Conv2d(8, 5, 1), nn.Linear(7, 3))
+        off = 0
+        for p, n in zip(net.parameters(), g["sizes"]):
+            p.data.copy_(T(flat[off:off + n]).reshape(p.shape))
+            off += int(n)
+        return net
+    return build
+
+
+def test_ema_teacher_update_matches_reference_bitwise(golden):
+    g = golden("ema")
+    build = ema_nets(g)
+    cases = {"after_it0_stage0": (0, {}), "after_it7_stage0": (7, {}), "after_it5000_stage0": (5000, {}),
+             "after_it3_stage0_mean": (3, {"stage0": False, "mean": True}), "after_it3_stage0": (3, {"stage0": False})}
+    # key naming in the fixture: "_".join(kwargs) or "stage0"
+    for key, (it, kw) in cases.items():
+        fixture_key = f"after_it{it}_{'_'.join(k for k in kw) or 'stage0'}"
+        teacher, student = build(g["teacher"]), build(g["student"])
+        O.update_teacher_params(teacher, student, it, **kw)
+        got = torch.cat([p.detach().reshape(-1) for p in teacher.parameters()]).numpy()
+        assert np.array_equal(got, g[fixture_key]), key
+
+
 def test_process_label(golden):
     g = golden("process_label")
     assert np.array_equal(O.process_label(T(g["label"])).numpy(), g["onehot"])
