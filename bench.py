@@ -294,6 +294,33 @@ def bench_stages(D, S, dev, peak, world, quick):
     add("consensus_select", b * hh * ww, 24, lambda: D.consensus_select(tl, wl),
         extra={"note": "ALU-bound: 19 classes x (FMUL+FFMA+compare) per pixel on bit-exact interpolated weights"})
 
+    # next rows f2 / f4: cross_entropy2d fwd+bwd on the student logits of config 2, EMA teacher update of a
+    # ResNet-101-sized parameter set (44.5 M fp32 parameters in 314 tensors)
+    del feat
+    xs = S.logits((4, C, hh, ww), g)
+    ce_t = S.block_labels(4, hh, ww, g)
+    upc = torch.tensor(1.0, device=dev)
+
+    def ce_step():
+        x = xs.detach().requires_grad_(True)
+        loss = D.cross_entropy2d(x, ce_t)
+        (grad,) = torch.autograd.grad(loss, x, grad_outputs=upc)
+        return loss, grad
+
+    add("cross_entropy2d_fwd_bwd", 4 * hh * ww, (4 * C + 8) + (8 * C + 8), ce_step)
+    del xs
+    sizes = [64 * 3 * 49] + [256 * 64, 64 * 64 * 9, 64 * 256, 256, 256, 64] * 3 + [512 * 128 * 4, 128 * 128 * 9, 512] * 4 + \
+            [1024 * 256, 256 * 256 * 9, 256 * 1024, 1024, 1024, 256] * 23 + [2048 * 512, 512 * 512 * 9, 512 * 2048, 2048] * 3 + \
+            [19 * 2048 * 9] * 4
+    from diga_b200.util.utils import ema_update_tensors
+    tea = [torch.randn(sz, device=dev) for sz in sizes]
+    stu = [torch.randn(sz, device=dev) for sz in sizes]
+    n_par = sum(sizes)
+    add("ema_teacher_update", n_par, 12, lambda: ema_update_tensors(tea, stu, 0.999), unit="parameters",
+        extra={"tensors": len(sizes), "parameters": n_par})
+    del tea, stu
+    feat = S.features((b, d, h, w), g)
+
     # centroid accumulation + running update: i.i.d. random classes (worst case for the shared-memory accumulators)
     # and segmentation-like maps (4x4 feature-pixel blocks = 32x32 image blocks)
     logits_iid = S.logits((b, C, h, w), g)

@@ -146,7 +146,7 @@ static int launch_ce(const float* logits, const int64_t* target, const float* we
   }
   const int64_t total = n * (hw / VEC);
   int64_t grid = (total + BLOCK - 1) / BLOCK;
-  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * tunable(GRAD ? "ce_waves_bwd" : "ce_waves_fwd", GRAD ? 8 : 2);
+  const int64_t cap = (int64_t)sm_count() * blocks_per_sm * tunable(GRAD ? "ce_waves_bwd" : "ce_waves_fwd", GRAD ? 8 : 1);
   if (grid > cap) grid = cap;
   if (grid > kCeMaxPartials) grid = kCeMaxPartials;
   if (grid < 1) grid = 1;

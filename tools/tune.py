@@ -132,6 +132,22 @@ def sweep_cm():
     report("class_presence", {}, timeit(lambda: L.check(L.lib.diga_class_presence(sl.data_ptr(), b, hh * ww, bm.data_ptr(), fl.data_ptr(), L.stream()))), px * 8)
 
 
+def sweep_ce():
+    g = S.gen(6, dev)
+    n, hh, ww = 8, 512, 1024
+    x = S.logits((n, 19, hh, ww), g); t = S.block_labels(n, hh, ww, g)
+    ws = L.ce_workspace(dev); loss = torch.empty((), device=dev); den = torch.empty((), device=dev)
+    dx = torch.empty_like(x); up = torch.tensor(1.0, device=dev)
+    px = n * hh * ww
+    for vec, waves in itertools.product((2, 1), (1, 2, 4, 8)):
+        L.set_tunable("ce_vec", vec); L.set_tunable("ce_waves_fwd", waves); L.set_tunable("ce_waves_bwd", waves)
+        report("ce_fwd", {"vec": vec, "waves": waves}, timeit(lambda: L.check(L.lib.diga_cross_entropy2d_fwd(
+            x.data_ptr(), t.data_ptr(), None, n, 19, hh * ww, 1, loss.data_ptr(), den.data_ptr(), ws.data_ptr(), L.stream()))), px * 84)
+        report("ce_bwd", {"vec": vec, "waves": waves}, timeit(lambda: L.check(L.lib.diga_cross_entropy2d_bwd(
+            x.data_ptr(), t.data_ptr(), None, n, 19, hh * ww, 1, up.data_ptr(), den.data_ptr(), dx.data_ptr(), L.stream()))), px * 160)
+    L.set_tunable("ce_vec", 2); L.set_tunable("ce_waves_fwd", 1); L.set_tunable("ce_waves_bwd", 8)
+
+
 def sweep_misc():
     g = S.gen(5, dev)
     b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
@@ -149,6 +165,6 @@ def sweep_misc():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kd", "pl", "accum", "cm", "misc"]
+    which = sys.argv[1:] or ["kd", "pl", "accum", "cm", "ce", "misc"]
     for name in which:
         globals()["sweep_" + name]()
