@@ -160,6 +160,7 @@ int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const fl
                         const int64_t* tlabel, int64_t B, int64_t channels, int64_t hw, float* mask, float* mix,
                         int64_t* mixlabel, diga_stream_t stream) {
   using namespace diga;
+  if (B == 0 || hw == 0) return DIGA_OK;      // empty batch: pointers may be NULL
   DIGA_REQUIRE(slabel && lut_host, DIGA_ERR_INVALID, "classmix_blend: null label/lut");
   DIGA_REQUIRE(!mix || (a && b), DIGA_ERR_INVALID, "classmix_blend: mix needs both images");
   DIGA_REQUIRE(!mixlabel || tlabel, DIGA_ERR_INVALID, "classmix_blend: mixlabel needs tlabel");

@@ -222,11 +222,11 @@ namespace diga {
 extern "C" int diga_pseudo_label(const float* logits, const float* logits_ds, int64_t n, int64_t C, int64_t hw,
                                  uint8_t* label_u8, int64_t* label_i64, float* conf, diga_stream_t stream) {
   using namespace diga;
-  DIGA_REQUIRE(logits, DIGA_ERR_INVALID, "pseudo_label: null logits");
   DIGA_REQUIRE(n >= 0 && hw >= 0, DIGA_ERR_INVALID, "pseudo_label: negative size");
   DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "pseudo_label: C=%lld outside [1,%d]", (long long)C,
                DIGA_MAX_CLASSES);
-  if (n == 0 || hw == 0) return DIGA_OK;
+  if (n == 0 || hw == 0) return DIGA_OK;      // empty batch: nothing to read, pointers may be NULL
+  DIGA_REQUIRE(logits, DIGA_ERR_INVALID, "pseudo_label: null logits");
   DIGA_REQUIRE(aligned(logits, 4) && aligned(logits_ds, 4) && aligned(conf, 4) && aligned(label_i64, 8),
                DIGA_ERR_MISALIGNED, "pseudo_label: misaligned pointer");
   cudaStream_t st = (cudaStream_t)stream;

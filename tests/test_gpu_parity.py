@@ -554,6 +554,39 @@ def test_no_cpu_fallback(D):
     assert L.launch_count() == before + 1
 
 
+def test_edge_shapes(D):
+    """Empty batches, single pixels, the maximum class count, images with nothing to accumulate."""
+    z = torch.zeros(0, 19, 8, 8, device=dev())
+    lab, conf = D.pseudo_label(z)
+    assert lab.shape == (0, 8, 8) and conf.shape == (0, 8, 8)
+    assert D.classmix(torch.zeros(0, 4, 4, dtype=torch.int64, device=dev()), torch.zeros(0, 3, 4, 4, device=dev()),
+                      torch.zeros(0, 3, 4, 4, device=dev()))[0].shape == (0, 4, 4)
+    # one pixel, two views
+    t, s = torch.randn(2, 19, 1, 1, device=dev()), torch.randn(2, 19, 1, 1, device=dev())
+    assert_rel(D.distillation_loss(t, s).item(), O.distillation_loss(t, s).item())
+    # 32 classes (the ABI maximum) through the padded instantiation
+    z32 = 3 * torch.randn(2, 32, 9, 11, device=dev())
+    lab32, conf32 = D.pseudo_label(z32)
+    assert torch.equal(lab32.long(), z32.argmax(1))
+    assert_normwise(conf32, torch.softmax(z32, 1).max(1).values)
+    cf = D.Class_Features(32, 256)
+    feat = torch.randn(1, 256, 9, 11, device=dev())
+    cf.objective_vectors = torch.randn(32, 256)
+    ocf = O.ClassFeaturesOracle(32, 256)
+    ocf.objective_vectors = cf.objective_vectors.clone()
+    assert_normwise(cf.feat_centroid_distance(feat), ocf.feat_centroid_distance(feat))
+    # nothing to accumulate: every label disagrees with the prediction -> no vectors, state untouched
+    cf19 = D.Class_Features(19, 64)
+    before = cf19.objective_vectors.clone()
+    f = torch.randn(2, 64, 6, 7, device=dev())
+    out = 3 * torch.randn(2, 19, 6, 7, device=dev())
+    labels = torch.full((2, 1, 6, 7), 255.0, device=dev())
+    vec, ids = cf19.calculate_mean_vector(f, out, labels)
+    assert vec == [] and ids == []
+    cf19.update_from_features(f, out, labels)
+    assert torch.equal(cf19.objective_vectors, before) and float(cf19.objective_vectors_num.sum()) == 0.0
+
+
 def test_streams_and_noncontiguous(D):
     """Launches follow torch's current stream; non-contiguous inputs are accepted like the reference's ops."""
     s = torch.cuda.Stream()
