@@ -48,6 +48,8 @@ SIGNATURES = {
     "diga_onehot_labels": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "diga_proto_workspace_bytes": (C.c_size_t, [_i64, _i64]),
     "diga_proto_distance": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_proto_prepare": (_i, [_p, _i64, _i64, _p, _p]),
+    "diga_proto_distance_prepared": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_consensus_select": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "diga_upsample_bilinear": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "diga_pseudo_label_upsampled": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),

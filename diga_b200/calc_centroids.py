@@ -43,6 +43,7 @@ class Class_Features:
         self.centroid_momentum = 0.0001
         self.valid_classes = list(range(numbers))
         self._proto_ws = None
+        self._proto_key = None      # (data_ptr, tensor version, device) of the centroids the workspace was prepared from
 
     # -- state ----------------------------------------------------------------------------------
     def _to_state(self, value):
@@ -57,6 +58,7 @@ class Class_Features:
     @objective_vectors.setter
     def objective_vectors(self, value):
         self._objective_vectors = self._to_state(value)
+        self._proto_key = None
 
     @property
     def objective_vectors_num(self):
@@ -129,6 +131,7 @@ class Class_Features:
         v = vector.detach().to(device=self._device, dtype=torch.float32).reshape(-1).contiguous()
         if v.numel() != self.feat_dim:
             raise ValueError(f"vector has {v.numel()} elements, centroids have {self.feat_dim}")
+        self._proto_key = None
         L.check(L.lib.diga_centroid_update_single(v.data_ptr(), int(id), self.class_numbers, self.feat_dim,
                                                   self._objective_vectors.data_ptr(),
                                                   self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
@@ -142,6 +145,7 @@ class Class_Features:
         n, c, d = vec.shape
         if d != self.feat_dim:
             raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")
+        self._proto_key = None
         L.check(L.lib.diga_centroid_update(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d,
                                            self._objective_vectors.data_ptr(), self._objective_vectors_num.data_ptr(),
                                            mode, int(bool(start_mean)), float(self.centroid_momentum), L.stream()))
@@ -170,10 +174,17 @@ class Class_Features:
         need = int(L.lib.diga_proto_workspace_bytes(c, d))
         if self._proto_ws is None or self._proto_ws.numel() < need or self._proto_ws.device != f.device:
             self._proto_ws = torch.empty(need, dtype=torch.uint8, device=f.device)
+            self._proto_key = None
         dist = torch.empty((n, c, h, w), dtype=torch.float32, device=f.device) if want_dist else None
         weight = torch.empty((n, c, h, w), dtype=torch.float32, device=f.device) if want_weight else None
-        L.check(L.lib.diga_proto_distance(f.data_ptr(), cen.data_ptr(), n, d, c, h * w, L.ptr(dist), L.ptr(weight),
-                                          self._proto_ws.data_ptr(), L.stream()))
+        # the split centroid operands are rebuilt only when the centroids changed (assignment, in-place torch op, or one
+        # of our own update kernels, which reset the key)
+        key = (cen.data_ptr(), cen._version, f.device, L.stream())
+        if key != self._proto_key:
+            L.check(L.lib.diga_proto_prepare(cen.data_ptr(), c, d, self._proto_ws.data_ptr(), L.stream()))
+            self._proto_key = key
+        L.check(L.lib.diga_proto_distance_prepared(f.data_ptr(), cen.data_ptr(), n, d, c, h * w, L.ptr(dist), L.ptr(weight),
+                                                   self._proto_ws.data_ptr(), L.stream()))
         return dist, weight
 
     def feat_centroid_distance(self, feat):

@@ -12,7 +12,8 @@ namespace diga {
 int tunable(const char* name, int dflt);
 int proto_umma_supported(int64_t n, int64_t D, int64_t C, int64_t hw);
 int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw, float* dist,
-                      float* weight, void* workspace, cudaStream_t st);
+                      float* weight, void* workspace, int prepared, cudaStream_t st);
+int proto_umma_prepare(const float* centroids, int64_t D, int64_t C, void* workspace, cudaStream_t st);
 size_t proto_umma_workspace_bytes(int64_t C, int64_t D);
 
 // Epilogue shared by both kernels: dist -> (dist, softmax(-dist)) for one pixel.
@@ -93,8 +94,8 @@ extern "C" {
 
 size_t diga_proto_workspace_bytes(int64_t C, int64_t D) { return diga::proto_umma_workspace_bytes(C, D); }
 
-int diga_proto_distance(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw, float* dist,
-                        float* weight, void* workspace, diga_stream_t stream) {
+static int proto_distance_impl(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw, float* dist,
+                               float* weight, void* workspace, int prepared, diga_stream_t stream) {
   using namespace diga;
   DIGA_REQUIRE(feat && centroids, DIGA_ERR_INVALID, "proto_distance: null input");
   DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "proto_distance: C=%lld outside [1,%d]", (long long)C,
@@ -105,7 +106,7 @@ int diga_proto_distance(const float* feat, const float* centroids, int64_t n, in
   if (n == 0 || hw == 0 || (!dist && !weight)) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (tunable("proto_path", 0) != 1 && workspace != nullptr && proto_umma_supported(n, D, C, hw))
-    return proto_umma_launch(feat, centroids, n, D, C, hw, dist, weight, workspace, st);
+    return proto_umma_launch(feat, centroids, n, D, C, hw, dist, weight, workspace, prepared, st);
   constexpr int BLOCK = 128, DK = 16;
   dim3 grid((unsigned)((hw + BLOCK - 1) / BLOCK), (unsigned)n);
   DIGA_DISPATCH_C(C, {
@@ -113,6 +114,24 @@ int diga_proto_distance(const float* feat, const float* centroids, int64_t n, in
   });
   DIGA_CHECK_LAUNCH("proto_distance_fp32_kernel");
   return DIGA_OK;
+}
+
+int diga_proto_distance(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw, float* dist,
+                        float* weight, void* workspace, diga_stream_t stream) {
+  return proto_distance_impl(feat, centroids, n, D, C, hw, dist, weight, workspace, 0, stream);
+}
+
+int diga_proto_prepare(const float* centroids, int64_t C, int64_t D, void* workspace, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(centroids && workspace, DIGA_ERR_INVALID, "proto_prepare: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES && D >= 1, DIGA_ERR_INVALID, "proto_prepare: bad sizes");
+  if (!proto_umma_supported(1, D, C, 1)) return DIGA_OK;      // the FP32 kernel reads the centroids directly
+  return proto_umma_prepare(centroids, D, C, workspace, (cudaStream_t)stream);
+}
+
+int diga_proto_distance_prepared(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw,
+                                 float* dist, float* weight, void* workspace, diga_stream_t stream) {
+  return proto_distance_impl(feat, centroids, n, D, C, hw, dist, weight, workspace, 1, stream);
 }
 
 }  // extern "C"

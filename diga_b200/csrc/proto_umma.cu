@@ -44,9 +44,11 @@ constexpr int NPAD = 32;      // classes padded to the MMA N
 constexpr int KC = 32;        // channels per pipeline chunk
 constexpr int KSTEP = 8;      // channels per tcgen05.mma.kind::tf32
 constexpr int SA = 8;         // shared-memory feature stages (135 KB in flight per SM)
-constexpr int SB = 8;         // shared-memory centroid stages: deep enough to hide the L2 -> smem refill latency that
-                              // follows an MMA retirement (with 4 stages that loop alone cost 450 ns per chunk)
-constexpr int ST = 6;         // TMEM A-operand stages (6 x 64 columns + 2 x 32 accumulator columns <= 512)
+constexpr int CPS = 2;        // chunks per operand stage: the MMA warp hands over 64 channels at a time, which halves its
+                              // per-chunk wait / commit overhead (it was the critical path at 32)
+constexpr int ST = 3;         // operand stages: TMEM A operand (3 x 128 columns) paired with a shared-memory centroid stage
+constexpr int SB = ST;        // (one full/empty barrier pair per stage serves both operands)
+constexpr int NACC = 2 * NPAD;   // accumulator columns per tile: [hi*hi + lo*hi | hi*lo]; 6 x 64 + 2 x 64 = 512 columns
 constexpr int NWG = 4;        // converter warpgroups; chunk c is converted by warpgroup c % NWG
 constexpr int BOX_G = KC / 4;                           // channel groups (of 4 rows) per TMA box
 constexpr int BOX_W = TILE_M + 4;                       // 128 pixels + the 0..3 floats below a 16-byte aligned start
@@ -55,16 +57,17 @@ constexpr int A_STAGE_FLOATS = 4 * A_BOX_FLOATS;
 constexpr int A_STAGE_BYTES = A_STAGE_FLOATS * 4;       // 16896
 constexpr int B_TILE_BYTES = NPAD * KSTEP * 4;          // 1024: one [32 x 8] tf32 operand tile
 constexpr int B_KSTEP_BYTES = 2 * B_TILE_BYTES;         // hi tile + lo tile
-constexpr int B_STAGE_BYTES = (KC / KSTEP) * B_KSTEP_BYTES;   // 8192
+constexpr int B_STAGE_BYTES = CPS * (KC / KSTEP) * B_KSTEP_BYTES;   // 16384
 constexpr int CONV_WARPS = 4 * NWG, EPI_WARPS = 4;
 constexpr int WARP_MMA = CONV_WARPS + EPI_WARPS, WARP_LOAD = WARP_MMA + 1, WARP_LOAD_B = WARP_MMA + 2;
 constexpr int THREADS = (WARP_LOAD_B + 1) * 32;         // 736
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_ACC_COL = ST * 64;                   // accumulators behind the A stages
+constexpr int TMEM_STAGE_COLS = CPS * 2 * KC;           // 128: per chunk 32 hi + 32 lo columns
+constexpr int TMEM_ACC_COL = ST * TMEM_STAGE_COLS;      // accumulators behind the A stages
 
 struct Barriers {
   uint64_t a_full[SA], a_empty[SA];
-  uint64_t b_full[SB], b_empty[SB], t_full[ST], t_empty[ST];
+  uint64_t op_full[ST], op_empty[ST];     // A operand in TMEM (4 converter warps) + centroid tile in smem (TMA tx)
   uint64_t acc_full[2], acc_empty[2], norm_full[2];
 };
 
@@ -162,12 +165,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): core matrices of 8 rows x 16 B;
 // LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
-  constexpr uint64_t LBO = (NPAD / 8) * 128;   // 512: [k-half][row-group][8 rows][16 B]
+  constexpr uint64_t LBO = (2 * NPAD / 8) * 128;   // 1024: [k-half][8 row-groups: b_hi rows 0..31, b_lo rows 32..63][8 rows][16 B]
   constexpr uint64_t SBO = 128;
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((LBO >> 4) << 16) | ((SBO >> 4) << 32) | (1ull << 46);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, N = 32, M = 128.
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, both K-major, M = 128, N = 32 or 64.
+constexpr uint32_t idesc_n(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
 
 // ---- operand preparation: centroids [C, D] -> per-8-channel [hi tile | lo tile] in the exact smem layout ------------
 __global__ void proto_prepare_kernel(const float* __restrict__ cen, int nclass, int D, unsigned char* __restrict__ ws,
@@ -179,9 +184,9 @@ __global__ void proto_prepare_kernel(const float* __restrict__ cen, int nclass, 
     const float v = n < nclass ? cen[(size_t)n * D + ks * KSTEP + k] : 0.f;
     const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
     const float lo = v - hi;
-    const size_t off = (size_t)ks * B_KSTEP_BYTES + (k >> 2) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4;
-    *reinterpret_cast<float*>(ws + off) = hi;
-    *reinterpret_cast<float*>(ws + off + B_TILE_BYTES) = lo;
+    const size_t off = (size_t)ks * B_KSTEP_BYTES + (k >> 2) * 1024 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(ws + off) = hi;                       // rows 0..31 of the stacked operand
+    *reinterpret_cast<float*>(ws + off + (NPAD / 8) * 128) = lo;    // rows 32..63
   }
   // ||c||^2: one warp per class row (blocks 0..3 hold 8 warps each), coalesced loads, two-level fp32 sum
   const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -207,7 +212,7 @@ __global__ void proto_prepare_kernel(const float* __restrict__ cen, int nclass, 
 // ---- main kernel ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char* __restrict__ ws, size_t cnorm_off, int nclass,
-                  int64_t n_img, int D, int64_t hw, float* __restrict__ dist, float* __restrict__ weight, int dbg) {
+                  int64_t n_img, int D, int64_t hw, int tile_px, float* __restrict__ dist, float* __restrict__ weight, int dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* a_ring = reinterpret_cast<float*>(smem + SMEM_A);
   unsigned char* b_ring = smem + SMEM_B;
@@ -218,15 +223,17 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int nch = D / KC;
-  const int64_t tiles_per_img = (hw + TILE_M - 1) / TILE_M;
+  // A tile is `tile_px` <= 128 pixels wide (rows beyond it ride along in the MMA for free but are never loaded): the
+  // host picks the width that makes the tile count fill whole rounds of CTAs (see proto_umma_launch).
+  const int64_t tiles_per_img = (hw + tile_px - 1) / tile_px;
+  const int box_w = tile_px + 4, box_floats = BOX_G * box_w;
   const int64_t n_tiles = n_img * tiles_per_img;
   const int hwm = (int)(hw & 3);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&fmap) : "memory");
     for (int i = 0; i < SA; ++i) { mbar_init(&bar->a_full[i], 1); mbar_init(&bar->a_empty[i], 4); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&bar->b_full[i], 1); mbar_init(&bar->b_empty[i], 1); }
-    for (int i = 0; i < ST; ++i) { mbar_init(&bar->t_full[i], 4); mbar_init(&bar->t_empty[i], 1); }
+    for (int i = 0; i < ST; ++i) { mbar_init(&bar->op_full[i], 4 * CPS + 1); mbar_init(&bar->op_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar->acc_full[i], 1); mbar_init(&bar->acc_empty[i], 4); mbar_init(&bar->norm_full[i], CONV_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -253,17 +260,17 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
     uint32_t ga = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t img = tile / tiles_per_img;
-      const int p0 = (int)((tile - img * tiles_per_img) * TILE_M);
+      const int p0 = (int)((tile - img * tiles_per_img) * tile_px);
       for (int c = 0; c < nch; ++c, ++ga) {
         const uint32_t sa = ga % SA;
         prof.wait(0, &bar->a_empty[sa], ((ga / SA) & 1) ^ 1);
         const int grp = (int)((img * D + (int64_t)c * KC) >> 2);
         float* dst = a_ring + sa * A_STAGE_FLOATS;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bar->a_full[sa], A_STAGE_BYTES);
+          mbar_arrive_expect_tx(&bar->a_full[sa], 4 * box_floats * 4);
 #pragma unroll
           for (int r = 0; r < 4; ++r)
-            tma_load_2d(dst + r * A_BOX_FLOATS, &fmap, ((int)(r * hw) + p0) & ~3, grp, &bar->a_full[sa]);
+            tma_load_2d(dst + r * box_floats, &fmap, ((int)(r * hw) + p0) & ~3, grp, &bar->a_full[sa]);
         }
         __syncwarp();
       }
@@ -272,12 +279,12 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
     // ===================== centroid loader: refills a stage as soon as the MMAs that read it have retired ==============
     uint32_t gb = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int c = 0; c < nch; ++c, ++gb) {
+      for (int c = 0; c < nch; c += CPS, ++gb) {
         const uint32_t sb = gb % SB;
-        prof.wait(0, &bar->b_empty[sb], ((gb / SB) & 1) ^ 1);
+        prof.wait(0, &bar->op_empty[sb], ((gb / SB) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bar->b_full[sb], B_STAGE_BYTES);
-          bulk_g2s(b_ring + sb * B_STAGE_BYTES, ws + (size_t)c * B_STAGE_BYTES, B_STAGE_BYTES, &bar->b_full[sb]);
+          mbar_arrive_expect_tx(&bar->op_full[sb], B_STAGE_BYTES);
+          bulk_g2s(b_ring + sb * B_STAGE_BYTES, ws + (size_t)c * (B_STAGE_BYTES / CPS), B_STAGE_BYTES, &bar->op_full[sb]);
         }
         __syncwarp();
       }
@@ -289,28 +296,26 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
       const uint32_t acc = it & 1;
       prof.wait(0, &bar->acc_empty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + TMEM_ACC_COL + acc * NPAD;
-      for (int c = 0; c < nch; ++c, ++gc) {
-        const uint32_t st = gc % ST, sb = gc % SB;
-        prof.wait(1, &bar->b_full[sb], (gc / SB) & 1);
-        prof.wait(2, &bar->t_full[st], (gc / ST) & 1);
+      const uint32_t d_tmem = tmem_base + TMEM_ACC_COL + acc * NACC;
+      for (int c = 0; c < nch; c += CPS, ++gc) {                // gc counts operand stages (pairs of chunks) here
+        const uint32_t st = gc % ST;
+        prof.wait(1, &bar->op_full[st], (gc / ST) & 1);      // A operands stored to TMEM and centroid tiles landed
         tc_fence_after();
-        const uint32_t a_hi = tmem_base + st * 64, a_lo = a_hi + KC;
-        const uint32_t b_base = smem_u32(b_ring + sb * B_STAGE_BYTES);
+        const uint32_t a_base = tmem_base + st * TMEM_STAGE_COLS;
+        const uint32_t b_base = smem_u32(b_ring + st * B_STAGE_BYTES);
         if (elect_one()) {
           if (!(dbg & 1)) {
 #pragma unroll
-            for (int ks = 0; ks < KC / KSTEP; ++ks) {
-              const uint64_t b_hi = make_b_desc(b_base + ks * B_KSTEP_BYTES);
-              const uint64_t b_lo = make_b_desc(b_base + ks * B_KSTEP_BYTES + B_TILE_BYTES);
-              tc_mma_tf32_ts(d_tmem, a_hi + ks * KSTEP, b_hi, kIdesc, (c | ks) != 0);
-              tc_mma_tf32_ts(d_tmem, a_hi + ks * KSTEP, b_lo, kIdesc, 1u);
-              tc_mma_tf32_ts(d_tmem, a_lo + ks * KSTEP, b_hi, kIdesc, 1u);
+            for (int ks = 0; ks < CPS * KC / KSTEP; ++ks) {
+              const uint32_t a_hi = a_base + (ks / (KC / KSTEP)) * 2 * KC + (ks % (KC / KSTEP)) * KSTEP, a_lo = a_hi + KC;
+              const uint64_t b_desc = make_b_desc(b_base + ks * B_KSTEP_BYTES);
+              // D[:, 0:64) (+)= A_hi * [b_hi | b_lo]^T ;  D[:, 0:32) += A_lo * b_hi^T   (2 MMAs instead of 3 per 8 channels)
+              tc_mma_tf32_ts(d_tmem, a_hi, b_desc, idesc_n(2 * NPAD), (c | ks) != 0);
+              tc_mma_tf32_ts(d_tmem, a_lo, b_desc, idesc_n(NPAD), 1u);
             }
           }
-          tc_commit(&bar->t_empty[st]);       // TMEM operand stage and centroid stage are free when these MMAs retire
-          tc_commit(&bar->b_empty[sb]);
-          if (c == nch - 1) tc_commit(&bar->acc_full[acc]);
+          tc_commit(&bar->op_empty[st]);      // both operand stages are free when these MMAs retire
+          if (c + CPS >= nch) tc_commit(&bar->acc_full[acc]);
         }
         __syncwarp();
       }
@@ -326,7 +331,7 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
       float fn = 0.f;
       for (int c = wg; c < nch; c += NWG) {
         const uint32_t gc = it * (uint32_t)nch + (uint32_t)c;
-        const uint32_t sa = gc % SA, st = gc % ST;
+        const uint32_t sa = gc % SA, pr = gc / CPS, st = pr % ST;       // pr: operand stage use (pair of chunks)
         prof.wait(0, &bar->a_full[sa], (gc / SA) & 1);
         const float* src = a_ring + sa * A_STAGE_FLOATS + row;
         const long long t_lds = prof.on ? clock64() : 0;
@@ -337,7 +342,7 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
         } else
 #pragma unroll
         for (int j = 0; j < KC; ++j)   // channel c*32+j = box r = j&3, group j>>2; box r starts (r*hw)&3 floats early
-          x[j] = src[(j & 3) * A_BOX_FLOATS + (j >> 2) * BOX_W + (((j & 3) * hwm) & 3)];
+          x[j] = src[(j & 3) * box_floats + (j >> 2) * box_w + (((j & 3) * hwm) & 3)];
         float part = 0.f;
 #pragma unroll
         for (int j = 0; j < KC; ++j) part = fmaf(x[j], x[j], part);
@@ -345,9 +350,9 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->a_empty[sa]);
         if (prof.on) prof.acc[3] += clock64() - t_lds;
-        prof.wait(1, &bar->t_empty[st], ((gc / ST) & 1) ^ 1);
+        prof.wait(1, &bar->op_empty[st], ((pr / ST) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t t_hi = tmem_base + lane_addr + st * 64;
+        const uint32_t t_hi = tmem_base + lane_addr + st * TMEM_STAGE_COLS + (gc % CPS) * 2 * KC;
 #pragma unroll
         for (int q = 0; q < KC / 8; ++q) {
           uint32_t hi[8], lo[8];
@@ -369,7 +374,7 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
         if (prof.on) prof.acc[2] += clock64() - t_st;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar->t_full[st]);
+        if (lane == 0) mbar_arrive(&bar->op_full[st]);
       }
       norm_part[(acc * NWG + wg) * TILE_M + row] = fn;
       __syncwarp();
@@ -384,14 +389,16 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, par = (it >> 1) & 1;
       const int64_t img = tile / tiles_per_img;
-      const int64_t p = (tile - img * tiles_per_img) * TILE_M + row;
+      const int64_t p = row < tile_px ? (tile - img * tiles_per_img) * tile_px + row : hw;   // rows past the tile width are padding
       prof.wait(0, &bar->acc_full[acc], par);
       prof.wait(1, &bar->norm_full[acc], par);
       tc_fence_after();
-      uint32_t r0[16], r1[16];
-      const uint32_t t = tmem_base + lane_addr + TMEM_ACC_COL + acc * NPAD;
+      uint32_t r0[16], r1[16], r2[16], r3[16];
+      const uint32_t t = tmem_base + lane_addr + TMEM_ACC_COL + acc * NACC;
       tc_ld16(t, r0);
       tc_ld16(t + 16, r1);
+      tc_ld16(t + 32, r2);
+      tc_ld16(t + 48, r3);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float fn = 0.f;
 #pragma unroll
@@ -404,7 +411,7 @@ proto_umma_kernel(const __grid_constant__ CUtensorMap fmap, const unsigned char*
         float dmin = 3.4e38f;
 #pragma unroll
         for (int c = 0; c < NPAD; ++c) {
-          const float dot = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 15]);
+          const float dot = __uint_as_float(c < 16 ? r0[c & 15] : r1[c & 15]) + __uint_as_float(c < 16 ? r2[c & 15] : r3[c & 15]);
           const float d2 = fmaf(-2.f, dot, fn + cnorm[c]);
           d[c] = sqrtf(fmaxf(d2, 0.f));
           if (c < nclass) dmin = fminf(dmin, d[c]);
@@ -454,7 +461,7 @@ size_t proto_umma_workspace_bytes(int64_t C, int64_t D) {
 }
 
 int proto_umma_supported(int64_t n, int64_t D, int64_t C, int64_t hw) {
-  return n >= 1 && hw >= 1 && C >= 1 && C <= umma::NPAD && (D % umma::KC) == 0 && D >= 256 && D <= (1 << 20) &&
+  return n >= 1 && hw >= 1 && C >= 1 && C <= umma::NPAD && (D % (umma::KC * umma::CPS)) == 0 && D >= 256 && D <= (1 << 20) &&
          4 * hw < ((int64_t)1 << 31) && n * D / 4 < ((int64_t)1 << 31);
 }
 
@@ -473,8 +480,18 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+int proto_umma_prepare(const float* centroids, int64_t D, int64_t C, void* workspace, cudaStream_t st) {
+  using namespace umma;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  const size_t cnorm_off = (size_t)(D / KSTEP) * B_KSTEP_BYTES;
+  const int total = (int)(D / KSTEP) * NPAD * KSTEP;
+  proto_prepare_kernel<<<(total + 255) / 256, 256, 0, st>>>(centroids, (int)C, (int)D, ws, cnorm_off);
+  DIGA_CHECK_LAUNCH("proto_prepare_kernel");
+  return DIGA_OK;
+}
+
 int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw, float* dist,
-                      float* weight, void* workspace, cudaStream_t st) {
+                      float* weight, void* workspace, int prepared, cudaStream_t st) {
   using namespace umma;
   if (!aligned(feat, 16) || !aligned(workspace, 128)) {
     set_error("proto_umma: feature pointer must be 16-byte and workspace 128-byte aligned");
@@ -485,11 +502,33 @@ int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int6
     set_error("proto_umma: cuTensorMapEncodeTiled not available from the driver");
     return DIGA_ERR_CUDA;
   }
+  // Tile width.  Time per tile is proportional to the pixels it loads, time per launch to rounds * width, so instead of
+  // 128-pixel tiles whose count rarely fills the last round of CTAs (528 tiles on 148 SMs: 4 rounds for 3.57 of work)
+  // the width is chosen, among the per-image tile counts up to one extra round, to minimise rounds * width
+  // (8 x 65x129: 74 tiles of 116 px per image = 592 = 4 x 148 tiles, -9 % time).
+  int tile_px = TILE_M;
+  if (tunable("umma_fit_tiles", 1)) {
+    const int64_t sms = sm_count();
+    const int64_t t_min = (hw + TILE_M - 1) / TILE_M;
+    double best = 1e30;
+    for (int64_t t = t_min; t <= t_min + (sms + n - 1) / n + 1; ++t) {
+      int64_t px = (hw + t - 1) / t;
+      px = (px + 3) & ~(int64_t)3;
+      if (px < 32) break;
+      if (px > TILE_M) continue;
+      const int64_t rounds = (n * ((hw + px - 1) / px) + sms - 1) / sms;
+      const double cost = (double)rounds * (double)(px + 6);       // +6: box padding and per-tile fixed cost
+      if (cost < best - 1e-9) {
+        best = cost;
+        tile_px = (int)px;
+      }
+    }
+  }
   // features viewed as [n*D/4 groups][4*hw]: the group pitch 16*hw bytes is a legal TMA stride for every hw
   CUtensorMap fmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)(4 * hw), (cuuint64_t)(n * D / 4)};
   const cuuint64_t gstride[1] = {(cuuint64_t)(16 * hw)};
-  const cuuint32_t box[2] = {(cuuint32_t)BOX_W, (cuuint32_t)BOX_G};
+  const cuuint32_t box[2] = {(cuuint32_t)(tile_px + 4), (cuuint32_t)BOX_G};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(&fmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -500,9 +539,10 @@ int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int6
   }
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   const size_t cnorm_off = (size_t)(D / KSTEP) * B_KSTEP_BYTES;
-  const int total = (int)(D / KSTEP) * NPAD * KSTEP;
-  proto_prepare_kernel<<<(total + 255) / 256, 256, 0, st>>>(centroids, (int)C, (int)D, ws, cnorm_off);
-  DIGA_CHECK_LAUNCH("proto_prepare_kernel");
+  if (!prepared) {
+    const int rc = proto_umma_prepare(centroids, D, C, workspace, st);
+    if (rc != DIGA_OK) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(proto_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
@@ -512,10 +552,10 @@ int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int6
     }
     configured = true;
   }
-  const int64_t tiles = n * ((hw + TILE_M - 1) / TILE_M);
+  const int64_t tiles = n * ((hw + tile_px - 1) / tile_px);
   int64_t grid = sm_count();
   if (grid > tiles) grid = tiles;
-  proto_umma_kernel<<<(unsigned)grid, THREADS, SMEM_TOTAL, st>>>(fmap, ws, cnorm_off, (int)C, n, (int)D, hw, dist, weight,
+  proto_umma_kernel<<<(unsigned)grid, THREADS, SMEM_TOTAL, st>>>(fmap, ws, cnorm_off, (int)C, n, (int)D, hw, tile_px, dist, weight,
                                                                      tunable("umma_debug", 0));
   DIGA_CHECK_LAUNCH("proto_umma_kernel");
   return DIGA_OK;

@@ -144,6 +144,11 @@ int diga_centroid_reduce_images(const float* vec, const float* vecsum, const uin
 size_t diga_proto_workspace_bytes(int64_t C, int64_t D);
 int diga_proto_distance(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C, int64_t hw,
                         float* dist, float* weight, void* workspace, diga_stream_t stream);
+/* Same, split in two for many calls against unchanged centroids (offline pseudo-label rectification): prepare the
+ * split centroid operands once, then call the _prepared form with the same workspace. */
+int diga_proto_prepare(const float* centroids, int64_t C, int64_t D, void* workspace, diga_stream_t stream);
+int diga_proto_distance_prepared(const float* feat, const float* centroids, int64_t n, int64_t D, int64_t C,
+                                 int64_t hw, float* dist, float* weight, void* workspace, diga_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a4  bilateral-consensus selection — train_DiGA_gta2city_self_training.py:298-304
