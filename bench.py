@@ -271,6 +271,9 @@ def bench_stages(D, S, dev, peak, world, quick):
     l1, l2 = S.logits((n, C, 129, 257), g), S.logits((n, C, 65, 129), g)
     add("pseudo_label_fused_upsample", n * hh * ww, 5, lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww)),
         extra={"note": "replaces two bilinear up-samplings (2 x 76 B/px written + read) and the 157 B/px kernel; ALU-bound"})
+    add("pseudo_label_fused_upsample_labels_only", n * hh * ww, 1,
+        lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww), want_conf=False),
+        extra={"note": "what pseudolabel_generator.py keeps: the uint8 label map (the confidence is discarded there)"})
 
     # config 3 pieces: B=8 @512x1024, features [8,2048,65,129]
     b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048

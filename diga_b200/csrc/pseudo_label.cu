@@ -122,7 +122,9 @@ static int launch_pl(const float* z1, const float* z2, int nclass, int64_t n, in
 // Interpolation mirrors ATen (bilinear.cuh).
 // ------------------------------------------------------------------------------------------------
 // One thread = one output column x RY consecutive rows; both scales are walked with a ColumnInterp each.
-template <int C, bool PAD, int RY, int BLOCK, bool HAS2>
+// CONF=false drops the 19 exponentials per pixel: the reference computes the confidence and throws it away
+// (`label, _ = np.argmax(...), np.max(...)`, pseudolabel_generator.py:85), and this kernel is instruction-bound.
+template <int C, bool PAD, int RY, int BLOCK, bool HAS2, bool CONF>
 __global__ void __launch_bounds__(BLOCK)
 pseudo_label_upsampled_kernel(const float* __restrict__ z1, int h1, int w1, float sh1, float sw1,
                               const float* __restrict__ z2, int h2, int w2, float sh2, float sw2, int nclass, int H, int W,
@@ -170,14 +172,16 @@ pseudo_label_upsampled_kernel(const float* __restrict__ z1, int h1, int w1, floa
         m = gt ? z[c] : m;
         am = gt ? c : am;
       }
-    float S = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) S += fast_exp(z[c] - m);
     const int64_t o = (img * H + Y) * W + X;
     if (lab8) lab8[o] = (uint8_t)am;
     if (lab64) lab64[o] = am;
-    if (conf) conf[o] = 1.0f / S;
+    if constexpr (CONF) {
+      float S = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (!PAD || c < nclass) S += fast_exp(z[c] - m);
+      conf[o] = 1.0f / S;
+    }
   }
 }
 
@@ -203,15 +207,17 @@ extern "C" int diga_pseudo_label_upsampled(const float* logits, int64_t h1, int6
   dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), (unsigned)((H + RY - 1) / RY), (unsigned)n);
   const float sh1 = bilinear_scale_host(h1, H), sw1 = bilinear_scale_host(w1, W);
   const float sh2 = logits_ds ? bilinear_scale_host(h2, H) : 0.f, sw2 = logits_ds ? bilinear_scale_host(w2, W) : 0.f;
+#define DIGA_PLU_GO(HAS2, CONF)                                                                                      \
+  pseudo_label_upsampled_kernel<kC, kPad, RY, BLOCK, HAS2, CONF><<<grid, BLOCK, 0, st>>>(                              \
+      logits, (int)h1, (int)w1, sh1, sw1, logits_ds, (int)h2, (int)w2, sh2, sw2, (int)C, (int)H, (int)W, label_u8, label_i64, conf)
   DIGA_DISPATCH_C(C, {
-    if (logits_ds)
-      pseudo_label_upsampled_kernel<kC, kPad, RY, BLOCK, true><<<grid, BLOCK, 0, st>>>(
-          logits, (int)h1, (int)w1, sh1, sw1, logits_ds, (int)h2, (int)w2, sh2, sw2, (int)C, (int)H, (int)W, label_u8,
-          label_i64, conf);
-    else
-      pseudo_label_upsampled_kernel<kC, kPad, RY, BLOCK, false><<<grid, BLOCK, 0, st>>>(
-          logits, (int)h1, (int)w1, sh1, sw1, nullptr, 0, 0, 0.f, 0.f, (int)C, (int)H, (int)W, label_u8, label_i64, conf);
+    if (logits_ds) {
+      if (conf) DIGA_PLU_GO(true, true); else DIGA_PLU_GO(true, false);
+    } else {
+      if (conf) DIGA_PLU_GO(false, true); else DIGA_PLU_GO(false, false);
+    }
   });
+#undef DIGA_PLU_GO
   DIGA_CHECK_LAUNCH("pseudo_label_upsampled_kernel");
   return DIGA_OK;
 }

@@ -225,6 +225,14 @@ def pseudo_label_to_uint8(label: np.ndarray) -> np.ndarray:
     return np.asarray(label.astype(np.float64), dtype=np.uint8)
 
 
+def colorize_mask(mask: np.ndarray, palette):
+    """pseudolabel_generator.py:45-49 — 'P'-mode PIL image, palette index = trainId."""
+    from PIL import Image
+    new_mask = Image.fromarray(mask.astype(np.uint8)).convert('P')    # :47
+    new_mask.putpalette(palette)                                       # :48
+    return new_mask
+
+
 # --------------------------------------------------------------------------------------
 # a4  bilateral-consensus ("threshold-free dynamic") selection
 #     (G/train_DiGA_gta2city_self_training.py:298-304)

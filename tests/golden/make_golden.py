@@ -172,6 +172,20 @@ def main():
     exec(_lines("pseudolabel_generator.py", 77, 85), ns)
     save("pseudo_label_two_scale", logits=lo, logits_ds=lo_ds, size=np.array([64, 96]), label=ns["label"])
 
+    # ---- f3 palette PNG: exec G/pseudolabel_generator.py:38-49 (palette, colorize_mask) + :91-92 -----------------
+    import io
+    from PIL import Image
+    ns = {"np": np, "Image": Image}
+    exec(_lines("pseudolabel_generator.py", 38, 49), ns)
+    gen_png = torch.Generator().manual_seed(4242)                                             # own stream: other fixtures unchanged
+    lab_f64 = torch.randint(0, 19, (24, 40), generator=gen_png).numpy().astype(np.float64)   # float64 staging array (:66)
+    out_img = ns["colorize_mask"](np.asarray(lab_f64, dtype=np.uint8))                       # :92, :100
+    bio = io.BytesIO()
+    out_img.save(bio, format="PNG")
+    back = Image.open(io.BytesIO(bio.getvalue()))
+    save("palette_png", label=lab_f64, palette=np.array(ns["palette"]), mode=np.array([ord(ch) for ch in back.mode]),
+         indices=np.array(back), png_palette=np.array(back.getpalette()))
+
     # ---- a2 ClassMix: exec self_training.py:259-275 (image only) and :306-325 (DACS) -------
     b, hh, ww = 3, 32, 48
     slabel = _blocky_labels(gen, b, hh, ww, 8)

@@ -130,3 +130,29 @@ def test_self_training_step_hot_path():
             assert normwise(got["centroids"][k], ref["centroids"][k]), f"centroid {k}"
         assert abs(got["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
         assert normwise(got["g_stu"], ref["g_stu"]) and normwise(got["g_cp"], ref["g_cp"])
+
+
+def test_generate_pseudo_labels_writes_reference_format(tmp_path):
+    """pseudolabel_generator.py:69-105 end to end on a stand-in model: PNG files named after the image, 'P' mode with the
+    Cityscapes palette, indices equal to the reference math (two-scale max -> argmax) evaluated with torch on the GPU."""
+    from PIL import Image
+    import diga_b200 as D
+    from diga_b200.pseudolabel import CITYSCAPES_PALETTE, generate_pseudo_labels
+    model = TinySeg().to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    size = (128, 192)
+    loader = [(torch.randn((2, 3, *size), generator=gen), None, [f"a/b/img_{k}_{j}.png" for j in range(2)]) for k in range(3)]
+    n = generate_pseudo_labels(model, loader, str(tmp_path), size=size, workers=2)
+    assert n == 6 and len(os.listdir(tmp_path)) == 6
+    with torch.no_grad():
+        for image, _, names in loader:
+            image = image.to(DEV)
+            image_ds = F.interpolate(image, (size[0] // 2, size[1] // 2), mode="bilinear", align_corners=True)
+            out_ds, out = model(image_ds)[2], model(image)[2]
+            fused = torch.max(O.upsample_bilinear_ac(out_ds, size), O.upsample_bilinear_ac(out, size))
+            ref = torch.softmax(fused, 1).argmax(1).cpu().numpy()
+            for j, name in enumerate(names):
+                png = Image.open(os.path.join(tmp_path, name.split("/")[-1]))
+                assert png.mode == "P" and png.getpalette() == CITYSCAPES_PALETTE
+                got = np.array(png)
+                assert got.dtype == np.uint8 and (got != ref[j]).mean() < 1e-4       # exact softmax ties only

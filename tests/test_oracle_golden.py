@@ -70,6 +70,23 @@ def test_ema_teacher_update_matches_reference_bitwise(golden):
         assert np.array_equal(got, g[fixture_key]), key
 
 
+def test_palette_png_format(golden):
+    """f3: 'P'-mode PNG, palette index = trainId (pseudolabel_generator.py:38-49, 91-100) — oracle and product helper."""
+    import io
+    from PIL import Image
+    g = golden("palette_png")
+    from diga_b200.pseudolabel import CITYSCAPES_PALETTE, colorize_mask
+    assert CITYSCAPES_PALETTE == g["palette"].tolist()
+    for img in (O.colorize_mask(np.asarray(g["label"], dtype=np.uint8), g["palette"].tolist()),
+                colorize_mask(np.asarray(g["label"], dtype=np.uint8))):
+        bio = io.BytesIO()
+        img.save(bio, format="PNG")
+        back = Image.open(io.BytesIO(bio.getvalue()))
+        assert back.mode == "".join(chr(c) for c in g["mode"]) == "P"
+        assert np.array_equal(np.array(back), g["indices"])
+        assert back.getpalette() == g["png_palette"].tolist()
+
+
 def test_process_label(golden):
     g = golden("process_label")
     assert np.array_equal(O.process_label(T(g["label"])).numpy(), g["onehot"])
