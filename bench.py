@@ -335,6 +335,30 @@ def bench_stages(D, S, dev, peak, world, quick):
     add("centroid_accumulate_update_d2048_blocky_classes", b * h * w, d * 4 + C * 4 + 1,
         lambda: cf.update_from_features(feat, logits_blk, None, "mean"), unit="feature-px", extra=per_img)
 
+    # config 4 as the reference drives it: one 512x1024 image per call ([1,2048,65,129])
+    f1, o1 = feat[:1].contiguous(), logits_iid[:1].contiguous()
+    add("calc_centroids_per_image_call_d2048", h * w, d * 4 + C * 4 + 1,
+        lambda: cf.update_from_features(f1, o1, None, "mean"), unit="feature-px",
+        extra=lambda ms: {"images_per_s": 1 / (ms * 1e-3) * world, "note": "batch 1 per call like calc_centroids.py:67-78; "
+                          "68.7 MB per launch is too small to fill the machine, batch the loader for throughput"})
+
+    # config 5, one full-resolution image: labels from the two-scale logits, prototype weights at 129x257, consensus selection
+    del feat
+    f5 = S.features((1, d, 129, 257), g)
+    l5a, l5b = S.logits((1, C, 129, 257), g), S.logits((1, C, 65, 129), g)
+
+    def config5_image():
+        lab, _ = D.pseudo_label_two_scale(l5a, l5b, (1024, 2048), want_conf=False)
+        wts = cf.get_centroid_weight(f5)
+        return D.consensus_select(lab.long(), wts, want_feat_pseudo=False)
+
+    add("config5_pseudo_label_plus_rectification_per_image", 1024 * 2048, (d * 4 + C * 4) * 129 * 257 / (1024 * 2048) + 1 + 16,
+        config5_image, extra=lambda ms: {"images_per_s": 1 / (ms * 1e-3) * world,
+                                         "note": "pseudo_label_two_scale + get_centroid_weight([1,2048,129,257]) + consensus_select "
+                                                 "(+ a torch uint8->int64 cast); algorithmic bytes dominated by the 272 MB feature map"})
+    del f5
+    feat = S.features((b, d, h, w), g)
+
     # config 4 shape of the exchange: mean pass + ONE all-reduce of [19, D+1] (NCCL over NVLink when world > 1)
     acc = P.new_mean_accumulator(C, d, dev)
 
