@@ -56,6 +56,10 @@ SIGNATURES = {
     "diga_ce_workspace_bytes": (C.c_size_t, []),
     "diga_cross_entropy2d_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
     "diga_cross_entropy2d_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
+    "diga_loss_up_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64, _i64, _i64, _i64]),
+    "diga_loss_up_fwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p]),
+    "diga_loss_up_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p, _p]),
+    "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
     "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
 }
 
@@ -123,6 +127,12 @@ def _workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def loss_up_workspace(n, c, h, w, hh, ww, device: torch.device) -> torch.Tensor:
+    """Workspace of the fused up-sampling losses (reduction partials + gradient patches), one per geometry/stream."""
+    nbytes = int(lib.diga_loss_up_workspace_bytes(n, c, h, w, hh, ww))
+    return _workspace(("loss_up", n, c, h, w, hh, ww), nbytes, device)
 
 
 def kd_workspace(device: torch.device) -> torch.Tensor:

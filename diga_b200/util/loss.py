@@ -107,3 +107,116 @@ def cross_entropy2d(input, target, weight=None, size_average=True):
         raise ValueError(f"cross_entropy2d: expected [N,C,H,W] logits and [N,H,W] targets, got {tuple(input.shape)} and "
                          f"{tuple(target.shape)}")
     return _CrossEntropy2d.apply(input, target, weight, size_average)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# f1 for the loss consumers: the same losses evaluated straight from the stride-8 logits (csrc/loss_up.cu).  The
+# reference up-samples first (train_DiGA_gta2city_self_training.py:289,:344,:348,:351: nn.Upsample(bilinear,
+# align_corners=True)) and so materialises, per loss, the up-sampled logits and their gradient (76 B/px each).
+# ----------------------------------------------------------------------------------------------------------------------
+def _size2(size):
+    hh, ww = (int(size[0]), int(size[1]))
+    return hh, ww
+
+
+class _LossesUpsampled(torch.autograd.Function):
+    """(loss_ce, loss_kd) of the first ``n_ce`` / all images of ``student_low``; either part may be switched off."""
+
+    @staticmethod
+    def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average):
+        s = L.f32c(student_low.detach())
+        t = None if teacher_low is None else L.f32c(teacher_low.detach())
+        tg = None if target is None else L.i64c(target)
+        wt = None if weight is None else L.f32c(weight.detach()).to(s.device)
+        n, c, h, w = s.shape
+        hh, ww = size
+        n_ce = 0 if tg is None else tg.shape[0]
+        dev = s.device
+        loss_kd = torch.zeros((), dtype=torch.float32, device=dev) if t is None else torch.empty((), dtype=torch.float32, device=dev)
+        loss_ce = torch.zeros((), dtype=torch.float32, device=dev) if tg is None else torch.empty((), dtype=torch.float32, device=dev)
+        denom = torch.ones((), dtype=torch.float32, device=dev)
+        ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
+        L.check(L.lib.diga_loss_up_fwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww, float(scale),
+                                       int(bool(size_average)), loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(),
+                                       ws.data_ptr(), L.stream()))
+        ctx.save_for_backward(s, denom)
+        ctx.aux = (t, tg, wt, (hh, ww), float(scale), int(bool(size_average)), n_ce)
+        return loss_ce, loss_kd
+
+    @staticmethod
+    def backward(ctx, g_ce, g_kd):
+        s, denom = ctx.saved_tensors
+        t, tg, wt, (hh, ww), scale, size_average, n_ce = ctx.aux
+        n, c, h, w = s.shape
+        dev = s.device
+        as_scalar = lambda g: (torch.zeros((), dtype=torch.float32, device=dev) if g is None
+                               else g.to(dtype=torch.float32, device=dev).contiguous())
+        g_ce, g_kd = as_scalar(g_ce), as_scalar(g_kd)                 # 0-dim device scalars, read on the GPU
+        ds = torch.empty_like(s)
+        ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
+        L.check(L.lib.diga_loss_up_bwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww, scale,
+                                       size_average, g_kd.data_ptr(), g_ce.data_ptr(), denom.data_ptr(), ds.data_ptr(),
+                                       ws.data_ptr(), L.stream()))
+        return None, ds, None, None, None, None, None
+
+
+def _check_low(student_low, size, what):
+    if student_low.dim() != 4:
+        raise ValueError(f"{what}: expected [N,C,h,w] logits, got {tuple(student_low.shape)}")
+    hh, ww = _size2(size)
+    if hh < student_low.shape[2] or ww < student_low.shape[3]:
+        raise ValueError(f"{what}: output size {(hh, ww)} must not be smaller than the logits {tuple(student_low.shape[2:])} "
+                         "(the reference only up-samples)")
+    return hh, ww
+
+
+def distillation_loss_upsampled(teacher_low, student_low, size, scale=0.5):
+    """``distillation_loss(upsample(teacher_low), upsample(student_low), scale)`` with ``upsample =
+    nn.Upsample(size, mode='bilinear', align_corners=True)`` (self_training.py:289,:351-352), neither up-sampled tensor
+    nor its gradient materialised.  Autograd-connected to ``student_low`` ([2B,C,h,w]) only."""
+    L.require_cuda(teacher_low, student_low, what="distillation_loss_upsampled input")
+    if teacher_low.shape != student_low.shape or student_low.dim() != 4 or student_low.shape[0] % 2:
+        raise ValueError(f"distillation_loss_upsampled: expected two [2B,C,h,w] tensors, got {tuple(teacher_low.shape)} and "
+                         f"{tuple(student_low.shape)}")
+    size = _check_low(student_low, size, "distillation_loss_upsampled")
+    return _LossesUpsampled.apply(teacher_low, student_low, None, None, size, scale, True)[1]
+
+
+def cross_entropy2d_upsampled(input_low, target, weight=None, size_average=True):
+    """``cross_entropy2d(upsample(input_low), target, weight, size_average)`` with the up-sampling to ``target``'s
+    resolution fused (self_training.py:344,:348-349,:355).  ``input_low [N,C,h,w]`` fp32, ``target [N,H,W]`` int64."""
+    L.require_cuda(input_low, target, weight, what="cross_entropy2d_upsampled input")
+    if target.dim() != 3 or input_low.dim() != 4 or target.shape[0] != input_low.shape[0]:
+        raise ValueError(f"cross_entropy2d_upsampled: expected [N,C,h,w] logits and [N,H,W] targets, got "
+                         f"{tuple(input_low.shape)} and {tuple(target.shape)}")
+    size = _check_low(input_low, target.shape[1:], "cross_entropy2d_upsampled")
+    return _LossesUpsampled.apply(None, input_low, target, weight, size, 0.0, size_average)[0]
+
+
+def seg_distillation_losses_upsampled(teacher_low, student_low, target, scale=0.5, weight=None, size_average=True):
+    """The two losses that share ``s_pred_cat_stu`` in the self-training step (self_training.py:348-352) from ONE pass over
+    the stride-8 logits: returns ``(cross_entropy2d(upsample(student_low[:B]), target), distillation_loss(upsample(
+    teacher_low), upsample(student_low), scale))``; the backward adds both gradients in one kernel."""
+    L.require_cuda(teacher_low, student_low, target, weight, what="seg_distillation_losses_upsampled input")
+    if teacher_low.shape != student_low.shape or student_low.dim() != 4 or student_low.shape[0] % 2:
+        raise ValueError("seg_distillation_losses_upsampled: expected two [2B,C,h,w] logit tensors")
+    if target.dim() != 3 or not (1 <= target.shape[0] <= student_low.shape[0]):
+        raise ValueError("seg_distillation_losses_upsampled: target must be [n_ce,H,W] with 1 <= n_ce <= 2B")
+    size = _check_low(student_low, target.shape[1:], "seg_distillation_losses_upsampled")
+    return _LossesUpsampled.apply(teacher_low, student_low, target, weight, size, scale, size_average)
+
+
+def distillation_loss_upsampled_and_grad(teacher_low, student_low, size, scale=0.5, grad_scale=1.0):
+    """Single-pass variant: ``(loss, grad_scale * dloss/dstudent_low)`` for call sites that know ``lambda_distil``."""
+    L.require_cuda(teacher_low, student_low, what="distillation_loss_upsampled_and_grad input")
+    if teacher_low.shape != student_low.shape or student_low.dim() != 4 or student_low.shape[0] % 2:
+        raise ValueError("distillation_loss_upsampled_and_grad: expected two [2B,C,h,w] tensors")
+    hh, ww = _check_low(student_low, size, "distillation_loss_upsampled_and_grad")
+    t, s = L.f32c(teacher_low.detach()), L.f32c(student_low.detach())
+    n, c, h, w = s.shape
+    loss = torch.empty((), dtype=torch.float32, device=s.device)
+    ds = torch.empty_like(s)
+    ws = L.loss_up_workspace(n, c, h, w, hh, ww, s.device)
+    L.check(L.lib.diga_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), n, c, h, w, hh, ww, float(scale), float(grad_scale),
+                                     loss.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
+    return loss, ds

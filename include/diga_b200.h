@@ -188,6 +188,35 @@ int diga_cross_entropy2d_bwd(const float* logits, const int64_t* target, const f
                              diga_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f1 (next row 1) for the loss consumers — train_DiGA_gta2city_self_training.py:289,:344,:348-352,:355
+ *   The losses evaluated on bilinear(align_corners=True) up-sampled logits, straight from the stride-8 logits:
+ *   neither the up-sampled [n,C,H,W] tensors nor their gradients are materialised.
+ *     KD (util/loss.py:125-143): teacher_low, student_low [n,C,h,w], n = 2B even; loss_kd as diga_kd_fwd on the
+ *        up-sampled pair.  teacher_low == NULL switches KD off.
+ *     CE (util/loss.py:48-62): target [n_ce,H,W] int64 supervises the FIRST n_ce images of student_low (n_ce == n for
+ *        a plain cross_entropy2d; n_ce == B for the source half of s_pred_cat_stu, :348-349); semantics of
+ *        diga_cross_entropy2d_fwd.  target == NULL switches CE off.
+ *   bwd: dstudent_low [n,C,h,w] (fully overwritten) = upstream_kd[0]*dloss_kd/dstudent_low
+ *        + upstream_ce[0]*dloss_ce/dstudent_low, i.e. the transposed interpolation applied to the per-pixel gradient;
+ *        no atomics, bitwise deterministic.  upstream_* / denom are DEVICE scalars (denom = denom_out of the forward).
+ *   kd_up_fwd_bwd: KD loss and upstream_host * gradient in a single pass.
+ *   workspace: diga_loss_up_workspace_bytes(n, C, h, w, H, W) bytes, 16-byte aligned; its first 16 bytes zero-filled
+ *        once by the caller (the kernels leave them zeroed).  Requires H >= h and W >= w.
+ * ------------------------------------------------------------------------------------------ */
+size_t diga_loss_up_workspace_bytes(int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W);
+int diga_loss_up_fwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
+                     int64_t n, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
+                     int size_average, float* loss_kd, float* loss_ce, float* denom_out, void* workspace,
+                     diga_stream_t stream);
+int diga_loss_up_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
+                     int64_t n, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
+                     int size_average, const float* upstream_kd, const float* upstream_ce, const float* denom,
+                     float* dstudent_low, void* workspace, diga_stream_t stream);
+int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
+                       int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
+                       void* workspace, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f4 (next row)  EMA teacher update — util/utils.py:103-116
  *   For each of `count` parameter tensors: teacher = alpha * teacher + (1 - alpha) * student (fp32, in place,
  *   separately rounded like the torch expression).  The three tables live in HOST memory (device pointers and

@@ -319,6 +319,27 @@ def cross_entropy2d(input, target, weight=None, size_average=True):
     return loss
 
 
+def distillation_loss_upsampled(teacher_low, student_low, size, scale=0.5):
+    """``distillation_loss(upsample_src(tea), upsample_src(stu))``: train_DiGA_gta2city_self_training.py:289,:351-352
+    (bilinear ``align_corners=True`` up-sampling in front of G/util/loss.py:125-143)."""
+    return distillation_loss(upsample_bilinear_ac(teacher_low, size), upsample_bilinear_ac(student_low, size), scale)
+
+
+def cross_entropy2d_upsampled(input_low, target, weight=None, size_average=True):
+    """``seg_loss(upsample(pred), label)``: train_DiGA_gta2city_self_training.py:344,:348-349,:355."""
+    return cross_entropy2d(upsample_bilinear_ac(input_low, target.shape[-2:]), target, weight, size_average)
+
+
+def seg_distillation_losses_upsampled(teacher_low, student_low, target, scale=0.5, weight=None, size_average=True):
+    """The two losses that share ``s_pred_cat_stu`` (train_DiGA_gta2city_self_training.py:348-352):
+    ``seg_loss(upsample_src(s_pred_cat_stu[:B]), slabelv)`` and ``distillation_loss(upsample_src(tea), upsample_src(stu))``."""
+    size = target.shape[-2:]
+    s_pred_stu = upsample_bilinear_ac(student_low[:target.shape[0]], size)            # :348 (its own up-sampling)
+    loss_semseg = cross_entropy2d(s_pred_stu, target, weight, size_average)           # :349
+    s_pred_cat_stu = upsample_bilinear_ac(student_low, size)                          # :351
+    return loss_semseg, distillation_loss(upsample_bilinear_ac(teacher_low, size), s_pred_cat_stu, scale)   # :289,:352
+
+
 def ema_alpha(iteration, stage0=True, mean=False, replace=False):
     """G/util/utils.py:105-112."""
     if stage0 == True:      # noqa: E712

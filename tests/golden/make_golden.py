@@ -49,7 +49,12 @@ def _blocky_labels(gen, b, h, w, block, n_cls=19, p_ignore=0.1):
     return lab.contiguous().long()
 
 
+ONLY = set(sys.argv[1:])      # `python make_golden.py losses_up` rewrites only the named fixtures
+
+
 def save(name, **arrays):
+    if ONLY and name not in ONLY:
+        return
     out = {}
     for k, v in arrays.items():
         if isinstance(v, torch.Tensor):
@@ -243,6 +248,30 @@ def main():
          centroids_after=cf.objective_vectors, num_after=cf.objective_vectors_num,
          ids_t=np.array(ns["ids_t"]), ids_s=np.array(ns["ids_s"]),
          newlabels_t=ns["newlabels_t"], newlabels_s=ns["newlabels_s"])
+
+    # ---- f1 for the loss consumers: exec self_training.py:289 (teacher up-sampling), :344 (cross_pred_mix), :348-352
+    #      (seg loss + KD on the shared student logits), :355-356, :382 (total loss), backward to the STRIDE-8 logits ----
+    gen_up = torch.Generator().manual_seed(9090)                       # own stream: other fixtures unchanged
+    bsz, c, fh, fw, oh, ow = 2, 19, 9, 13, 64, 96
+    stu_low = (3.0 * torch.randn((2 * bsz, c, fh, fw), generator=gen_up)).requires_grad_(True)
+    tea_low = 3.0 * torch.randn((2 * bsz, c, fh, fw), generator=gen_up)
+    mix_low = (3.0 * torch.randn((bsz, c, fh, fw), generator=gen_up)).requires_grad_(True)
+    sl = _blocky_labels(gen_up, bsz, oh, ow, 8)
+    ml = _blocky_labels(gen_up, bsz, oh, ow, 8, p_ignore=0.3)
+    up = nn.Upsample(size=[oh, ow], mode="bilinear", align_corners=True)
+    ns = {"torch": torch, "upsample_src": up, "upsample_tgt": up, "seg_loss": ref.cross_entropy2d,
+          "distillation_loss": ref.distillation_loss, "lambda_seg": 1.0, "lambda_distil": 0.25,
+          "s_pred_cat_tea": tea_low.clone(), "s_pred_cat_stu": stu_low, "s_pred_stu": stu_low[:bsz],
+          "cross_pred_mix": mix_low, "slabelv": sl, "crossmix_label": ml}
+    for first, last in ((289, 289), (344, 344), (348, 349), (351, 352)):
+        exec(_lines("train_DiGA_gta2city_self_training.py", first, last), ns)
+    loss_src = ns["loss_semseg"].detach().clone()
+    for first, last in ((355, 356), (382, 382), (385, 385)):
+        exec(_lines("train_DiGA_gta2city_self_training.py", first, last), ns)
+    save("losses_up", student_low=stu_low, teacher_low=tea_low, mix_low=mix_low, slabel=sl, mixlabel=ml,
+         size=np.array([oh, ow]), lambda_seg=1.0, lambda_distil=0.25, kd_scale=0.5,
+         loss_semseg_src=loss_src, loss_semseg=ns["loss_semseg"], loss_distil=ns["loss_s_distil"],
+         total_loss=ns["total_loss"], grad_student_low=stu_low.grad, grad_mix_low=mix_low.grad)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,184 @@
+"""GPU parity of the fused up-sampling losses (csrc/loss_up.cu): KD and cross_entropy2d evaluated
+from the stride-8 logits, against the golden fixture made by the reference's own statements and against the oracle
+(`loss(upsample(low))` with autograd through F.interpolate) on seeded inputs.  Bar: 1e-5 relative (norm-wise for
+gradients); the backward is additionally required to be bitwise deterministic."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import diga_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-5
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a)).to(DEV)
+
+
+def normwise(got, want, what, rtol=RTOL):
+    got, want = got.detach().double().cpu(), torch.as_tensor(want).detach().double().cpu()
+    assert got.shape == want.shape, what
+    err, scale = (got - want).abs().max().item(), want.abs().max().item()
+    assert err <= rtol * max(scale, 1e-30), f"{what}: max|diff| {err:.3e} > {rtol} * {scale:.3e}"
+
+
+def rel(got, want, what, rtol=RTOL):
+    got, want = float(got), float(want)
+    assert abs(got - want) <= rtol * abs(want), f"{what}: {got!r} vs {want!r}"
+
+
+@pytest.fixture(scope="module")
+def D():
+    import diga_b200
+    return diga_b200
+
+
+def test_losses_up_golden(D, golden):
+    g = golden("losses_up")
+    stu = T(g["student_low"]).requires_grad_(True)
+    mix = T(g["mix_low"]).requires_grad_(True)
+    tea, sl, ml = T(g["teacher_low"]), T(g["slabel"]), T(g["mixlabel"])
+    loss_src, loss_kd = D.seg_distillation_losses_upsampled(tea, stu, sl, float(g["kd_scale"]))
+    loss_seg = loss_src + D.cross_entropy2d_upsampled(mix, ml)
+    total = float(g["lambda_seg"]) * loss_seg + float(g["lambda_distil"]) * loss_kd
+    total.backward()
+    rel(loss_src, g["loss_semseg_src"], "loss_semseg (source)")
+    rel(loss_seg, g["loss_semseg"], "loss_semseg")
+    rel(loss_kd, g["loss_distil"], "loss_s_distil")
+    rel(total, g["total_loss"], "total_loss")
+    normwise(stu.grad, g["grad_student_low"], "d total / d s_pred_cat_stu (stride 8)")
+    normwise(mix.grad, g["grad_mix_low"], "d total / d cross_pred_mix (stride 8)")
+
+
+GEOMS = [  # n2, C, (h, w), (H, W)
+    (4, 19, (9, 13), (64, 96)),          # W < one tile
+    (2, 19, (17, 33), (128, 256)),       # two full tiles, exact 8x cells
+    (2, 19, (12, 21), (83, 301)),        # ragged strips / tiles, non-integer scale
+    (2, 16, (7, 40), (50, 300)),         # Synthia class count
+    (2, 7, (5, 6), (21, 37)),            # padded generic class count
+    (2, 19, (6, 9), (6, 9)),             # identity geometry (scale 1)
+    (2, 19, (1, 1), (5, 130)),           # single source pixel
+    (2, 19, (3, 5), (40, 41)),           # 13x up-sampling: more than two strips per source row
+]
+
+
+def inputs(n2, c, lo, seed, sigma=3.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    tea = sigma * torch.randn((n2, c, *lo), generator=g, device=DEV)
+    stu = sigma * torch.randn((n2, c, *lo), generator=g, device=DEV)
+    return tea, stu, g
+
+
+def labels(n, hi, c, g):
+    t = torch.randint(0, c, (n, *hi), generator=g, device=DEV)
+    r = torch.rand((n, *hi), generator=g, device=DEV)
+    t[r < 0.2] = 255
+    t[r > 0.97] = -1
+    return t
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", GEOMS)
+def test_kd_upsampled_vs_oracle(D, n2, c, lo, hi):
+    tea, stu, _ = inputs(n2, c, lo, 11)
+    for scale, up in ((0.5, 0.25), (0.25, 1.0)):
+        s1 = stu.clone().requires_grad_(True)
+        loss = D.distillation_loss_upsampled(tea, s1, hi, scale)
+        (loss * up).backward()
+        s2 = stu.clone().requires_grad_(True)
+        ref = O.distillation_loss_upsampled(tea, s2, hi, scale)                # eager chain on the same GPU
+        (ref * up).backward()
+        rel(loss, ref, "kd_up loss")
+        normwise(s1.grad, s2.grad, "kd_up grad")
+        # fp64 evaluation of the same chain on the CPU: the fused result must be as close to it as the eager chain is
+        s3 = stu.double().cpu().requires_grad_(True)
+        ref64 = O.distillation_loss_upsampled(tea.double().cpu(), s3, hi, scale)
+        (ref64 * up).backward()
+        rel(loss, ref64, "kd_up loss vs fp64")
+        normwise(s1.grad, s3.grad, "kd_up grad vs fp64")
+        # single-pass variant
+        l2, g2 = D.distillation_loss_upsampled_and_grad(tea, stu, hi, scale, up)
+        assert torch.equal(l2, loss.detach()) and torch.equal(g2, s1.grad)
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", GEOMS)
+def test_ce_upsampled_vs_oracle(D, n2, c, lo, hi):
+    _, x, g = inputs(n2, c, lo, 12)
+    tgt = labels(n2, hi, c, g)
+    wt = 0.5 + torch.rand((c,), generator=g, device=DEV)
+    for weight, avg in ((None, True), (wt, False), (wt, True)):
+        x1 = x.clone().requires_grad_(True)
+        loss = D.cross_entropy2d_upsampled(x1, tgt, weight, avg)
+        (loss * 0.7).backward()
+        x2 = x.double().cpu().requires_grad_(True)
+        ref = O.cross_entropy2d_upsampled(x2, tgt.cpu(), None if weight is None else weight.double().cpu(), avg)
+        (ref * 0.7).backward()
+        rel(loss, ref, "ce_up loss")
+        normwise(x1.grad, x2.grad, "ce_up grad")
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", GEOMS[:5])
+def test_seg_plus_kd_upsampled_is_the_sum_of_its_parts(D, n2, c, lo, hi):
+    tea, stu, g = inputs(n2, c, lo, 13)
+    tgt = labels(n2 // 2, hi, c, g)
+    s1 = stu.clone().requires_grad_(True)
+    l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s1, tgt, 0.5)
+    (1.0 * l_ce + 0.25 * l_kd).backward()
+    s2 = stu.double().cpu().requires_grad_(True)
+    r_ce, r_kd = O.seg_distillation_losses_upsampled(tea.double().cpu(), s2, tgt.cpu(), 0.5)
+    (1.0 * r_ce + 0.25 * r_kd).backward()
+    rel(l_ce, r_ce, "fused ce")
+    rel(l_kd, r_kd, "fused kd")
+    normwise(s1.grad, s2.grad, "fused grad")
+    # and bit-equal losses to the two stand-alone calls (same per-pixel expressions, same reduction order)
+    assert torch.equal(l_kd.detach(), D.distillation_loss_upsampled(tea, stu, hi, 0.5))
+    assert torch.equal(l_ce.detach(), D.cross_entropy2d_upsampled(stu[:n2 // 2].contiguous(), tgt))
+    # only one of the two outputs used: the other upstream is None
+    s3 = stu.clone().requires_grad_(True)
+    D.seg_distillation_losses_upsampled(tea, s3, tgt, 0.5)[1].backward()
+    s4 = stu.clone().requires_grad_(True)
+    D.distillation_loss_upsampled(tea, s4, hi, 0.5).backward()
+    normwise(s3.grad, s4.grad, "kd-only upstream")
+
+
+def test_losses_up_config2_size_matches_materialised_path_and_is_deterministic(D):
+    """[8,19,65,129] -> 512x1024 (config 2's logits before nn.Upsample): the fused path against diga's own materialised
+    path (bit-identical interpolation + kd kernel) and torch's up-sampling backward; two runs are bit-equal."""
+    n2, c, lo, hi = 8, 19, (65, 129), (512, 1024)
+    tea, stu, g = inputs(n2, c, lo, 14)
+    tgt = labels(n2 // 2, hi, c, g)
+    s1 = stu.clone().requires_grad_(True)
+    l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s1, tgt, 0.5)
+    (l_ce + 0.25 * l_kd).backward()
+    s2 = stu.clone().requires_grad_(True)
+    up_s = O.upsample_bilinear_ac(s2, hi)
+    m_kd = D.distillation_loss(O.upsample_bilinear_ac(tea, hi), up_s, 0.5)
+    m_ce = D.cross_entropy2d(up_s[:n2 // 2], tgt)
+    (m_ce + 0.25 * m_kd).backward()
+    rel(l_kd, m_kd, "kd"), rel(l_ce, m_ce, "ce")
+    normwise(s1.grad, s2.grad, "grad vs materialised path")
+    s3 = stu.clone().requires_grad_(True)
+    a_ce, a_kd = D.seg_distillation_losses_upsampled(tea, s3, tgt, 0.5)
+    (a_ce + 0.25 * a_kd).backward()
+    assert torch.equal(a_ce, l_ce) and torch.equal(a_kd, l_kd) and torch.equal(s3.grad, s1.grad)
+    # linearity of the backward in the upstream scalars (size-independent property)
+    s4 = stu.clone().requires_grad_(True)
+    b_ce, b_kd = D.seg_distillation_losses_upsampled(tea, s4, tgt, 0.5)
+    (2.0 * b_ce + 0.5 * b_kd).backward()
+    normwise(s4.grad, 2.0 * s1.grad, "linearity")
+
+
+def test_losses_up_errors(D):
+    tea, stu, g = inputs(2, 19, (8, 8), 15)
+    with pytest.raises(ValueError):
+        D.distillation_loss_upsampled(tea, stu, (4, 4))                        # down-sampling
+    with pytest.raises(ValueError):
+        D.distillation_loss_upsampled(tea[:1], stu[:1], (16, 16))              # odd batch
+    with pytest.raises(RuntimeError):
+        D.distillation_loss_upsampled(tea.cpu(), stu.cpu(), (16, 16))          # no CPU fallback
+    with pytest.raises(ValueError):
+        D.cross_entropy2d_upsampled(stu, torch.zeros((3, 16, 16), dtype=torch.long, device=DEV))
+    with pytest.raises(RuntimeError):
+        big = torch.zeros((2, 40, 4, 4), device=DEV)
+        D.distillation_loss_upsampled(big, big, (8, 8))                        # C > 32

@@ -215,3 +215,24 @@ def test_oracle_vs_live_reference():
             ocf.update_objective_SingleVector(i, v.detach().cpu().numpy(), "mean")
     assert torch.equal(rcf.objective_vectors, ocf.objective_vectors)
     assert torch.equal(rcf.get_centroid_weight(feat), ocf.get_centroid_weight(feat))
+
+
+def test_losses_upsampled_match_reference_bitwise(golden):
+    """self_training.py:289,:344,:348-356,:382-385 — both seg losses + KD from the stride-8 logits, with backward."""
+    g = golden("losses_up")
+    stu = T(g["student_low"]).requires_grad_(True)
+    mix = T(g["mix_low"]).requires_grad_(True)
+    tea, sl, ml = T(g["teacher_low"]), T(g["slabel"]), T(g["mixlabel"])
+    size = tuple(int(v) for v in g["size"])
+    loss_src, loss_kd = O.seg_distillation_losses_upsampled(tea, stu, sl, float(g["kd_scale"]))
+    loss_seg = loss_src + O.cross_entropy2d_upsampled(mix, ml)
+    total = float(g["lambda_seg"]) * loss_seg + float(g["lambda_distil"]) * loss_kd
+    total.backward()
+    assert np.array_equal(loss_src.detach().numpy(), g["loss_semseg_src"])
+    assert np.array_equal(loss_seg.detach().numpy(), g["loss_semseg"])
+    assert np.array_equal(loss_kd.detach().numpy(), g["loss_distil"])
+    assert np.array_equal(total.detach().numpy(), g["total_loss"])
+    assert np.array_equal(stu.grad.numpy(), g["grad_student_low"])
+    assert np.array_equal(mix.grad.numpy(), g["grad_mix_low"])
+    # the stand-alone forms are the same op chains
+    assert np.array_equal(O.distillation_loss_upsampled(tea, stu.detach(), size, float(g["kd_scale"])).numpy(), g["loss_distil"])
