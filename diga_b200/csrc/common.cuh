@@ -122,6 +122,23 @@ __device__ __forceinline__ float fast_log(float x) {
   return r * kLn2;
 }
 
+// The raw MUFU forms (log2 domain), for kernels that fold the log2(e) factor into an FFMA.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {   // MUFU.RCP, 1 ulp
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -18,9 +18,11 @@
 //                the rows) row i0 is complete for this strip and is flushed;
 //   horizontal : a flush stages the 128 column values per class in shared memory, and the CTA reduces the runs of
 //                columns that share a source column (i0 is monotone in X, so a run is a contiguous range);
-//   the CTA writes its partial low-resolution patch [R rows][C][K cols] to a scratch slot of its own;
+//   the CTA writes its partial low-resolution patch [R rows][K cols][C padded to 4] to a scratch slot of its own;
 //   gather     : a second, tiny kernel adds the <= 2x2 patches that overlap each low-resolution element, in fixed order.
 #include "bilinear.cuh"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace diga {
@@ -45,7 +47,7 @@ static inline void host_tap(float scale, int dst, int in, int* i0, int* i1) {
 
 static LossUpPlan make_plan(int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W) {
   LossUpPlan p;
-  p.ry = tunable("lossup_ry", 16);
+  p.ry = tunable("lossup_ry", 32);
   if (p.ry < 1) p.ry = 1;
   p.SX = (int)((W + kLuBlock - 1) / kLuBlock);
   p.SY = (int)((H + p.ry - 1) / p.ry);
@@ -69,7 +71,8 @@ static LossUpPlan make_plan(int64_t n, int64_t C, int64_t h, int64_t w, int64_t 
   p.ctas = n * p.SY * p.SX;
   p.off_partial = 16;
   p.off_scratch = (p.off_partial + (size_t)p.ctas * 3 * sizeof(double) + 15) & ~(size_t)15;
-  p.bytes = p.off_scratch + (size_t)p.ctas * p.R * C * p.K * sizeof(float);
+  const int64_t cp = C == 19 ? 20 : (C == 16 ? 16 : 32);   // class pitch of a patch column (DIGA_DISPATCH_C: 19, 16, padded 32)
+  p.bytes = p.off_scratch + (size_t)p.ctas * p.R * cp * p.K * sizeof(float);
   return p;
 }
 
@@ -96,20 +99,104 @@ struct LossUpArgs {
 
 __device__ __forceinline__ int lu_swz(int x) { return x + (x >> 3); }
 
+// Three-input max (sm_100: one FMNMX3 instead of two FMNMX).
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Vertical walk of one column in the log2 domain.  For the current source cell the thread keeps, per class,
+//     top[c] = (row_i0[c] - ref) * log2(e)     dif[c] = (row_i1[c] - row_i0[c]) * log2(e)
+// where row_* are the horizontally interpolated source rows and `ref` is the largest value either row holds in any
+// class, so that every interpolated value  v_c = top[c] + l1 * dif[c]  (ONE FFMA per class and output row) is <= 0 and
+// can go straight into ex2: no per-pixel max, no per-pixel rescaling.  softmax / log-sum-exp / soft-target cross
+// entropy are invariant to the choice of ref; `ref` only has to keep the sums away from underflow, which the caller
+// checks per pixel (it falls back to the exact per-pixel max when a sum drops below 2^-60).
+// The loss path is held to 1e-5, not to the bit pattern of ATen's up-sampler (the label paths keep ColumnInterp).
+template <int C, bool PAD>
+struct LerpColumn {
+  float top[C], dif[C];
+  float ref2 = 0.f;       // reference, log2 units
+
+  // dst[c] = l0s * v[c][k] + l1s * v[c][k + 1] - sub.  `q` points at v[0][k]; one 64-bit pointer bump per class, the
+  // second load is the same register with an immediate offset (PAIR = false: single-column source, w == 1).
+  template <bool PAIR>
+  __device__ __forceinline__ void hrow(float (&dst)[C], const float* __restrict__ q, int64_t class_stride, float l0s, float l1s,
+                                       float sub, int nclass) {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
+        dst[c] = fmaf(l0s, __ldg(q), fmaf(l1s, __ldg(q + (PAIR ? 1 : 0)), -sub));
+        q += class_stride;
+      }
+  }
+  __device__ __forceinline__ float rowmax(const float (&v)[C], int nclass) {
+    float m0 = v[0], m1 = v[0], m2 = v[0];
+#pragma unroll
+    for (int c = 1; c + 1 < C; c += 2) {
+      float& m = ((c >> 1) % 3 == 0) ? m0 : ((c >> 1) % 3 == 1) ? m1 : m2;
+      if (!PAD || c + 1 < nclass) m = fmax3(m, v[c], v[c + 1]);
+      else if (c < nclass) m = fmaxf(m, v[c]);
+    }
+    if constexpr ((C & 1) == 0) {
+      if (!PAD || C - 1 < nclass) m0 = fmaxf(m0, v[C - 1]);
+    }
+    return fmax3(m0, m1, m2);
+  }
+  // rows r0 (-> top) and r1 (-> bottom) of the cell; `fresh` = first cell of the strip, otherwise the old bottom row
+  // (top + dif) becomes the new top row.
+  __device__ __forceinline__ void enter(bool fresh, const float* __restrict__ base, int64_t row_stride, int64_t class_stride, int r0,
+                                        int r1, bool pair, float l0s, float l1s, int nclass) {
+    if (fresh) {
+      if (pair) hrow<true>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
+      else hrow<false>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
+      ref2 = 0.f;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) top[c] += dif[c];
+    }
+    float m = rowmax(top, nclass);
+    if (r1 != r0) {
+      if (pair) hrow<true>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
+      else hrow<false>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
+      m = fmaxf(m, rowmax(dif, nclass));
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dif[c] -= top[c];
+        top[c] -= m;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dif[c] = 0.f;
+        top[c] -= m;
+      }
+    }
+    ref2 += m;
+  }
+  __device__ __forceinline__ float value(float l1, int c) const { return fmaf(l1, dif[c], top[c]); }
+};
+
 template <int C, bool PAD, bool KD, bool CE, bool LOSS, bool GRAD>
-__global__ void __launch_bounds__(kLuBlock, GRAD ? 2 : 3)
+__global__ void __launch_bounds__(kLuBlock, GRAD ? 2 : 4)
 loss_up_kernel(const LossUpArgs a) {
+  extern __shared__ __align__(16) int2 ytab[];             // per-row vertical taps of the strip
   const int n = blockIdx.z, ky = blockIdx.y, kx = blockIdx.x, tid = threadIdx.x;
   const int X0 = kx * kLuBlock, X = X0 + tid;
   const bool in_range = X < a.W;
   const int Y0 = ky * a.ry, Yend = min(Y0 + a.ry, a.H);
   const int64_t plane = (int64_t)a.h * a.w;
   const int nclass = a.nclass;
-  Tap tx[1];
-  tx[0] = bilinear_tap(a.sw, in_range ? X : a.W - 1, a.w);
-  const float* sbase = a.stu + (int64_t)n * nclass * plane;
-  const float* tbase = nullptr;
+  const Tap tx = bilinear_tap(a.sw, in_range ? X : a.W - 1, a.w);
+  // Horizontal tap as the column pair (kc, kc + 1): a lane clamped at the last source column (i1 == i0) reads the pair
+  // (i0 - 1, i0) with weights (0, l0 + l1) so that the second load is always "first + 1" (a 1-column source has no pair).
+  const bool clamped = tx.i1 == tx.i0, pair = a.w > 1;
+  const int kc = (clamped && pair) ? tx.i0 - 1 : tx.i0;
+  const float l0s = (clamped ? (pair ? 0.f : tx.l0 + tx.l1) : tx.l0) * kLog2e;
+  const float l1s = (clamped ? (pair ? tx.l0 + tx.l1 : 0.f) : tx.l1) * kLog2e;
   float wkd = 0.f;
+  const float* tbase = nullptr;
   if constexpr (KD) {
     const int nt = n < a.B ? n + a.B : n - a.B;          // the other view supervises this one (loss.py:130-133)
     tbase = a.tea + (int64_t)nt * nclass * plane;
@@ -121,25 +208,37 @@ loss_up_kernel(const LossUpArgs a) {
   float ckd = 0.f, cce = 0.f;
   if constexpr (GRAD) {
     if constexpr (KD) ckd = (a.up_kd != nullptr ? __ldg(a.up_kd) : a.up_kd_host) * a.inv_count_kd * wkd;
-    if (ce_img) cce = __ldg(a.up_ce) / (a.size_average ? __ldg(a.denom) : 1.0f);
+    if (ce_img) cce = a.up_ce != nullptr ? __ldg(a.up_ce) / (a.size_average ? __ldg(a.denom) : 1.0f) : 1.0f;
   }
 
-  // ---- backward staging (shared memory) ------------------------------------------------------------------------------
-  __shared__ float sa[GRAD ? C : 1][GRAD ? kLuLd : 1];
-  __shared__ float sb[GRAD ? C : 1][GRAD ? kLuLd : 1];
+  // ---- CTA geometry: source rows from ylo, source columns xlo..xhi --------------------------------------------------
+  const int nvalid = min(kLuBlock, a.W - X0);
+  const int xlo = bilinear_tap(a.sw, X0, a.w).i0;
+  const int Kt = bilinear_tap(a.sw, X0 + nvalid - 1, a.w).i1 - xlo + 1;
+  const int ylo = bilinear_tap(a.sh, Y0, a.h).i0;
+  const float* scol = a.stu + (int64_t)n * nclass * plane + (int64_t)ylo * a.w + kc;   // (row ylo, class 0, column kc)
+  const float* tcol = KD ? tbase + (int64_t)ylo * a.w + kc : nullptr;
+
+  // per-row vertical taps, computed once per CTA: {local row of i0 | (i1 - i0) << 16, l1}
+  for (int i = tid; i < Yend - Y0; i += kLuBlock) {
+    const Tap t = bilinear_tap(a.sh, Y0 + i, a.h);
+    ytab[i] = make_int2((t.i0 - ylo) | ((t.i1 - t.i0) << 16), __float_as_int(t.l1));
+  }
+
+  // ---- backward staging (shared memory): [column (swizzled)][class], classes padded to a multiple of four ----------
+  constexpr int CP = (C + 3) & ~3, CQ = CP / 4;
+  __shared__ __align__(16) float sa[GRAD ? kLuLd : 1][GRAD ? CP : 4];
+  __shared__ __align__(16) float sb[GRAD ? kLuLd : 1][GRAD ? CP : 4];
   __shared__ int st[GRAD ? kLuBlock + 4 : 1];
-  int xlo = 0, Kt = 0, ylo = 0;
   const int64_t cta = ((int64_t)n * gridDim.y + ky) * gridDim.x + kx;
   if constexpr (GRAD) {
-    const int nvalid = min(kLuBlock, a.W - X0);
-    xlo = bilinear_tap(a.sw, X0, a.w).i0;
-    Kt = bilinear_tap(a.sw, X0 + nvalid - 1, a.w).i1 - xlo + 1;
-    ylo = bilinear_tap(a.sh, Y0, a.h).i0;
     for (int i = tid; i <= Kt; i += kLuBlock) st[i] = nvalid;
-    __syncthreads();
+  }
+  __syncthreads();
+  if constexpr (GRAD) {
     if (in_range) {
       const int prev = tid == 0 ? -1 : bilinear_tap(a.sw, X - 1, a.w).i0;
-      if (tx[0].i0 != prev) st[tx[0].i0 - xlo] = tid;      // first column of the run that maps to source column i0
+      if (tx.i0 != prev) st[tx.i0 - xlo] = tid;            // first column of the run that maps to source column i0
     }
     __syncthreads();
   }
@@ -148,95 +247,128 @@ loss_up_kernel(const LossUpArgs a) {
 #pragma unroll
     for (int c = 0; c < C; ++c) Gt[c] = Gb[c] = 0.f;
   }
+  // flush: horizontal half of the transposed interpolation for one completed source row.  Every column stages
+  // l0*G (-> source column i0) and l1*G (-> i0 + 1) as float4 class quads; a work item (source column, class quad) sums
+  // the contiguous run of output columns that map to it and stores one float4 of the CTA's patch [row][column][CP].
   auto flush = [&](const float (&G)[GRAD ? C : 1], int row) {
     if constexpr (GRAD) {
-      const bool clamped = tx[0].i1 == tx[0].i0;
       const int sx = lu_swz(tid);
+      const float wa = in_range ? (clamped ? tx.l0 + tx.l1 : tx.l0) : 0.f;
+      const float wb = (in_range && !clamped) ? tx.l1 : 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        if (!PAD || c < nclass) {
-          const float gv = in_range ? G[c] : 0.f;
-          float va = tx[0].l0 * gv, vb = tx[0].l1 * gv;
-          if (clamped) {
-            va += vb;
-            vb = 0.f;
-          }
-          sa[c][sx] = va;
-          sb[c][sx] = vb;
+      for (int q = 0; q < CQ; ++q) {
+        float4 va, vb;
+        float* pa = reinterpret_cast<float*>(&va);
+        float* pb = reinterpret_cast<float*>(&vb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * q + k;
+          const float gv = (c < C && (!PAD || c < nclass)) ? G[c < C ? c : 0] : 0.f;
+          pa[k] = wa * gv;
+          pb[k] = wb * gv;
         }
+        *reinterpret_cast<float4*>(&sa[sx][4 * q]) = va;
+        *reinterpret_cast<float4*>(&sb[sx][4 * q]) = vb;
+      }
       __syncthreads();
-      float* dst = a.scratch + ((cta * a.R + row) * nclass) * a.K;
-      for (int j = tid; j < nclass * Kt; j += kLuBlock) {
-        const int c = j / Kt, xl = j - c * Kt;
-        float sum = 0.f;
-        for (int i = st[xl]; i < st[xl + 1]; ++i) sum += sa[c][lu_swz(i)];
+      float4* dst = reinterpret_cast<float4*>(a.scratch + ((cta * a.R + row) * a.K) * CP);
+      for (int j = tid; j < Kt * CQ; j += kLuBlock) {
+        const int xl = j / CQ, q = j - xl * CQ;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = st[xl]; i < st[xl + 1]; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(&sa[lu_swz(i)][4 * q]);
+          sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+        }
         if (xl > 0)
-          for (int i = st[xl - 1]; i < st[xl]; ++i) sum += sb[c][lu_swz(i)];
-        dst[c * a.K + xl] = sum;
+          for (int i = st[xl - 1]; i < st[xl]; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(&sb[lu_swz(i)][4 * q]);
+            sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+          }
+        dst[xl * CQ + q] = sum;
       }
       __syncthreads();
     }
   };
 
-  ColumnInterp<C, PAD, 1> cs;
-  ColumnInterp<KD ? C : 1, PAD, 1> ct;
+  LerpColumn<C, PAD> cs;
+  LerpColumn<KD ? C : 1, PAD> ct;
   float acc_kd = 0.f, acc_ce = 0.f, acc_cnt = 0.f;
-  int cur_i0 = -1, cur_i1 = -1;
+  int cur_r0 = -1, cur_r1 = -1;
   int64_t tgt = 0, tgt_next = 0;
   if (ce_img) tgt = ld_stream_i64(trow + (int64_t)Y0 * a.W);
 
   for (int Y = Y0; Y < Yend; ++Y) {
     if (ce_img && Y + 1 < Yend) tgt_next = ld_stream_i64(trow + (int64_t)(Y + 1) * a.W);
-    const Tap ty = bilinear_tap(a.sh, Y, a.h);
-    if constexpr (GRAD) {
-      if (cur_i0 >= 0 && ty.i0 != cur_i0) {                // crossed into the next source cell: row cur_i0 is complete
-        flush(Gt, cur_i0 - ylo);
+    const int t32 = (CE && tgt >= 0 && tgt < nclass) ? (int)tgt : -1;     // class index of a supervised pixel, else -1
+    const int2 yt = ytab[Y - Y0];
+    const int r0 = yt.x & 0xffff, r1 = r0 + (yt.x >> 16);
+    const float yl1 = __int_as_float(yt.y), yl0 = 1.0f - yl1;
+    if (r0 != cur_r0) {                                      // first row, or crossed into the next source cell (CTA-uniform)
+      if constexpr (GRAD) {
+        if (cur_r0 >= 0) {
+          flush(Gt, cur_r0);                                 // source row cur_r0 is complete for this strip
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          Gt[c] = Gb[c];
-          Gb[c] = 0.f;
+          for (int c = 0; c < C; ++c) {
+            Gt[c] = Gb[c];
+            Gb[c] = 0.f;
+          }
         }
       }
+      cs.enter(cur_r0 < 0, scol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+      if constexpr (KD) ct.enter(cur_r0 < 0, tcol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+      cur_r0 = r0;
+      cur_r1 = r1;
     }
-    cur_i0 = ty.i0;
-    cur_i1 = ty.i1;
-    cs.seek(ty, sbase, plane, a.w, tx, nclass);
-    if constexpr (KD) ct.seek(ty, tbase, plane, a.w, tx, nclass);
 
-    float s[C], t[KD ? C : 1];
+    // Per-pixel statistics in the log2 domain, relative to the cell reference (see LerpColumn):
+    //   es_c = 2^v_c, Ss = sum es_c, (KD) e_c = 2^u_c, St = sum e_c, cross2 = sum e_c v_c.
+    // Sums run as four interleaved chains.  EXACT re-bases on the per-pixel max (taken only after an underflow).
+    float es[GRAD ? C : 1], et[(GRAD && KD) ? C : 1];
+    float Ss = 0.f, St = 0.f, cross2 = 0.f, dtgt = 0.f;
+    auto stats = [&](auto exact_tag) {
+      constexpr bool EXACT = decltype(exact_tag)::value;
+      float ms = 0.f, mt = 0.f;
+      if constexpr (EXACT) {
+        ms = mt = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) {
-        s[c] = cs.value(ty, 0, c);
-        if constexpr (KD) t[c] = ct.value(ty, 0, c);
+        for (int c = 0; c < C; ++c)
+          if (!PAD || c < nclass) {
+            ms = fmaxf(ms, cs.value(yl1, c));
+            if constexpr (KD) mt = fmaxf(mt, ct.value(yl1, c));
+          }
       }
-    float ms = s[0], mt = KD ? t[0] : 0.f;
+      float Ss4[4] = {0.f, 0.f, 0.f, 0.f}, St4[4] = {0.f, 0.f, 0.f, 0.f}, cr4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 1; c < C; ++c)
-      if (!PAD || c < nclass) {
-        ms = fmaxf(ms, s[c]);
-        if constexpr (KD) mt = fmaxf(mt, t[c]);
-      }
-    float Ss = 0.f, St = 0.f, cross = 0.f, dtgt = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) {
-        const float d = s[c] - ms;
-        const float es = fast_exp(d);
-        Ss += es;
-        if constexpr (KD) {
-          const float e = fast_exp(t[c] - mt);
-          St += e;
-          cross = fmaf(e, d, cross);
-          t[c] = e;
+      for (int c = 0; c < C; ++c)
+        if (!PAD || c < nclass) {
+          float v = cs.value(yl1, c);
+          if constexpr (EXACT) v -= ms;
+          const float e_s = fast_ex2(v);
+          Ss4[c & 3] += e_s;
+          if constexpr (KD) {
+            float u = ct.value(yl1, c);
+            if constexpr (EXACT) u -= mt;
+            const float e_t = fast_ex2(u);
+            St4[c & 3] += e_t;
+            cr4[c & 3] = fmaf(e_t, v, cr4[c & 3]);
+            if constexpr (GRAD) et[c] = e_t;
+          }
+          if constexpr (CE) {
+            if (t32 == c) dtgt = v;
+          }
+          if constexpr (GRAD) es[c] = e_s;
         }
-        if constexpr (CE) {
-          if (tgt == c) dtgt = d;
-        }
-        s[c] = es;
+      Ss = (Ss4[0] + Ss4[1]) + (Ss4[2] + Ss4[3]);
+      if constexpr (KD) {
+        St = (St4[0] + St4[1]) + (St4[2] + St4[3]);
+        cross2 = (cr4[0] + cr4[1]) + (cr4[2] + cr4[3]);
       }
+    };
+    stats(std::false_type{});
+    if (Ss < 0x1p-60f || (KD && St < 0x1p-60f)) stats(std::true_type{});   // adjacent source rows > 41 logits apart
+
     float inv_t = 0.f;
-    if constexpr (KD) inv_t = 1.0f / St;
+    if constexpr (KD) inv_t = fast_rcp(St);
     float wt = 1.f;
     bool counted = false, valid = false;
     if constexpr (CE) {
@@ -244,53 +376,62 @@ loss_up_kernel(const LossUpArgs a) {
       valid = counted && tgt < nclass;                              // 255 (any id >= C) is ignored by nll_loss
       if (valid && a.weight != nullptr) wt = __ldg(a.weight + tgt);
     }
-    if constexpr (LOSS) {
-      const float lse = fast_log(Ss);
+    if constexpr (LOSS) {                                            // accumulated in log2 units (x ln 2 at the end)
+      const float lse2 = fast_lg2(Ss);
       if constexpr (KD) {
-        if (in_range) acc_kd += wkd * (lse - cross * inv_t);
+        if (in_range) acc_kd += wkd * (lse2 - cross2 * inv_t);
       }
       if constexpr (CE) {
-        if (valid) acc_ce += wt * (lse - dtgt);
+        if (valid) acc_ce += wt * (lse2 - dtgt);
         if (counted) acc_cnt += 1.f;
       }
     }
     if constexpr (GRAD) {
       const float cpx = (CE && valid) ? wt * cce : 0.f;
-      const float ga = (ckd + cpx) / Ss;
+      const float ga = (ckd + cpx) * fast_rcp(Ss);
       const float gb = ckd * inv_t;
 #pragma unroll
       for (int c = 0; c < C; ++c)
         if (!PAD || c < nclass) {
-          float g = ga * s[c];
-          if constexpr (KD) g = fmaf(-gb, t[c], g);
-          if constexpr (CE) g -= (tgt == c) ? cpx : 0.f;
-          Gt[c] = fmaf(ty.l0, g, Gt[c]);
-          Gb[c] = fmaf(ty.l1, g, Gb[c]);
+          float g = ga * es[c];
+          if constexpr (KD) g = fmaf(-gb, et[c], g);
+          if constexpr (CE) g -= (t32 == c) ? cpx : 0.f;
+          Gt[c] = fmaf(yl0, g, Gt[c]);
+          Gb[c] = fmaf(yl1, g, Gb[c]);
         }
     }
     tgt = tgt_next;
   }
 
   if constexpr (GRAD) {
-    if (cur_i1 == cur_i0) {                                  // clamped at the last source row: both taps hit it
+    if (cur_r1 == cur_r0) {                                  // clamped at the last source row: both taps hit it
 #pragma unroll
       for (int c = 0; c < C; ++c) Gt[c] += Gb[c];
-      flush(Gt, cur_i0 - ylo);
+      flush(Gt, cur_r0);
     } else {
-      flush(Gt, cur_i0 - ylo);
-      flush(Gb, cur_i1 - ylo);
+      flush(Gt, cur_r0);
+      flush(Gb, cur_r1);
     }
   }
 
   if constexpr (LOSS) {
-    __shared__ float red[kLuBlock / 32];
+    __shared__ float red[3][kLuBlock / 32];
     __shared__ bool is_last;
-    const float bk = block_sum<kLuBlock>(acc_kd, red);
+    const float wk = warp_sum(acc_kd), wc = CE ? warp_sum(acc_ce) : 0.f, wn = CE ? warp_sum(acc_cnt) : 0.f;
+    if ((tid & 31) == 0) {
+      red[0][tid >> 5] = wk;
+      red[1][tid >> 5] = wc;
+      red[2][tid >> 5] = wn;
+    }
     __syncthreads();
-    const float bc = block_sum<kLuBlock>(acc_ce, red);
-    __syncthreads();
-    const float bn = block_sum<kLuBlock>(acc_cnt, red);
     if (tid == 0) {
+      float bk = 0.f, bc = 0.f, bn = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLuBlock / 32; ++i) {
+        bk += red[0][i];
+        bc += red[1][i];
+        bn += red[2][i];
+      }
       a.partial[3 * cta + 0] = (double)bk;
       a.partial[3 * cta + 1] = (double)bc;
       a.partial[3 * cta + 2] = (double)bn;
@@ -322,9 +463,9 @@ loss_up_kernel(const LossUpArgs a) {
         __syncthreads();
       }
       if (tid == 0) {
-        if (KD && a.loss_kd) a.loss_kd[0] = (float)(dr[0][0] * (double)a.inv_count_kd);
+        if (KD && a.loss_kd) a.loss_kd[0] = (float)(dr[0][0] * 0.6931471805599453 * (double)a.inv_count_kd);
         if constexpr (CE) {
-          const float cnt = (float)dr[2][0], tot = (float)dr[1][0];
+          const float cnt = (float)dr[2][0], tot = (float)(dr[1][0] * 0.6931471805599453);
           if (a.loss_ce) a.loss_ce[0] = a.size_average ? tot / cnt : tot;   // fp32 division like `loss /= mask.data.sum()`
           if (a.denom_out) a.denom_out[0] = cnt;
         }
@@ -334,48 +475,65 @@ loss_up_kernel(const LossUpArgs a) {
   }
 }
 
-// dlow[n,c,y,x] = sum of the scratch patches that cover (y,x): strips in increasing ky, tiles in increasing kx.
+// dlow[n,c,y,x] = sum of the scratch patches that cover (y,x): strips in increasing ky, tiles in increasing kx (fixed
+// order: deterministic).  One CTA per (image, source row): the matching strips are CTA-uniform, a thread owns one
+// source column, resolves its patches (at most 2 x 2, else the generic loop) and adds their class vectors as float4s;
+// the stores are coalesced per class plane.
 template <int C, bool PAD>
 __global__ void __launch_bounds__(128)
-loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlow, int nclass, int n, int h, int w, int H,
-                      int W, float sh, float sw, int ry, int R, int K, int SX, int SY) {
-  const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (idx >= (int64_t)n * h * w) return;
-  const int x = (int)(idx % w);
-  const int y = (int)((idx / w) % h);
-  const int img = (int)(idx / ((int64_t)h * w));
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
-  // strips / tiles that can hold (y, x): output rows with i0 in {y-1, y} lie in [(y-1)/sh, (y+1)/sh]
-  int ky0 = 0, ky1 = SY - 1, kx0 = 0, kx1 = SX - 1;
+loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlow, int nclass, int h, int w, int H, int W,
+                      float sh, float sw, float inv_sh_ry, float inv_sw_bx, int ry, int R, int K, int SX, int SY) {
+  constexpr int CP = (C + 3) & ~3, CQ = CP / 4;
+  const int y = blockIdx.x, img = blockIdx.y;
+  // candidate strips: output rows with i0 in {y-1, y} lie in [(y-1)/sh, (y+1)/sh]; one strip of slack either side,
+  // then the exact test with the kernel's own tap arithmetic (matching strips are contiguous: ylo, yhi are monotone)
+  int kyA = 0, kyB = SY - 1;
   if (sh > 0.f) {
-    ky0 = max(0, (int)(((float)y - 1.f) / sh) / ry - 1);
-    ky1 = min(SY - 1, (int)(((float)y + 1.f) / sh) / ry + 1);
+    kyA = max(0, (int)((float)max(y - 1, 0) * inv_sh_ry) - 1);
+    kyB = min(SY - 1, (int)((float)(y + 1) * inv_sh_ry) + 1);
   }
-  if (sw > 0.f) {
-    kx0 = max(0, (int)(((float)x - 1.f) / sw) / kLuBlock - 1);
-    kx1 = min(SX - 1, (int)(((float)x + 1.f) / sw) / kLuBlock + 1);
-  }
-  for (int ky = ky0; ky <= ky1; ++ky) {
-    const int ylo = bilinear_tap(sh, ky * ry, h).i0;
-    const int yhi = bilinear_tap(sh, min((ky + 1) * ry, H) - 1, h).i1;
-    if (y < ylo || y > yhi) continue;
-    for (int kx = kx0; kx <= kx1; ++kx) {
-      const int xlo = bilinear_tap(sw, kx * kLuBlock, w).i0;
-      const int xhi = bilinear_tap(sw, min((kx + 1) * kLuBlock, W) - 1, w).i1;
-      if (x < xlo || x > xhi) continue;
-      const int64_t cta = ((int64_t)img * SY + ky) * SX + kx;
-      const float* src = scratch + ((cta * R + (y - ylo)) * nclass) * K + (x - xlo);
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-        if (!PAD || c < nclass) acc[c] += __ldcg(src + c * K);
+  while (kyA <= kyB && bilinear_tap(sh, min((kyA + 1) * ry, H) - 1, h).i1 < y) ++kyA;
+  while (kyB >= kyA && bilinear_tap(sh, kyB * ry, h).i0 > y) --kyB;
+  const int64_t plane = (int64_t)h * w;
+  for (int x = threadIdx.x; x < w; x += 128) {
+    int kxA = 0, kxB = SX - 1;
+    if (sw > 0.f) {
+      kxA = max(0, (int)((float)max(x - 1, 0) * inv_sw_bx) - 1);
+      kxB = min(SX - 1, (int)((float)(x + 1) * inv_sw_bx) + 1);
     }
-  }
-  float* dst = dlow + ((int64_t)img * nclass * h + y) * w + x;
+    while (kxA <= kxB && bilinear_tap(sw, min((kxA + 1) * kLuBlock, W) - 1, w).i1 < x) ++kxA;
+    while (kxB >= kxA && bilinear_tap(sw, kxB * kLuBlock, w).i0 > x) --kxB;
+    auto patch_ptr = [&](int ky, int kx) {
+      const int ylo = bilinear_tap(sh, ky * ry, h).i0, xlo = bilinear_tap(sw, kx * kLuBlock, w).i0;
+      const int64_t cta = ((int64_t)img * SY + ky) * SX + kx;
+      return reinterpret_cast<const float4*>(scratch + (((cta * R + (y - ylo)) * K) + (x - xlo)) * CP);
+    };
+    float4 acc[CQ];
 #pragma unroll
-  for (int c = 0; c < C; ++c)
-    if (!PAD || c < nclass) dst[(int64_t)c * h * w] = acc[c];
+    for (int q = 0; q < CQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto add = [&](const float4* p) {
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) {
+        const float4 v = __ldcg(p + q);
+        acc[q].x += v.x, acc[q].y += v.y, acc[q].z += v.z, acc[q].w += v.w;
+      }
+    };
+    const int ny = kyB - kyA + 1, nx = kxB - kxA + 1;
+    if (ny >= 1 && ny <= 2 && nx >= 1 && nx <= 2) {
+      add(patch_ptr(kyA, kxA));
+      if (nx == 2) add(patch_ptr(kyA, kxB));
+      if (ny == 2) add(patch_ptr(kyB, kxA));
+      if (nx == 2 && ny == 2) add(patch_ptr(kyB, kxB));
+    } else {
+      for (int ky = kyA; ky <= kyB; ++ky)
+        for (int kx = kxA; kx <= kxB; ++kx) add(patch_ptr(ky, kx));
+    }
+    float* dst = dlow + (int64_t)img * nclass * plane + (int64_t)y * w + x;
+    const float* av = reinterpret_cast<const float*>(acc);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) dst[c * plane] = av[c];
+  }
 }
 
 static int check_common(const char* who, const float* stu, int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W,
@@ -392,13 +550,16 @@ static int check_common(const char* who, const float* stu, int64_t n, int64_t C,
 template <bool KD, bool CE, bool LOSS, bool GRAD>
 static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* dlow, cudaStream_t st) {
   dim3 grid((unsigned)p.SX, (unsigned)p.SY, (unsigned)a.n);
+  const size_t tab_bytes = (size_t)p.ry * sizeof(int2);
+  DIGA_REQUIRE(tab_bytes <= 32 * 1024, DIGA_ERR_INVALID, "loss_up: strip height %d too large", p.ry);
   DIGA_DISPATCH_C(C, {
-    loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD><<<grid, kLuBlock, 0, st>>>(a);
+    loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD><<<grid, kLuBlock, tab_bytes, st>>>(a);
     DIGA_CHECK_LAUNCH("loss_up_kernel");
     if (GRAD) {
-      const int64_t total = (int64_t)a.n * a.h * a.w;
-      loss_up_gather_kernel<kC, kPad><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-          a.scratch, dlow, a.nclass, a.n, a.h, a.w, a.H, a.W, a.sh, a.sw, p.ry, p.R, p.K, p.SX, p.SY);
+      const float inv_sh_ry = a.sh > 0.f ? 1.0f / (a.sh * (float)p.ry) : 0.f;
+      const float inv_sw_bx = a.sw > 0.f ? 1.0f / (a.sw * (float)kLuBlock) : 0.f;
+      loss_up_gather_kernel<kC, kPad><<<dim3((unsigned)a.h, (unsigned)a.n), 128, 0, st>>>(
+          a.scratch, dlow, a.nclass, a.h, a.w, a.H, a.W, a.sh, a.sw, inv_sh_ry, inv_sw_bx, p.ry, p.R, p.K, p.SX, p.SY);
       DIGA_CHECK_LAUNCH("loss_up_gather_kernel");
     }
   });
@@ -507,6 +668,21 @@ int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64
   a.up_kd_host = upstream_host;
   a.loss_kd = loss_out;
   return launch_loss_up<true, false, true, true>(a, p, C, dstudent_low, (cudaStream_t)stream);
+}
+
+int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
+                       int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
+                       float* dlogits_sum, void* workspace, diga_stream_t stream) {
+  using namespace diga;
+  if (int rc = check_common("ce_up_fwd_bwd", logits_low, n, C, h, w, H, W, workspace)) return rc;
+  DIGA_REQUIRE(target && loss_out && denom_out && dlogits_sum, DIGA_ERR_INVALID, "ce_up_fwd_bwd: null pointer");
+  DIGA_REQUIRE(aligned(target, 8) && aligned(weight, 4) && aligned(dlogits_sum, 4), DIGA_ERR_MISALIGNED,
+               "ce_up_fwd_bwd: misaligned pointer");
+  const LossUpPlan p = make_plan(n, C, h, w, H, W);
+  LossUpArgs a = fill_args(p, workspace, nullptr, logits_low, target, weight, n, n, C, h, w, H, W, 0.f, size_average);
+  a.loss_ce = loss_out;
+  a.denom_out = denom_out;          // up_ce == null: the gradient of the SUMMED loss (the caller scales by upstream / denom)
+  return launch_loss_up<false, true, true, true>(a, p, C, dlogits_sum, (cudaStream_t)stream);
 }
 
 }  // extern "C"

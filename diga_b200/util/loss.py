@@ -120,7 +120,12 @@ def _size2(size):
 
 
 class _LossesUpsampled(torch.autograd.Function):
-    """(loss_ce, loss_kd) of the first ``n_ce`` / all images of ``student_low``; either part may be switched off."""
+    """(loss_ce, loss_kd) of the first ``n_ce`` / all images of ``student_low``; either part may be switched off.
+
+    With a single loss and a student that requires grad, the forward launches the loss+gradient kernel (the gradient with
+    a unit upstream costs one pass instead of two: both passes are bound by the same 38 exponentials per pixel) and the
+    backward only scales it by the upstream scalar on the device.  With both losses the backward is its own pass, because
+    the two upstream scalars are unknown until then."""
 
     @staticmethod
     def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average):
@@ -132,26 +137,44 @@ class _LossesUpsampled(torch.autograd.Function):
         hh, ww = size
         n_ce = 0 if tg is None else tg.shape[0]
         dev = s.device
-        loss_kd = torch.zeros((), dtype=torch.float32, device=dev) if t is None else torch.empty((), dtype=torch.float32, device=dev)
-        loss_ce = torch.zeros((), dtype=torch.float32, device=dev) if tg is None else torch.empty((), dtype=torch.float32, device=dev)
+        new = lambda: torch.empty((), dtype=torch.float32, device=dev)
+        zero = lambda: torch.zeros((), dtype=torch.float32, device=dev)
+        loss_kd = zero() if t is None else new()
+        loss_ce = zero() if tg is None else new()
         denom = torch.ones((), dtype=torch.float32, device=dev)
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
-        L.check(L.lib.diga_loss_up_fwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww, float(scale),
-                                       int(bool(size_average)), loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(),
-                                       ws.data_ptr(), L.stream()))
-        ctx.save_for_backward(s, denom)
-        ctx.aux = (t, tg, wt, (hh, ww), float(scale), int(bool(size_average)), n_ce)
+        size_average = int(bool(size_average))
+        unit = None
+        if ctx.needs_input_grad[1] and (t is None) != (tg is None):
+            unit = torch.empty_like(s)
+            if tg is None:
+                L.check(L.lib.diga_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), n, c, h, w, hh, ww, float(scale), 1.0,
+                                                 loss_kd.data_ptr(), unit.data_ptr(), ws.data_ptr(), L.stream()))
+            else:
+                L.check(L.lib.diga_ce_up_fwd_bwd(s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, c, h, w, hh, ww, size_average,
+                                                 loss_ce.data_ptr(), denom.data_ptr(), unit.data_ptr(), ws.data_ptr(),
+                                                 L.stream()))
+            ctx.save_for_backward(unit, denom)
+        else:
+            L.check(L.lib.diga_loss_up_fwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww,
+                                           float(scale), size_average, loss_kd.data_ptr(), loss_ce.data_ptr(),
+                                           denom.data_ptr(), ws.data_ptr(), L.stream()))
+            ctx.save_for_backward(s, denom)
+        ctx.aux = (t, tg, wt, (hh, ww), float(scale), size_average, n_ce, unit is not None)
         return loss_ce, loss_kd
 
     @staticmethod
     def backward(ctx, g_ce, g_kd):
         s, denom = ctx.saved_tensors
-        t, tg, wt, (hh, ww), scale, size_average, n_ce = ctx.aux
+        t, tg, wt, (hh, ww), scale, size_average, n_ce, have_unit = ctx.aux
         n, c, h, w = s.shape
         dev = s.device
         as_scalar = lambda g: (torch.zeros((), dtype=torch.float32, device=dev) if g is None
                                else g.to(dtype=torch.float32, device=dev).contiguous())
         g_ce, g_kd = as_scalar(g_ce), as_scalar(g_kd)                 # 0-dim device scalars, read on the GPU
+        if have_unit:                                                 # `s` is the unit gradient saved by the forward
+            coef = g_kd if tg is None else (g_ce / denom if size_average else g_ce)
+            return None, s * coef, None, None, None, None, None
         ds = torch.empty_like(s)
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
         L.check(L.lib.diga_loss_up_bwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww, scale,

@@ -212,6 +212,11 @@ int diga_loss_up_bwd(const float* teacher_low, const float* student_low, const i
                      int64_t n, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
                      int size_average, const float* upstream_kd, const float* upstream_ce, const float* denom,
                      float* dstudent_low, void* workspace, diga_stream_t stream);
+/* CE loss and, in the same pass, the gradient of the SUMMED loss (size_average only affects loss_out): the caller scales
+ * it by upstream / denom_out — what the autograd wrapper does when the logits require a gradient. */
+int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
+                       int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
+                       float* dlogits_sum, void* workspace, diga_stream_t stream);
 int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
                        int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
                        void* workspace, diga_stream_t stream);

@@ -37,4 +37,15 @@ elif which == "plup":
     l1, l2 = S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g)
     for _ in range(3):
         D.pseudo_label_two_scale(l1, l2, (1024, 2048))
+elif which == "lossup":
+    tea, stu = S.logits((8, 19, 65, 129), g), S.logits((8, 19, 65, 129), g)
+    tgt = S.block_labels(4, 512, 1024, g)
+    one, up = torch.tensor(1.0, device=dev), torch.tensor(0.25, device=dev)
+    for _ in range(2):
+        s = stu.detach().requires_grad_(True)
+        l_kd = D.distillation_loss_upsampled(tea, s, (512, 1024), 0.5)                 # loss kernel (KD)
+        torch.autograd.grad(l_kd, s, grad_outputs=up)                                  # grad kernel (KD) + gather
+        s = stu.detach().requires_grad_(True)
+        l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s, tgt, 0.5)             # loss kernel (KD+CE)
+        torch.autograd.grad([l_ce, l_kd], s, grad_outputs=[one, up])                   # grad kernel (KD+CE) + gather
 torch.cuda.synchronize()

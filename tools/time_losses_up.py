@@ -21,10 +21,25 @@ os.makedirs(os.path.dirname(out_path), exist_ok=True)
 fout = open(out_path, "a")
 
 
-def timeit(fn, iters=30, warm=5):
+def timeit(fn, iters=30, warm=5, graph=True):
+    """ms per call; sync-free calls are replayed from a CUDA graph so the Python call chain is not what is timed."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                keep = fn()                          # noqa: F841
+        torch.cuda.current_stream().wait_stream(side)
+        fn = gph.replay
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
