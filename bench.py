@@ -359,6 +359,87 @@ def bench_stages(D, S, dev, peak, world, quick):
     del f5
     feat = S.features((b, d, h, w), g)
 
+    # next row f1 for the loss consumers: the losses straight from the stride-8 logits (config 2's tensors before
+    # nn.Upsample): KD fwd+bwd, cross_entropy2d fwd+bwd, and the shared-student seg + KD pair of self_training.py:348-352
+    lo_t, lo_s = S.logits((8, C, h, w), g), S.logits((8, C, h, w), g)
+    up_kd = torch.tensor(UPSTREAM, device=dev)
+
+    def kd_up_step():
+        x = lo_s.detach().requires_grad_(True)
+        loss = D.distillation_loss_upsampled(lo_t, x, (hh, ww), 0.5)
+        return loss, torch.autograd.grad(loss, x, grad_outputs=up_kd)
+
+    def ce_up_step():
+        x = lo_s[:4].detach().requires_grad_(True)
+        loss = D.cross_entropy2d_upsampled(x, ce_t)
+        return loss, torch.autograd.grad(loss, x, grad_outputs=upc)
+
+    def seg_kd_up_step():
+        x = lo_s.detach().requires_grad_(True)
+        l_ce, l_kd = D.seg_distillation_losses_upsampled(lo_t, x, ce_t, 0.5)
+        return l_ce, l_kd, torch.autograd.grad([l_ce, l_kd], x, grad_outputs=[upc, up_kd])
+
+    lowres_bytes = 3 * C * 4 * (h * w) / (hh * ww)          # teacher + student read, gradient written, per output pixel
+    add("kd_fused_upsample_fwd_bwd", 8 * hh * ww, lowres_bytes, kd_up_step,
+        extra={"note": "distillation_loss_upsampled + autograd from [8,19,65,129]: replaces 2 up-samplings (76 B/px written each), "
+                       "the 380 B/px KD pair and the up-sampling backward; ALU/MUFU-bound (38 ex2 per pixel-position)"})
+    add("cross_entropy2d_fused_upsample_fwd_bwd", 4 * hh * ww, 8 + 2 * C * 4 * (h * w) / (hh * ww), ce_up_step)
+    add("seg_plus_kd_fused_upsample_fwd_bwd", 8 * hh * ww, lowres_bytes + 4, seg_kd_up_step,
+        extra={"note": "self_training.py:348-352 on the shared s_pred_cat_stu: CE on the source half + KD on both views, "
+                       "one loss pass + one gradient pass over the stride-8 logits"})
+
+    # config 3: the whole per-step hot path of train_DiGA_gta2city_self_training.py:259-356 (no backbone), B=8 @512x1024,
+    # D=2048: ClassMix #1, prototype weights, consensus selection, ClassMix #2 (DACS), two label-gated centroid EMA
+    # updates, seg losses + KD with backward to the stride-8 logits.  "dropin" = only the reference's own function names
+    # swapped (losses on nn.Upsample outputs, torch interpolates), "fused" = the patched call sites of INTEGRATION.md.
+    from diga_b200.calc_centroids import _labels_on_feature_grid
+    import torch.nn.functional as F
+    s_feat = S.features((b, d, h, w), g)
+    t_pred, s_pred = S.logits((b, C, h, w), g), S.logits((b, C, h, w), g)
+    rec, saug = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    tdata_aug, sdata = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    tea_cat, stu_cat = S.logits((2 * b, C, h, w), g), S.logits((2 * b, C, h, w), g)
+    cross_low = S.logits((b, C, h, w), g)
+    cf.objective_vectors_num = torch.full((C,), 150.0)
+    rng3 = random.Random(99)
+    lam = torch.tensor(0.25, device=dev)
+
+    def st_step(fused):
+        if fused:      # one presence pass over slabelv serves both ClassMix blocks; its host round trip hides behind a5 + a4
+            pres = D.present_classes_async(sl)
+            wts = cf.get_centroid_weight(feat)                                                     # :301
+            kept, feat_pseudo = D.consensus_select(tl, wts, (hh, ww))                              # :302-304
+            _, mix1 = D.classmix(sl, rec, saug, rng=rng3, present=pres, return_mask=False)         # :259-275
+            _, mix2, mixlabel = D.classmix(sl, tdata_aug, sdata, kept, rng=rng3, present=pres, return_mask=False)   # :306-325
+        else:
+            _, mix1 = D.classmix(sl, rec, saug, rng=rng3)                                          # :259-275
+            wts = cf.get_centroid_weight(feat)                                                     # :301
+            kept, feat_pseudo = D.consensus_select(tl, wts, (hh, ww))                              # :302-304
+            _, mix2, mixlabel = D.classmix(sl, tdata_aug, sdata, kept, rng=rng3)                   # :306-325
+        cf.update_from_features(feat, t_pred, _labels_on_feature_grid(kept, (h, w)), start_mean=False)     # :327-334
+        cf.update_from_features(s_feat, s_pred, _labels_on_feature_grid(sl, (h, w)), start_mean=False)     # :336-341
+        stu = stu_cat.detach().requires_grad_(True)
+        cpm = cross_low.detach().requires_grad_(True)
+        if fused:      # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each
+            part, l_src, l_kd = D.seg_distillation_total_upsampled(tea_cat, stu, sl, 1.0, 0.25, 0.5)   # :289,:348-352,:382
+            total = part + D.cross_entropy2d_upsampled(cpm, mixlabel)                              # :344,:355-356
+        else:
+            up = lambda x: F.interpolate(x, size=(hh, ww), mode="bilinear", align_corners=True)
+            l_src = D.cross_entropy2d(up(stu[:b]), sl)                                             # :348-349
+            l_kd = D.distillation_loss(up(tea_cat), up(stu), 0.5)                                  # :289,:351-352
+            l_mix = D.cross_entropy2d(up(cpm), mixlabel)                                           # :344,:355
+            total = (l_src + l_mix) + lam * l_kd                                                   # :356,:382
+        g_stu, g_mix = torch.autograd.grad(total, [stu, cpm])
+        return total, g_stu, g_mix, mix1, mix2
+
+    step_bytes = 48 + 68 + 24 + 3 * (d * 4 + C * 4) * (h * w) / (hh * ww) + 16
+    for name, fused in (("config3_self_training_step_dropin_functions", False), ("config3_self_training_step_fused_call_sites", True)):
+        add(name, b * hh * ww, step_bytes, lambda fused=fused: st_step(fused), sync_free=False,
+            extra={"note": "ClassMix x2 (one 32 B/image host round trip each, as the reference's random.sample needs), prototype "
+                           "weights, consensus selection, 2 centroid EMA updates, CE x2 + KD with backward; eager (host syncs); "
+                           "algorithmic bytes = the three [8,2048,65,129] feature reads + image/label traffic"})
+    del s_feat, rec, saug, tdata_aug, sdata
+
     # config 4 shape of the exchange: mean pass + ONE all-reduce of [19, D+1] (NCCL over NVLink when world > 1)
     acc = P.new_mean_accumulator(C, d, dev)
 

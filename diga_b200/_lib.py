@@ -60,6 +60,7 @@ SIGNATURES = {
     "diga_loss_up_fwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p]),
     "diga_loss_up_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p, _p]),
     "diga_ce_up_fwd_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p, _p]),
+    "diga_seg_kd_up_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
     "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
 }

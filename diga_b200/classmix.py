@@ -20,36 +20,62 @@ IGNORE = 255
 
 
 _pinned = {}
+_PINNED_SLOTS = 4          # outstanding asynchronous presence requests per size
 
 
 def _pinned_i32(n: int) -> torch.Tensor:
-    t = _pinned.get(n)
-    if t is None:
-        t = torch.empty((n,), dtype=torch.int32).pin_memory()
-        _pinned[n] = t
-    return t
+    slots = _pinned.setdefault(n, {"next": 0, "bufs": []})
+    if len(slots["bufs"]) < _PINNED_SLOTS:
+        slots["bufs"].append(torch.empty((n,), dtype=torch.int32).pin_memory())
+        return slots["bufs"][-1]
+    slots["next"] = (slots["next"] + 1) % _PINNED_SLOTS
+    return slots["bufs"][slots["next"]]
+
+
+class PresentClasses:
+    """Handle of an in-flight presence pass: the kernel and the 32 B/image D2H copy are queued on the current stream at
+    construction; ``result()`` waits for THAT copy only (a CUDA event), so work queued behind it keeps the GPU busy."""
+
+    def __init__(self, slabel: torch.Tensor):
+        L.require_cuda(slabel, what="classmix label")
+        lab = L.i64c(slabel)
+        self.b = lab.shape[0]
+        self._present = [] if self.b == 0 else None
+        if self.b == 0:
+            return
+        hw = lab.shape[1] * lab.shape[2]
+        # one device buffer [b*8 bitmap words | 1 flag word] and one pinned host mirror: a single D2H copy
+        self._buf = torch.empty((self.b * 8 + 1,), dtype=torch.int32, device=lab.device)
+        L.check(L.lib.diga_class_presence(lab.data_ptr(), self.b, hw, self._buf.data_ptr(), self._buf.data_ptr() + self.b * 32,
+                                          L.stream()))
+        self._host = _pinned_i32(self.b * 8 + 1)
+        self._host.copy_(self._buf, non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record()
+
+    def result(self):
+        if self._present is None:
+            self._done.synchronize()                                              # the one host sync
+            host = self._host.numpy().view(np.uint32)
+            if host[-1]:
+                raise ValueError("classmix: labels must lie in [0, 255] (trainIds plus the 255 ignore value)")
+            bits = np.unpackbits(host[:-1].copy().view(np.uint8).reshape(self.b, 32), axis=1, bitorder="little")
+            self._present = [np.nonzero(row)[0].tolist() for row in bits]
+            self._buf = None
+        return self._present
+
+
+def present_classes_async(slabel: torch.Tensor) -> PresentClasses:
+    """Start the presence pass for ``slabel`` and return its handle (pass it to ``classmix(..., present=handle)``).  Both
+    ClassMix blocks of a self-training step use the same ``slabelv`` (:265, :310), so one pass issued when the batch
+    arrives serves both, and its host round trip hides behind whatever is queued after it."""
+    return PresentClasses(slabel)
 
 
 def present_classes(slabel: torch.Tensor):
     """Per image, the sorted list of label values present — ``torch.unique(slabel[i]).tolist()`` (:265) — from a
     256-bit device bitmap (32 B per image over PCIe instead of a sort + sync per image)."""
-    L.require_cuda(slabel, what="classmix label")
-    lab = L.i64c(slabel)
-    b = lab.shape[0]
-    hw = lab.shape[1] * lab.shape[2]
-    if b == 0:
-        return []
-    # one device buffer [b*8 bitmap words | 1 flag word] and one pinned host mirror: a single D2H copy + stream sync
-    buf = torch.empty((b * 8 + 1,), dtype=torch.int32, device=lab.device)
-    L.check(L.lib.diga_class_presence(lab.data_ptr(), b, hw, buf.data_ptr(), buf.data_ptr() + b * 32, L.stream()))
-    host_t = _pinned_i32(b * 8 + 1)
-    host_t.copy_(buf, non_blocking=True)
-    torch.cuda.current_stream().synchronize()                                     # the one host sync
-    host = host_t.numpy().view(np.uint32)
-    if host[-1]:
-        raise ValueError("classmix: labels must lie in [0, 255] (trainIds plus the 255 ignore value)")
-    bits = np.unpackbits(host[:-1].copy().view(np.uint8).reshape(b, 32), axis=1, bitorder="little")
-    return [np.nonzero(row)[0].tolist() for row in bits]
+    return PresentClasses(slabel).result()
 
 
 def select_classes(present, rng=_random):
@@ -63,7 +89,7 @@ def select_classes(present, rng=_random):
     return chosen
 
 
-def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True, assume_labelled=False):
+def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True, assume_labelled=False, present=None):
     """ClassMix mask build + blend.
 
     ``slabel [B,H,W]`` int64 source labels; ``a``, ``b`` ``[B,CH,H,W]`` fp32; optional ``tlabel [B,H,W]`` int64.
@@ -72,15 +98,19 @@ def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=T
     Returns ``(mask, mix)`` or ``(mask, mix, mixlabel)``; ``mix`` is ``None`` when every label is 255, the case
     in which the reference never creates the tensor (:271 / :321).
 
+    ``present`` (a ``present_classes_async`` handle or the list ``present_classes`` returns) re-uses a presence pass over
+    the same ``slabel``; the class choice is still drawn here, in call order, from ``rng``.
     ``classes`` (per-image lists) skips the presence pass and the host draw; the all-255 test then needs its own
     device reduction + sync unless ``assume_labelled=True`` promises that some label differs from 255.
     """
     L.require_cuda(slabel, a, b, tlabel, what="classmix input")
     lab = L.i64c(slabel)
     bsz = lab.shape[0]
-    present = None
+    if isinstance(present, PresentClasses):
+        present = present.result()
     if classes is None:
-        present = present_classes(lab)
+        if present is None:
+            present = present_classes(lab)
         classes = select_classes(present, rng)
     lut_host = np.zeros((bsz, 256), dtype=np.uint8)
     for i, sel in enumerate(classes):

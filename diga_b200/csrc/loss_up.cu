@@ -69,7 +69,7 @@ static LossUpPlan make_plan(int64_t n, int64_t C, int64_t h, int64_t w, int64_t 
     if (hi - lo + 1 > p.K) p.K = hi - lo + 1;
   }
   p.ctas = n * p.SY * p.SX;
-  p.off_partial = 16;
+  p.off_partial = 32;                                   // [0,16): ticket, [16,32): target counter + its ticket
   p.off_scratch = (p.off_partial + (size_t)p.ctas * 3 * sizeof(double) + 15) & ~(size_t)15;
   const int64_t cp = C == 19 ? 20 : (C == 16 ? 16 : 32);   // class pitch of a patch column (DIGA_DISPATCH_C: 19, 16, padded 32)
   p.bytes = p.off_scratch + (size_t)p.ctas * p.R * cp * p.K * sizeof(float);
@@ -87,7 +87,8 @@ struct LossUpArgs {
   const float* up_kd;      // device scalars (backward)
   const float* up_ce;
   const float* denom;
-  float up_kd_host;        // used when up_kd == null (single-pass KD)
+  float up_kd_host;        // used when up_kd == null (single-pass variants)
+  float up_ce_host;        // used when up_ce == null
   int ry, R, K;
   float* scratch;
   double* partial;
@@ -208,7 +209,7 @@ loss_up_kernel(const LossUpArgs a) {
   float ckd = 0.f, cce = 0.f;
   if constexpr (GRAD) {
     if constexpr (KD) ckd = (a.up_kd != nullptr ? __ldg(a.up_kd) : a.up_kd_host) * a.inv_count_kd * wkd;
-    if (ce_img) cce = a.up_ce != nullptr ? __ldg(a.up_ce) / (a.size_average ? __ldg(a.denom) : 1.0f) : 1.0f;
+    if (ce_img) cce = (a.up_ce != nullptr ? __ldg(a.up_ce) : a.up_ce_host) / ((a.size_average && a.denom != nullptr) ? __ldg(a.denom) : 1.0f);
   }
 
   // ---- CTA geometry: source rows from ylo, source columns xlo..xhi --------------------------------------------------
@@ -536,6 +537,40 @@ loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlo
   }
 }
 
+// denom = #(target >= 0) (util/loss.py:56,:60) ahead of a single-pass loss+gradient launch, whose CE gradient needs it.
+// Integer atomics: exact and order-independent.  `counter` = {count, ticket}, left zeroed.
+__global__ void __launch_bounds__(256)
+count_targets_kernel(const int64_t* __restrict__ target, int64_t total, unsigned long long* __restrict__ counter,
+                     float* __restrict__ denom_out) {
+  unsigned int cnt = 0;
+  const int64_t pairs = total / 2;
+  const bool vec = (reinterpret_cast<uintptr_t>(target) & 15) == 0;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * 256) {
+      const longlong2 t = ld_stream_i64x2(target + 2 * i);
+      cnt += (t.x >= 0) + (t.y >= 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (total & 1)) cnt += target[total - 1] >= 0;
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) cnt += target[i] >= 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  __shared__ unsigned int wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int b = 0;
+    for (int i = 0; i < 8; ++i) b += wsum[i];
+    atomicAdd(&counter[0], (unsigned long long)b);
+    __threadfence();
+    if (atomicAdd(&counter[1], 1ull) == gridDim.x - 1) {
+      __threadfence();
+      denom_out[0] = (float)atomicExch(&counter[0], 0ull);
+      counter[1] = 0ull;
+    }
+  }
+}
+
 static int check_common(const char* who, const float* stu, int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W,
                         const void* workspace) {
   DIGA_REQUIRE(stu && workspace, DIGA_ERR_INVALID, "%s: null input / workspace", who);
@@ -681,8 +716,41 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
   const LossUpPlan p = make_plan(n, C, h, w, H, W);
   LossUpArgs a = fill_args(p, workspace, nullptr, logits_low, target, weight, n, n, C, h, w, H, W, 0.f, size_average);
   a.loss_ce = loss_out;
-  a.denom_out = denom_out;          // up_ce == null: the gradient of the SUMMED loss (the caller scales by upstream / denom)
+  a.denom_out = denom_out;
+  a.up_ce_host = 1.0f;              // unit upstream, no denominator: the gradient of the SUMMED loss (the caller scales it)
   return launch_loss_up<false, true, true, true>(a, p, C, dlogits_sum, (cudaStream_t)stream);
+}
+
+int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
+                           int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
+                           int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
+                           float* denom_out, float* dstudent_low, void* workspace, diga_stream_t stream) {
+  using namespace diga;
+  if (int rc = check_common("seg_kd_up_fwd_bwd", student_low, n2, C, h, w, H, W, workspace)) return rc;
+  DIGA_REQUIRE(teacher_low && target && loss_kd && loss_ce && denom_out && dstudent_low && (n2 % 2) == 0 && n_ce >= 1 && n_ce <= n2,
+               DIGA_ERR_INVALID, "seg_kd_up_fwd_bwd: all pointers, an even batch and 1 <= n_ce <= n2 are required");
+  DIGA_REQUIRE(aligned(teacher_low, 4) && aligned(target, 8) && aligned(weight, 4) && aligned(dstudent_low, 4), DIGA_ERR_MISALIGNED,
+               "seg_kd_up_fwd_bwd: misaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LossUpPlan p = make_plan(n2, C, h, w, H, W);
+  LossUpArgs a = fill_args(p, workspace, teacher_low, student_low, target, weight, n2, n_ce, C, h, w, H, W, scale, size_average);
+  if (size_average) {                                     // the CE gradient is divided by #(target >= 0): count it first
+    const int64_t total = n_ce * H * W;
+    int64_t grid = (total / 2 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    count_targets_kernel<<<(unsigned)grid, 256, 0, st>>>(target, total, reinterpret_cast<unsigned long long*>(
+                                                             reinterpret_cast<char*>(workspace) + 16), denom_out);
+    DIGA_CHECK_LAUNCH("count_targets_kernel");
+    a.denom = denom_out;
+  }
+  a.up_kd_host = lambda_kd_host;
+  a.up_ce_host = lambda_ce_host;
+  a.loss_kd = loss_kd;
+  a.loss_ce = loss_ce;
+  a.denom_out = denom_out;                                // rewritten with the same value by the loss reduction
+  return launch_loss_up<true, true, true, true>(a, p, C, dstudent_low, st);
 }
 
 }  // extern "C"

@@ -243,3 +243,53 @@ def distillation_loss_upsampled_and_grad(teacher_low, student_low, size, scale=0
     L.check(L.lib.diga_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), n, c, h, w, hh, ww, float(scale), float(grad_scale),
                                      loss.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
     return loss, ds
+
+
+class _SegDistillationTotal(torch.autograd.Function):
+    """``lambda_seg * CE + lambda_distil * KD`` from the stride-8 logits with the weights known up front: the forward
+    launches the loss+gradient kernel once (the weighted gradient comes out of the same pass), the backward scales it."""
+
+    @staticmethod
+    def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average, lambda_seg, lambda_distil):
+        s, t, tg = L.f32c(student_low.detach()), L.f32c(teacher_low.detach()), L.i64c(target)
+        wt = None if weight is None else L.f32c(weight.detach()).to(s.device)
+        n, c, h, w = s.shape
+        hh, ww = size
+        dev = s.device
+        loss_kd, loss_ce, denom = (torch.empty((), dtype=torch.float32, device=dev) for _ in range(3))
+        ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
+        if ctx.needs_input_grad[1]:
+            ds = torch.empty_like(s)
+            L.check(L.lib.diga_seg_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w,
+                                                 hh, ww, float(scale), int(bool(size_average)), float(lambda_seg),
+                                                 float(lambda_distil), loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(),
+                                                 ds.data_ptr(), ws.data_ptr(), L.stream()))
+            ctx.save_for_backward(ds)
+        else:
+            L.check(L.lib.diga_loss_up_fwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w, hh, ww,
+                                           float(scale), int(bool(size_average)), loss_kd.data_ptr(), loss_ce.data_ptr(),
+                                           denom.data_ptr(), ws.data_ptr(), L.stream()))
+        total = lambda_seg * loss_ce + lambda_distil * loss_kd
+        ctx.mark_non_differentiable(loss_ce, loss_kd)
+        return total, loss_ce, loss_kd
+
+    @staticmethod
+    def backward(ctx, g_total, _g_ce, _g_kd):
+        (ds,) = ctx.saved_tensors
+        return None, ds * g_total.to(dtype=torch.float32, device=ds.device), None, None, None, None, None, None, None
+
+
+def seg_distillation_total_upsampled(teacher_low, student_low, target, lambda_seg=1.0, lambda_distil=0.25, scale=0.5,
+                                     weight=None, size_average=True):
+    """``total = lambda_seg * seg_loss(upsample(student_low[:B]), target) + lambda_distil * distillation_loss(upsample(
+    teacher_low), upsample(student_low), scale)`` — self_training.py:348-352 and the source-image part of :382 — with the
+    loss weights known when the losses are computed, so loss and gradient cost ONE pass over the stride-8 logits.
+    Returns ``(total, loss_seg, loss_distil)``; only ``total`` carries a gradient (the two parts are for logging)."""
+    L.require_cuda(teacher_low, student_low, target, weight, what="seg_distillation_total_upsampled input")
+    if teacher_low.shape != student_low.shape or student_low.dim() != 4 or student_low.shape[0] % 2:
+        raise ValueError("seg_distillation_total_upsampled: expected two [2B,C,h,w] logit tensors")
+    if target.dim() != 3 or not (1 <= target.shape[0] <= student_low.shape[0]):
+        raise ValueError("seg_distillation_total_upsampled: target must be [n_ce,H,W] with 1 <= n_ce <= 2B")
+    size = _check_low(student_low, target.shape[1:], "seg_distillation_total_upsampled")
+    return _SegDistillationTotal.apply(teacher_low, student_low, target, weight, size, scale, size_average, float(lambda_seg),
+                                       float(lambda_distil))

@@ -200,7 +200,7 @@ int diga_cross_entropy2d_bwd(const float* logits, const int64_t* target, const f
  *        + upstream_ce[0]*dloss_ce/dstudent_low, i.e. the transposed interpolation applied to the per-pixel gradient;
  *        no atomics, bitwise deterministic.  upstream_* / denom are DEVICE scalars (denom = denom_out of the forward).
  *   kd_up_fwd_bwd: KD loss and upstream_host * gradient in a single pass.
- *   workspace: diga_loss_up_workspace_bytes(n, C, h, w, H, W) bytes, 16-byte aligned; its first 16 bytes zero-filled
+ *   workspace: diga_loss_up_workspace_bytes(n, C, h, w, H, W) bytes, 16-byte aligned; its first 32 bytes zero-filled
  *        once by the caller (the kernels leave them zeroed).  Requires H >= h and W >= w.
  * ------------------------------------------------------------------------------------------ */
 size_t diga_loss_up_workspace_bytes(int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W);
@@ -217,6 +217,12 @@ int diga_loss_up_bwd(const float* teacher_low, const float* student_low, const i
 int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
                        int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
                        float* dlogits_sum, void* workspace, diga_stream_t stream);
+/* Both losses of self_training.py:348-352 and the gradient of lambda_ce * loss_ce + lambda_kd * loss_kd (:382) in ONE pass
+ * over the stride-8 logits, for call sites that know the two loss weights when the losses are computed. */
+int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
+                           int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
+                           int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
+                           float* denom_out, float* dstudent_low, void* workspace, diga_stream_t stream);
 int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
                        int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
                        void* workspace, diga_stream_t stream);

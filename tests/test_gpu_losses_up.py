@@ -225,3 +225,26 @@ def test_no_grad_forward_takes_the_loss_only_pass(D):
     b = D.distillation_loss_upsampled(tea, s, (64, 96))
     assert L.launch_count() - before == 2                      # loss+gradient kernel and the patch gather
     assert torch.equal(a, b.detach())
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", [GEOMS[0], GEOMS[2], GEOMS[3], GEOMS[7]])
+def test_weighted_total_single_pass(D, n2, c, lo, hi):
+    """seg_distillation_total_upsampled (loss weights known up front, one pass) == the weighted sum of the two-output form,
+    with weights / sum reduction / dropped pixels, and the reference chain in fp64."""
+    tea, stu, g = inputs(n2, c, lo, 18)
+    tgt = labels(n2 // 2, hi, c, g)
+    wt = 0.5 + torch.rand((c,), generator=g, device=DEV)
+    for weight, avg, lam_s, lam_d in ((None, True, 1.0, 0.25), (wt, True, 0.7, 1.3), (wt, False, 1e-3, 0.5)):
+        s1 = stu.clone().requires_grad_(True)
+        total, l_ce, l_kd = D.seg_distillation_total_upsampled(tea, s1, tgt, lam_s, lam_d, 0.5, weight, avg)
+        assert not l_ce.requires_grad and not l_kd.requires_grad
+        (total * 0.5).backward()
+        s2 = stu.double().cpu().requires_grad_(True)
+        r_ce, r_kd = O.seg_distillation_losses_upsampled(tea.double().cpu(), s2, tgt.cpu(), 0.5,
+                                                         None if weight is None else weight.double().cpu(), avg)
+        ((lam_s * r_ce + lam_d * r_kd) * 0.5).backward()
+        rel(l_ce, r_ce, "ce"), rel(l_kd, r_kd, "kd"), rel(total, lam_s * r_ce + lam_d * r_kd, "total")
+        normwise(s1.grad, s2.grad, "weighted single-pass grad")
+        with torch.no_grad():
+            t2, _, _ = D.seg_distillation_total_upsampled(tea, stu, tgt, lam_s, lam_d, 0.5, weight, avg)
+        assert torch.equal(t2, total.detach())

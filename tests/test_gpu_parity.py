@@ -264,6 +264,27 @@ def test_classmix_vs_oracle(D, b, h, w, block):
     assert present_classes(sl.to(dev())) == [torch.unique(sl[i]).tolist() for i in range(b)]
 
 
+def test_classmix_shared_async_presence(D):
+    """One presence pass (present_classes_async) shared by both ClassMix blocks of a step == two independent calls,
+    the seeded `random` stream consumed in the same order (self_training.py:265-266 then :310-311)."""
+    g = torch.Generator(device=dev()).manual_seed(5)
+    b, h, w = 3, 48, 80
+    from diga_b200 import synthetic as S
+    sl = S.block_labels(b, h, w, g, 8)
+    tl = S.perturb_labels(sl, g, 8)
+    xa, xb, xc, xd = (S.images((b, 3, h, w), g) for _ in range(4))
+    r1 = random.Random(31)
+    m1, mix1 = D.classmix(sl, xa, xb, rng=r1)
+    m2, mix2, lab2 = D.classmix(sl, xc, xd, tl, rng=r1)
+    r2 = random.Random(31)
+    pres = D.present_classes_async(sl)
+    _ = D.pseudo_label(S.logits((1, 19, 16, 16), g))                       # unrelated work queued behind the request
+    n1, nix1 = D.classmix(sl, xa, xb, rng=r2, present=pres)
+    n2, nix2, nab2 = D.classmix(sl, xc, xd, tl, rng=r2, present=pres)
+    assert torch.equal(m1, n1) and torch.equal(mix1, nix1)
+    assert torch.equal(m2, n2) and torch.equal(mix2, nix2) and torch.equal(lab2, nab2)
+
+
 def test_classmix_all_ignore_and_bad_labels(D):
     sl = torch.full((2, 8, 8), 255, dtype=torch.int64, device=dev())
     a = torch.randn(2, 3, 8, 8, device=dev())
