@@ -132,6 +132,87 @@ def test_self_training_step_hot_path():
         assert normwise(got["g_stu"], ref["g_stu"]) and normwise(got["g_cp"], ref["g_cp"])
 
 
+def test_self_training_step_fused_call_sites():
+    """The same step through the patched call sites of INTEGRATION.md — one shared asynchronous ClassMix presence pass,
+    update_from_features, the losses straight from the stride-8 logits with the loss weights known up front — against
+    the reference-shaped op chain (nn.Upsample + losses, per-vector centroid updates) run with the oracle on the GPU."""
+    import diga_b200 as D
+    from diga_b200 import synthetic as S
+    from diga_b200.calc_centroids import _labels_on_feature_grid
+    g = S.gen(78)
+    b, c, d, hh, ww, h, w = 2, 19, 64, 64, 96, 8, 12
+    slabel = S.block_labels(b, hh, ww, g, 8)
+    pseudo = S.block_labels(b, hh, ww, g, 8)
+    rec, saug = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    tdata_aug, sdata = S.images((b, 3, hh, ww), g), S.images((b, 3, hh, ww), g)
+    t_feat, s_feat = S.features((b, d, h, w), g), S.features((b, d, h, w), g)
+    t_pred, s_pred = S.logits((b, c, h, w), g), S.logits((b, c, h, w), g)
+    t_pred[:, :5] += 3
+    s_pred[:, :5] += 3
+    cen = S.centroids(c, d, g)
+    tea_low, stu_low = S.logits((2 * b, c, h, w), g), S.logits((2 * b, c, h, w), g)
+    cross_low = S.logits((b, c, h, w), g)
+    lam_seg, lam_kd = 1.0, 0.25
+    to = lambda t: t.to(DEV)
+
+    def reference_shaped():
+        random.seed(321)
+        cf = O.ClassFeaturesOracle(c, d)
+        cf.objective_vectors = cen.clone()
+        cf.objective_vectors_num = torch.full((c,), 150.0)
+        out = {}
+        _, out["mix1"] = O.classmix(to(slabel), to(rec), to(saug), rng=random)
+        weights = cf.get_centroid_weight(to(t_feat))
+        kept, fp = O.consensus_select(to(pseudo), weights, (hh, ww))
+        _, out["mix2"], out["mixlabel"] = O.classmix(to(slabel), to(tdata_aug), to(sdata), kept, rng=random)
+        for lab, feat, pred in ((kept, t_feat, t_pred), (to(slabel), s_feat, s_pred)):
+            vec, ids = cf.calculate_mean_vector(to(feat), to(pred), O.nearest_labels_to_feature_grid(lab, (h, w)))
+            for v, i in zip(vec, ids):
+                cf.update_objective_SingleVector(i, v.detach(), start_mean=False)
+        stu, cpm = to(stu_low).clone().requires_grad_(True), to(cross_low).clone().requires_grad_(True)
+        l_src, l_kd = O.seg_distillation_losses_upsampled(to(tea_low), stu, to(slabel), 0.5)
+        l_seg = l_src + O.cross_entropy2d_upsampled(cpm, out["mixlabel"])
+        total = lam_seg * l_seg + lam_kd * l_kd
+        total.backward()
+        out.update(weights=weights, kept=kept, feat_pseudo=fp, centroids=cf.objective_vectors, loss=total.detach(),
+                   g_stu=stu.grad, g_cp=cpm.grad)
+        return out
+
+    def patched():
+        random.seed(321)
+        cf = D.Class_Features(c, d)
+        cf.objective_vectors = cen.clone()
+        cf.objective_vectors_num = torch.full((c,), 150.0)
+        out = {}
+        pres = D.present_classes_async(to(slabel))
+        weights = cf.get_centroid_weight(to(t_feat))
+        kept, fp = D.consensus_select(to(pseudo), weights, (hh, ww))
+        _, out["mix1"] = D.classmix(to(slabel), to(rec), to(saug), rng=random, present=pres)
+        _, out["mix2"], out["mixlabel"] = D.classmix(to(slabel), to(tdata_aug), to(sdata), kept, rng=random, present=pres)
+        cf.update_from_features(to(t_feat), to(t_pred), _labels_on_feature_grid(kept, (h, w)), start_mean=False)
+        cf.update_from_features(to(s_feat), to(s_pred), _labels_on_feature_grid(to(slabel), (h, w)), start_mean=False)
+        stu, cpm = to(stu_low).clone().requires_grad_(True), to(cross_low).clone().requires_grad_(True)
+        part, _, _ = D.seg_distillation_total_upsampled(to(tea_low), stu, to(slabel), lam_seg, lam_kd, 0.5)
+        total = part + lam_seg * D.cross_entropy2d_upsampled(cpm, out["mixlabel"])
+        total.backward()
+        out.update(weights=weights, kept=kept, feat_pseudo=fp, centroids=cf.objective_vectors, loss=total.detach(),
+                   g_stu=stu.grad, g_cp=cpm.grad)
+        return out
+
+    ref, got = reference_shaped(), patched()
+    assert torch.equal(got["mix1"], ref["mix1"]) and torch.equal(got["mix2"], ref["mix2"])
+    assert normwise(got["weights"], ref["weights"], 1e-4)
+    same = got["feat_pseudo"] == ref["feat_pseudo"]
+    assert same.float().mean().item() > 0.9995
+    assert torch.equal(got["kept"][same], ref["kept"][same])
+    if bool(same.all()):
+        assert torch.equal(got["mixlabel"], ref["mixlabel"])
+        for k in range(c):
+            assert normwise(got["centroids"][k], ref["centroids"][k]), f"centroid {k}"
+        assert abs(got["loss"].item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+        assert normwise(got["g_stu"], ref["g_stu"]) and normwise(got["g_cp"], ref["g_cp"])
+
+
 def test_generate_pseudo_labels_writes_reference_format(tmp_path):
     """pseudolabel_generator.py:69-105 end to end on a stand-in model: PNG files named after the image, 'P' mode with the
     Cityscapes palette, indices equal to the reference math (two-scale max -> argmax) evaluated with torch on the GPU."""
