@@ -275,6 +275,15 @@ def bench_stages(D, S, dev, peak, world, quick):
         lambda: D.pseudo_label_two_scale(l1, l2, (hh, ww), want_conf=False),
         extra={"note": "what pseudolabel_generator.py keeps: the uint8 label map (the confidence is discarded there)"})
 
+    # next row f5: evaluation confusion matrix (util/metrics.py:32-41) on the labels the fused kernel just produced (uint8)
+    # against an int64 ground truth: 9 B/px read, nothing written but 19 x 19 counters
+    from diga_b200.util.metrics import runningScore
+    gt_eval = S.block_labels(n, hh, ww, g)
+    pred_eval, _ = D.pseudo_label_two_scale(l1, l2, (hh, ww), want_conf=False)
+    rs = runningScore(C)
+    add("confusion_matrix_eval", n * hh * ww, 9, lambda: rs.update(gt_eval, pred_eval))
+    del gt_eval, pred_eval
+
     # config 3 pieces: B=8 @512x1024, features [8,2048,65,129]
     b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
     sl = S.block_labels(b, hh, ww, g)

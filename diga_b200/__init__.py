@@ -6,6 +6,7 @@ Host side mirrors the reference's interface for this path:
 * ``diga_b200.util.utils.process_label``             <- ``util/utils.py:158``
 * ``diga_b200.util.loss.cross_entropy2d``            <- ``util/loss.py:48``   (next row f2)
 * ``diga_b200.util.utils.update_teacher_params``     <- ``util/utils.py:103`` (next row f4)
+* ``diga_b200.util.metrics.runningScore``              <- ``util/metrics.py:26``  (next row f5)
 * ``diga_b200.calc_centroids.Class_Features`` / ``calc_centroids`` <- ``calc_centroids.py:84`` / ``:17``
 * ``diga_b200.classmix.classmix``                    <- inline block ``train_DiGA_gta2city_self_training.py:259-275, 306-325``
 * ``diga_b200.selection.consensus_select``           <- inline block ``:298-304``

@@ -236,6 +236,16 @@ int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64
 int diga_ema_update(float* const* teacher_host, const float* const* student_host, const int64_t* numel_host,
                     int64_t count, double alpha, diga_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f5 (next row)  evaluation confusion matrix — util/metrics.py:32-41 (runningScore._fast_hist / update)
+ *   hist[n_class * t + p] += 1 for every pixel with 0 <= t < n_class (t = label_true, p = label_pred); hist is an int64
+ *   [n_class, n_class] DEVICE matrix accumulated in place (exact, order-independent).  Labels are uint8 or int64 maps
+ *   (`*_is_u8`), `total` pixels each.  A prediction outside [0, n_class) on a counted pixel (where the reference's
+ *   bincount(...).reshape would raise) is skipped and reported as flags[0] |= 1 (flags is NOT cleared by the call).
+ * ------------------------------------------------------------------------------------------ */
+int diga_confusion_matrix(const void* label_true, int true_is_u8, const void* label_pred, int pred_is_u8, int64_t total,
+                          int64_t n_class, int64_t* hist, uint32_t* flags, diga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,6 +360,41 @@ def update_teacher_params(teacher, student, iteration, stage0=True, mean=False, 
 
 
 # --------------------------------------------------------------------------------------
+# f5  evaluation confusion matrix   (G/util/metrics.py:26-76)
+# --------------------------------------------------------------------------------------
+class RunningScoreOracle:
+    """``runningScore`` restated (G/util/metrics.py:26-76) without the per-class ``print`` of :62-63."""
+
+    def __init__(self, n_classes):
+        self.n_classes = n_classes
+        self.confusion_matrix = np.zeros((n_classes, n_classes))                       # :30
+
+    def _fast_hist(self, label_true, label_pred, n_class):
+        mask = (label_true >= 0) & (label_true < n_class)                                # :33
+        return np.bincount(n_class * label_true[mask].astype(int) + label_pred[mask],   # :34-36
+                           minlength=n_class ** 2).reshape(n_class, n_class)
+
+    def update(self, label_trues, label_preds):
+        for lt, lp in zip(label_trues, label_preds):                                     # :40-41
+            self.confusion_matrix += self._fast_hist(lt.flatten(), lp.flatten(), self.n_classes)
+
+    def get_scores(self):
+        hist = self.confusion_matrix
+        with np.errstate(divide="ignore", invalid="ignore"):
+            acc = np.diag(hist).sum() / hist.sum()                                       # :51
+            acc_cls = np.nanmean(np.diag(hist) / hist.sum(axis=1))                       # :52-53
+            iu = np.diag(hist) / (hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist))   # :54
+            mean_iu = np.nanmean(iu)                                                     # :57
+            freq = hist.sum(axis=1) / hist.sum()                                         # :58
+            fwavacc = (freq[freq > 0] * iu[freq > 0]).sum()                              # :59
+        cls_iu = dict(zip(range(self.n_classes), iu))                                    # :60
+        return {'Overall Acc: \t': acc, 'Mean Acc : \t': acc_cls, 'FreqW Acc : \t': fwavacc, 'Mean IoU : \t': mean_iu}, cls_iu
+
+    def reset(self):
+        self.confusion_matrix = np.zeros((self.n_classes, self.n_classes))               # :76
+
+
+# --------------------------------------------------------------------------------------
 # drivers used as CPU baseline / multi-rank checks
 # --------------------------------------------------------------------------------------
 def centroid_pass(feats: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], numbers=19, feat_dim=256,

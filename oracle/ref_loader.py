@@ -33,7 +33,7 @@ def available(tree: str = "G") -> bool:
 
 def load(tree: str = "G") -> types.SimpleNamespace:
     """Returns a namespace with ``distillation_loss``, ``cross_entropy2d``, ``process_label``, ``update_teacher_params``,
-    ``Class_Features``."""
+    ``Class_Features``, ``runningScore``."""
     if not available(tree):
         raise FileNotFoundError(f"reference tree {tree} not found under {REF_ROOT}")
     loaded = getattr(load, "_tree", None)
@@ -54,7 +54,8 @@ def load(tree: str = "G") -> types.SimpleNamespace:
         from util.loss import distillation_loss, cross_entropy2d          # noqa: E402
         from util.utils import process_label, update_teacher_params       # noqa: E402
         from calc_centroids import Class_Features        # noqa: E402
+        from util.metrics import runningScore            # noqa: E402
     load._tree = tree
     return types.SimpleNamespace(distillation_loss=distillation_loss, process_label=process_label,
                                  Class_Features=Class_Features, cross_entropy2d=cross_entropy2d,
-                                 update_teacher_params=update_teacher_params, tree=tree)
+                                 update_teacher_params=update_teacher_params, runningScore=runningScore, tree=tree)

@@ -273,6 +273,22 @@ def main():
          loss_semseg_src=loss_src, loss_semseg=ns["loss_semseg"], loss_distil=ns["loss_s_distil"],
          total_loss=ns["total_loss"], grad_student_low=stu_low.grad, grad_mix_low=mix_low.grad)
 
+    # ---- f5 evaluation confusion matrix: runningScore.update / get_scores (G/util/metrics.py:26-76) ----------------
+    import contextlib
+    import io as _io
+    gen_m = torch.Generator().manual_seed(777)
+    gt = _blocky_labels(gen_m, 3, 40, 56, 8).numpy()                                   # int64 with 255 = ignore
+    pred = _blocky_labels(gen_m, 3, 40, 56, 4, p_ignore=0.0).numpy()
+    pred[0] = np.where(gt[0] < 19, gt[0], pred[0])                                     # one well-predicted image
+    rs = ref.runningScore(19)
+    rs.update(gt[:2], pred[:2])
+    rs.update(gt[2:], pred[2:])
+    with contextlib.redirect_stdout(_io.StringIO()):                                   # :62-63 prints per-class IoU
+        score, cls_iu = rs.get_scores()
+    save("running_score", gt=gt, pred=pred, confusion_matrix=rs.confusion_matrix,
+         overall_acc=score['Overall Acc: \t'], mean_acc=score['Mean Acc : \t'], fwavacc=score['FreqW Acc : \t'],
+         mean_iu=score['Mean IoU : \t'], cls_iu=np.array([cls_iu[k] for k in range(19)]))
+
 
 if __name__ == "__main__":
     main()

@@ -236,3 +236,27 @@ def test_losses_upsampled_match_reference_bitwise(golden):
     assert np.array_equal(mix.grad.numpy(), g["grad_mix_low"])
     # the stand-alone forms are the same op chains
     assert np.array_equal(O.distillation_loss_upsampled(tea, stu.detach(), size, float(g["kd_scale"])).numpy(), g["loss_distil"])
+
+
+def test_running_score_matches_reference(golden):
+    """runningScore (G/util/metrics.py:26-76): confusion matrix and every score bit for bit; live reference when present."""
+    g = golden("running_score")
+    rs = O.RunningScoreOracle(19)
+    rs.update(g["gt"][:2], g["pred"][:2])
+    rs.update(g["gt"][2:], g["pred"][2:])
+    score, cls_iu = rs.get_scores()
+    assert np.array_equal(rs.confusion_matrix, g["confusion_matrix"])
+    assert score['Overall Acc: \t'] == g["overall_acc"] and score['Mean Acc : \t'] == g["mean_acc"]
+    assert score['FreqW Acc : \t'] == g["fwavacc"] and score['Mean IoU : \t'] == g["mean_iu"]
+    assert np.array_equal(np.array([cls_iu[k] for k in range(19)]), g["cls_iu"], equal_nan=True)
+    assert (g["gt"] == 255).any()
+    rs.reset()
+    assert rs.confusion_matrix.sum() == 0
+    if ref_loader.available("G"):
+        import contextlib
+        import io
+        live = ref_loader.load("G").runningScore(19)
+        live.update(g["gt"], g["pred"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            lscore, _ = live.get_scores()
+        assert np.array_equal(live.confusion_matrix, g["confusion_matrix"]) and lscore['Mean IoU : \t'] == g["mean_iu"]
