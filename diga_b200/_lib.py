@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiga_b200.so")
+LIB_PATH = os.environ.get("DIGA_B200_LIB") or os.path.join(_HERE, "libdiga_b200.so")   # override: A/B builds of the same ABI
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(

@@ -22,7 +22,7 @@ LIB = os.path.join(PKG, "libdiga_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("DIGA_NVCC_EXTRA", "").split()
 
 
 def _sources():

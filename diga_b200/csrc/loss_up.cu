@@ -179,8 +179,14 @@ struct LerpColumn {
   __device__ __forceinline__ float value(float l1, int c) const { return fmaf(l1, dif[c], top[c]); }
 };
 
+#ifndef LU_MINB_LOSS
+#define LU_MINB_LOSS 3      // resident CTAs per SM the loss-only kernels are compiled for (168 registers, no spills; 4 spills and is slower)
+#endif
+#ifndef LU_MINB_GRAD
+#define LU_MINB_GRAD 2      // ... and the gradient kernels (up to 255 registers: Gt/Gb and the two exp arrays stay in registers)
+#endif
 template <int C, bool PAD, bool KD, bool CE, bool LOSS, bool GRAD>
-__global__ void __launch_bounds__(kLuBlock, GRAD ? 2 : 4)
+__global__ void __launch_bounds__(kLuBlock, GRAD ? LU_MINB_GRAD : LU_MINB_LOSS)
 loss_up_kernel(const LossUpArgs a) {
   extern __shared__ __align__(16) int2 ytab[];             // per-row vertical taps of the strip
   const int n = blockIdx.z, ky = blockIdx.y, kx = blockIdx.x, tid = threadIdx.x;
