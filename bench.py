@@ -459,6 +459,74 @@ def bench_stages(D, S, dev, peak, world, quick):
 
     add("centroid_mean_pass_allreduce_d2048", b * h * w, d * 4 + C * 4 + 1, mean_pass, unit="feature-px", sync_free=(world == 1),
         extra=lambda ms: {"images_per_s": b / (ms * 1e-3) * world, "allreduce_bytes": C * (d + 1) * 4})
+    # ---- whole-set runs of BASELINE configs 4 and 5: this rank's share images[rank::world] of a synthetic 2975-image target
+    # set, cycling through a pool of distinct pre-generated inputs (>> L2), timed once with CUDA events,
+    # max over ranks ------------------------------------------------------------------------------------------------------
+    del feat
+    torch.cuda.empty_cache()
+    n_set = 2975 if not quick else 600
+    mine = len(P.shard_indices(n_set, dist_env()[0], world))
+
+    def time_once(fn):
+        fn(min(mine, 16))                                                  # warm-up on a few images
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(mine)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        return max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    # config 4: calc_centroids 'mean' pass, 8 images per call, ONE all-reduce of [19, D+1] at the end
+    pool4 = [(S.features((b, d, h, w), g), S.logits((b, C, h, w), g)) for _ in range(4)]       # 4 x 550 MB of features
+    acc4 = P.new_mean_accumulator(C, d, dev)
+
+    def run_config4(n_img):
+        acc4.zero_()
+        done, k = 0, 0
+        while done < n_img:
+            f, o = pool4[k % len(pool4)]
+            take = min(b, n_img - done)
+            cf.accumulate_mean_pass(acc4, f[:take], o[:take])
+            done += take
+            k += 1
+        return P.finish_mean_pass(acc4)
+
+    ms4 = time_once(run_config4)
+    out["config4_calc_centroids_whole_set"] = {
+        "images": n_set, "images_per_rank": mine, "ms": ms4, "images_per_s": n_set / (ms4 * 1e-3),
+        "px_per_s": n_set * h * w / (ms4 * 1e-3), "unit": "feature-px/s (all ranks)",
+        "image_px_per_s": n_set * hh * ww / (ms4 * 1e-3), "algo_bytes_per_px": d * 4 + C * 4 + 1,
+        "gbs_per_gpu": mine * h * w * (d * 4 + C * 4 + 1) / (ms4 * 1e-3) / 1e9,
+        "frac_hbm": mine * h * w * (d * 4 + C * 4 + 1) / (ms4 * 1e-3) / 1e9 / peak, "allreduce_bytes": C * (d + 1) * 4,
+        "note": "calc_centroids.py:67-78 over the rank's share, batches of 8 x [2048,65,129], one NCCL all-reduce at the end; "
+                "eager launches (the loop is the public API), events around the whole share"}
+    del pool4
+
+    # config 5: full-resolution pseudo-labels with prototype rectification, one 1024x2048 image per call
+    pool5 = [(S.features((1, d, 129, 257), g), S.logits((1, C, 129, 257), g), S.logits((1, C, 65, 129), g)) for _ in range(4)]
+
+    def run_config5(n_img):
+        kept = None
+        for k in range(n_img):
+            f, la, lb = pool5[k % len(pool5)]
+            lab, _ = D.pseudo_label_two_scale(la, lb, (1024, 2048), want_conf=False)
+            kept = D.consensus_select(lab.long(), cf.get_centroid_weight(f), want_feat_pseudo=False)
+        return kept
+
+    ms5 = time_once(run_config5)
+    px5 = 1024 * 2048
+    out["config5_pseudo_labels_whole_set"] = {
+        "images": n_set, "images_per_rank": mine, "ms": ms5, "images_per_s": n_set / (ms5 * 1e-3),
+        "px_per_s": n_set * px5 / (ms5 * 1e-3), "unit": "px/s (all ranks)",
+        "algo_bytes_per_px": (d * 4 + C * 4) * 129 * 257 / px5 + 1 + 16,
+        "gbs_per_gpu": mine * ((d * 4 + C * 4) * 129 * 257 + 17 * px5) / (ms5 * 1e-3) / 1e9,
+        "frac_hbm": mine * ((d * 4 + C * 4) * 129 * 257 + 17 * px5) / (ms5 * 1e-3) / 1e9 / peak,
+        "note": "pseudolabel_generator.py:69-85 + the rectification of self_training.py:298-304 per image: fused two-scale "
+                "labels, prototype weights of [1,2048,129,257], consensus selection; no collective (image-sharded)"}
+    del pool5
     return out
 
 
