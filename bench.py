@@ -552,6 +552,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
     import diga_b200 as D
     from diga_b200 import _lib as L, synthetic as S
