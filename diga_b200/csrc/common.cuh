@@ -139,6 +139,32 @@ __device__ __forceinline__ float fast_rcp(float x) {   // MUFU.RCP, 1 ulp
   return r;
 }
 
+// First index of the maximum of v[0..C) (torch.max / np.argmax tie rule) as a pairwise tournament: in every comparison
+// the left operand covers the lower indices and the right one wins only if STRICTLY greater, so ties resolve to the lowest
+// index exactly like the left-to-right scan, but the dependency depth is log2(C) instead of C (the scan left the
+// ALU-bound label kernels waiting on their own compare -> select chain).  Entries c >= nclass must hold -inf.
+template <int C>
+__device__ __forceinline__ void argmax_first(const float (&v)[C], float& best, int& arg) {
+  float bv[C];
+  int bi[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    bv[c] = v[c];
+    bi[c] = c;
+  }
+#pragma unroll
+  for (int stride = 1; stride < C; stride *= 2) {
+#pragma unroll
+    for (int i = 0; i + stride < C; i += 2 * stride) {
+      const bool gt = bv[i + stride] > bv[i];
+      bv[i] = gt ? bv[i + stride] : bv[i];
+      bi[i] = gt ? bi[i + stride] : bi[i];
+    }
+  }
+  best = bv[0];
+  arg = bi[0];
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

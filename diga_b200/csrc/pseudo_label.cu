@@ -157,21 +157,17 @@ pseudo_label_upsampled_kernel(const float* __restrict__ z1, int h1, int w1, floa
     }
     float z[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c)
+    for (int c = 0; c < C; ++c) {
+      float val = -INFINITY;
       if (!PAD || c < nclass) {
-        float val = c1.value(ty1, 0, c);
+        val = c1.value(ty1, 0, c);
         if constexpr (HAS2) val = fmaxf(val, c2.value(ty2, 0, c));   // torch.max(output_ds, output), :80
-        z[c] = val;
       }
-    float m = z[0];
-    int am = 0;
-#pragma unroll
-    for (int c = 1; c < C; ++c)
-      if (!PAD || c < nclass) {
-        const bool gt = z[c] > m;
-        m = gt ? z[c] : m;
-        am = gt ? c : am;
-      }
+      z[c] = val;
+    }
+    float m;
+    int am;
+    argmax_first<C>(z, m, am);
     const int64_t o = (img * H + Y) * W + X;
     if (lab8) lab8[o] = (uint8_t)am;
     if (lab64) lab64[o] = am;

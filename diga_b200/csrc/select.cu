@@ -34,10 +34,10 @@ upsample_bilinear_kernel(const float* __restrict__ in, int64_t planes, int h, in
 // One thread = PX adjacent output pixels x RY consecutive output rows (ColumnInterp keeps the horizontally
 // interpolated source rows of all classes in registers while it walks down).  A warp covers 32*PX adjacent
 // pixels of a row, so the int64 accesses are 128-bit and fully coalesced.  torch.max(dim=1): first index on ties.
-template <int C, bool PAD, int PX, int RY, int BLOCK>
+template <int C, bool PAD, int PX, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict__ pseudo, int nclass, int h, int w, int H,
-                        int W, float sh, float sw, int64_t* __restrict__ kept, int64_t* __restrict__ feat_pseudo) {
+                        int W, float sh, float sw, int RY, int64_t* __restrict__ kept, int64_t* __restrict__ feat_pseudo) {
   const int64_t img = blockIdx.z;
   const int Y0 = blockIdx.y * RY;
   const int X0 = (blockIdx.x * BLOCK + threadIdx.x) * PX;
@@ -69,16 +69,12 @@ consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict_
     int64_t am[PX];
 #pragma unroll
     for (int v = 0; v < PX; ++v) {
-      float best = ci.value(ty, v, 0);
-      int arg = 0;
+      float val[C];
 #pragma unroll
-      for (int c = 1; c < C; ++c)
-        if (!PAD || c < nclass) {
-          const float val = ci.value(ty, v, c);
-          const bool gt = val > best;
-          best = gt ? val : best;
-          arg = gt ? c : arg;
-        }
+      for (int c = 0; c < C; ++c) val[c] = (!PAD || c < nclass) ? ci.value(ty, v, c) : -INFINITY;
+      float best;
+      int arg;
+      argmax_first<C>(val, best, arg);
       am[v] = arg;
     }
     const int64_t o = (img * H + Y) * W + X0;
@@ -132,17 +128,23 @@ int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, in
   cudaStream_t st = (cudaStream_t)stream;
   const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
   const bool pair = (W % 2) == 0 && aligned(pseudo, 16) && aligned(kept, 16) && aligned(feat_pseudo, 16);
-  constexpr int BLOCK = 128, RY = 8;
+  // Launch shape (tools/tune.py select, profiles/r01_tune_select.jsonl): a thread walks RY output rows of PX adjacent
+  // columns.  Longer walks amortise the two source rows a strip interpolates first but leave too few warps (RY = 64:
+  // 48 us, 128: 80 us); two columns x 16 rows is the best of the sweep (35.7 us).  The kernel is ALU-bound: per pixel
+  // 19 x (bit-exact 2-op interpolation + 3-op arg-max) plus the strip set-up, 190 instructions at 67 % issue.
+  constexpr int BLOCK = 128;
+  const int RY = tunable("select_ry", 16) < 1 ? 1 : tunable("select_ry", 16);
+  const bool two = pair && tunable("select_px", 2) == 2;
   const unsigned gy = (unsigned)((H + RY - 1) / RY);
   DIGA_DISPATCH_C(C, {
-    if (pair) {
+    if (two) {
       dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), gy, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 2, RY, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
-                                                                             (int)H, (int)W, sh, sw, kept, feat_pseudo);
+      consensus_select_kernel<kC, kPad, 2, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
+                                                                         (int)W, sh, sw, RY, kept, feat_pseudo);
     } else {
       dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), gy, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 1, RY, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w,
-                                                                             (int)H, (int)W, sh, sw, kept, feat_pseudo);
+      consensus_select_kernel<kC, kPad, 1, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
+                                                                         (int)W, sh, sw, RY, kept, feat_pseudo);
     }
   });
   DIGA_CHECK_LAUNCH("consensus_select_kernel");

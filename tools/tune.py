@@ -104,6 +104,19 @@ def sweep_accum():
     L.set_tunable("accum_variant", 0)
 
 
+def sweep_select():
+    g = S.gen(6, dev)
+    b, hh, ww, h, w = 8, 512, 1024, 65, 129
+    wl = torch.softmax(S.logits((b, 19, h, w), g), 1)
+    tl = S.block_labels(b, hh, ww, g)
+    for px, ry in itertools.product((1, 2), (8, 16, 32, 64, 128)):
+        L.set_tunable("select_px", px); L.set_tunable("select_ry", ry)
+        report("consensus_select", {"px": px, "ry": ry}, timeit(lambda: D.consensus_select(tl, wl)), b * hh * ww * 24)
+        report("consensus_select_no_feat_pseudo", {"px": px, "ry": ry},
+               timeit(lambda: D.consensus_select(tl, wl, want_feat_pseudo=False)), b * hh * ww * 16)
+    L.set_tunable("select_px", 2); L.set_tunable("select_ry", 16)
+
+
 def sweep_cm():
     import random
     g = S.gen(4, dev)
