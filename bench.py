@@ -284,6 +284,14 @@ def bench_stages(D, S, dev, peak, world, quick):
     add("confusion_matrix_eval", n * hh * ww, 9, lambda: rs.update(gt_eval, pred_eval))
     del gt_eval, pred_eval
 
+    # next row f3, reader half: decoded 1024x2048 label PNGs -> PIL-NEAREST resize to 512x1024 + id look-up -> int64
+    from diga_b200.util.labels import resize_remap_labels, trainid_lut
+    raw_ids = torch.randint(0, 34, (8, 1024, 2048), device=dev, dtype=torch.uint8, generator=g)
+    lut_ids = trainid_lut()
+    add("label_reader_resize_remap", 8 * 512 * 1024, 9, lambda: resize_remap_labels(raw_ids, (512, 1024), lut_ids),
+        extra={"note": "CityLoader.py:93-95 + :113-132 after the PNG decode: 1 B gathered + 8 B written per output pixel"})
+    del raw_ids
+
     # config 3 pieces: B=8 @512x1024, features [8,2048,65,129]
     b, hh, ww, h, w, d = 8, 512, 1024, 65, 129, 2048
     sl = S.block_labels(b, hh, ww, g)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "diga_seg_kd_up_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
     "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
+    "diga_label_resize_remap": (_i, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
     "diga_confusion_matrix": (_i, [_p, _i, _p, _i, _i64, _i64, _p, _p, _p]),
 }
 

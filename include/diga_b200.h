@@ -246,6 +246,15 @@ int diga_ema_update(float* const* teacher_host, const float* const* student_host
 int diga_confusion_matrix(const void* label_true, int true_is_u8, const void* label_pred, int pred_is_u8, int64_t total,
                           int64_t n_class, int64_t* hist, uint32_t* flags, diga_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f3 (next row), reader half — util/loader/CityLoader.py:93-95 (NEAREST resize) + :115-132 (id re-assignment)
+ *   out[i, y, x] = lut[src[i, ytab[y], xtab[x]]]: src uint8 [n, h0, w0] (decoded label / pseudo-label PNGs), ytab [H] and
+ *   xtab [W] int32 DEVICE tables of source indices (Pillow's NEAREST transform, built by the caller once per geometry),
+ *   lut_host[256] uint8 in HOST memory (consumed before the call returns: id -> trainId, or v < 19 ? v : 255), out int64.
+ * ------------------------------------------------------------------------------------------ */
+int diga_label_resize_remap(const uint8_t* src, int64_t n, int64_t h0, int64_t w0, const int32_t* ytab, const int32_t* xtab,
+                            int64_t H, int64_t W, const uint8_t* lut_host, int64_t* out, diga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

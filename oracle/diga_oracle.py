@@ -395,6 +395,33 @@ class RunningScoreOracle:
 
 
 # --------------------------------------------------------------------------------------
+# f3 reader half: label maps as the loader delivers them   (G/util/loader/CityLoader.py:86-95, :113-131)
+# --------------------------------------------------------------------------------------
+CITY_ID_TO_TRAINID = {7: 0, 8: 1, 11: 2, 12: 3, 13: 4, 17: 5, 19: 6, 20: 7, 21: 8, 22: 9, 23: 10, 24: 11, 25: 12, 26: 13,
+                      27: 14, 28: 15, 31: 16, 32: 17, 33: 18}                       # CityLoader.py:49-56
+
+
+def city_loader_labels(label_img, pseudo_img, crop_size=None, n_classes=19, id_to_trainid=None):
+    """``CityLoader.__getitem__`` restricted to the two label maps, PIL images in, int64 numpy maps out: NEAREST resize
+    to ``crop_size`` = (H, W) (:92-95), ground-truth ids -> trainIds (:113-118), pseudo-label ids >= n_classes -> 255
+    (:123, :129-131).  ``np.compat.long`` of the reference is int64."""
+    from PIL import Image
+    id_to_trainid = id_to_trainid or CITY_ID_TO_TRAINID
+    if crop_size is not None:                                                          # :92
+        label_img = label_img.resize((crop_size[1], crop_size[0]), Image.NEAREST)     # :94
+        pseudo_img = pseudo_img.resize((crop_size[1], crop_size[0]), Image.NEAREST)   # :96
+    label = np.asarray(label_img, np.int64)                                            # :122
+    pseudo_label = np.asarray(pseudo_img, np.int64)                                    # :123
+    label_copy = 255 * np.ones(label.shape, dtype=np.int64)                            # :125
+    for k, v in id_to_trainid.items():                                                 # :126-127
+        label_copy[label == k] = v
+    pseudo_label_copy = 255 * np.ones(pseudo_label.shape, dtype=np.int64)              # :129
+    for v in range(n_classes):                                                         # :130-131
+        pseudo_label_copy[pseudo_label == v] = v
+    return label_copy, pseudo_label_copy
+
+
+# --------------------------------------------------------------------------------------
 # drivers used as CPU baseline / multi-rank checks
 # --------------------------------------------------------------------------------------
 def centroid_pass(feats: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], numbers=19, feat_dim=256,

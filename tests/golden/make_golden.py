@@ -289,6 +289,32 @@ def main():
          overall_acc=score['Overall Acc: \t'], mean_acc=score['Mean Acc : \t'], fwavacc=score['FreqW Acc : \t'],
          mean_iu=score['Mean IoU : \t'], cls_iu=np.array([cls_iu[k] for k in range(19)]))
 
+    # ---- f3 reader half: exec G/util/loader/CityLoader.py:92-96 (NEAREST resize) and :122-132 (id re-assignment) on two
+    #      synthetic PNG-like images (a labelIds map with ids 0..33 and a 'P'-mode pseudo-label map with indices 0..18, 255)
+    from PIL import Image
+
+    class _NP:                                     # numpy with the `np.compat.long` the reference still uses (removed in numpy 2)
+        compat = type("compat", (), {"long": np.int64})
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+    gen_l = torch.Generator().manual_seed(515)
+    h0, w0, crop = 60, 104, (32, 56)
+    ids = torch.randint(0, 34, (h0 // 4, w0 // 4), generator=gen_l).repeat_interleave(4, 0).repeat_interleave(4, 1).numpy().astype(np.uint8)
+    pl = torch.randint(0, 19, (h0 // 4, w0 // 4), generator=gen_l).repeat_interleave(4, 0).repeat_interleave(4, 1).numpy().astype(np.uint8)
+    pl[:8, :12] = 255
+    pl[20:24, 40:44] = 19                                                              # an index outside the class range
+    me = type("Self", (), {"crop_size": crop, "use_pseudo": True, "n_classes": 19,
+                           "id_to_trainid": {7: 0, 8: 1, 11: 2, 12: 3, 13: 4, 17: 5, 19: 6, 20: 7, 21: 8, 22: 9, 23: 10, 24: 11,
+                                             25: 12, 26: 13, 27: 14, 28: 15, 31: 16, 32: 17, 33: 18}})()
+    ns = {"np": _NP(), "Image": Image, "self": me, "label": Image.fromarray(ids), "pseudo_label": Image.fromarray(pl),
+          "image": Image.fromarray(np.zeros((h0, w0, 3), np.uint8))}
+    exec(_lines("util/loader/CityLoader.py", 92, 96), ns)
+    exec(_lines("util/loader/CityLoader.py", 122, 132), ns)
+    save("city_loader_labels", ids=ids, pseudo=pl, crop_size=np.array(crop), label_copy=ns["label_copy"],
+         pseudo_label_copy=ns["pseudo_label_copy"])
+
 
 if __name__ == "__main__":
     main()

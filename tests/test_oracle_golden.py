@@ -260,3 +260,22 @@ def test_running_score_matches_reference(golden):
         with contextlib.redirect_stdout(io.StringIO()):
             lscore, _ = live.get_scores()
         assert np.array_equal(live.confusion_matrix, g["confusion_matrix"]) and lscore['Mean IoU : \t'] == g["mean_iu"]
+
+
+def test_city_loader_labels_match_reference(golden):
+    """CityLoader.py:92-96, :122-132 (label / pseudo-label maps): the oracle restatement and the host-side NEAREST index
+    table the CUDA reader uses, both against what the reference's own statements produced."""
+    from PIL import Image
+    g = golden("city_loader_labels")
+    crop = tuple(int(v) for v in g["crop_size"])
+    lab, pl = O.city_loader_labels(Image.fromarray(g["ids"]), Image.fromarray(g["pseudo"]), crop)
+    assert np.array_equal(lab, g["label_copy"]) and np.array_equal(pl, g["pseudo_label_copy"])
+    assert lab.dtype == np.int64 and (g["pseudo_label_copy"] == 255).any() and (g["pseudo"] == 19).any()
+    # the index tables of diga_b200.util.labels (pure host code, no CUDA) reproduce Pillow's NEAREST transform
+    from diga_b200.util.labels import pil_nearest_table as table      # host code; the package loads without a GPU
+    rng = np.random.default_rng(3)
+    for h0, w0, hh, ww in [(1024, 2048, 512, 1024), (1024, 2048, 512, 896), (1052, 1914, 512, 896), (60, 104, 32, 56), (7, 9, 20, 31)] + \
+            [tuple(int(v) for v in rng.integers(1, 200, 4)) for _ in range(60)]:
+        img = rng.integers(0, 256, (h0, w0), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((ww, hh), Image.NEAREST))
+        assert np.array_equal(img[table(h0, hh)][:, table(w0, ww)], ref), (h0, w0, hh, ww)
