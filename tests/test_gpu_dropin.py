@@ -237,3 +237,30 @@ def test_generate_pseudo_labels_writes_reference_format(tmp_path):
                 assert png.mode == "P" and png.getpalette() == CITYSCAPES_PALETTE
                 got = np.array(png)
                 assert got.dtype == np.uint8 and (got != ref[j]).mean() < 1e-4       # exact softmax ties only
+
+
+def test_evaluate_val_driver_matches_reference_loop():
+    """diga_b200.util.metrics.evaluate_val (evaluate_val.py:72-90) on a stand-in model: same confusion matrix and scores as
+    the reference statements (nn.Upsample x2, torch.max, arg-max, numpy bincount) evaluated with torch on the GPU + oracle."""
+    import contextlib
+    import io
+    from diga_b200 import synthetic as S
+    from diga_b200.util.metrics import evaluate_val, runningScore
+    model = TinySeg().to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    size = (128, 192)
+    g = S.gen(9)
+    loader = [(torch.randn((1, 3, *size), generator=gen), S.block_labels(1, *size, g, 16)) for _ in range(3)]
+    rs = runningScore(19)
+    with contextlib.redirect_stdout(io.StringIO()):
+        score, cls_iu = evaluate_val(model, loader, 19, size, rs)
+    ref = O.RunningScoreOracle(19)
+    with torch.no_grad():
+        for image, gt in loader:
+            image = image.to(DEV)
+            image_ds = F.interpolate(image, (size[0] // 2, size[1] // 2), mode="bilinear", align_corners=True)
+            pred = torch.max(O.upsample_bilinear_ac(model(image_ds)[2], size), O.upsample_bilinear_ac(model(image)[2], size))
+            ref.update(gt.numpy(), pred.max(1)[1].cpu().numpy())
+    assert (rs.confusion_matrix != ref.confusion_matrix).sum() <= 2          # exact softmax/logit ties only
+    rscore, _ = ref.get_scores()
+    assert abs(score['Mean IoU : \t'] - rscore['Mean IoU : \t']) < 1e-4
