@@ -344,7 +344,8 @@ loss_up_kernel(const LossUpArgs a) {
             if constexpr (KD) mt = fmaxf(mt, ct.value(yl1, c));
           }
       }
-      float Ss4[4] = {0.f, 0.f, 0.f, 0.f}, St4[4] = {0.f, 0.f, 0.f, 0.f}, cr4[4] = {0.f, 0.f, 0.f, 0.f};
+      float Ss4[4] = {0.f, 0.f, 0.f, 0.f};
+      [[maybe_unused]] float St4[4] = {0.f, 0.f, 0.f, 0.f}, cr4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < C; ++c)
         if (!PAD || c < nclass) {
