@@ -37,6 +37,32 @@ elif which == "plup":
     l1, l2 = S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g)
     for _ in range(3):
         D.pseudo_label_two_scale(l1, l2, (1024, 2048))
+elif which == "ce":
+    x = S.logits((4, 19, 512, 1024), g); t = S.block_labels(4, 512, 1024, g); one = torch.tensor(1.0, device=dev)
+    for _ in range(3):
+        xx = x.detach().requires_grad_(True)
+        torch.autograd.grad(D.cross_entropy2d(xx, t), xx, grad_outputs=one)
+elif which == "ema":
+    from diga_b200.util.utils import ema_update_tensors
+    sizes = [1024 * 256, 256 * 256 * 9, 256 * 1024, 1024] * 23 + [2048 * 512, 512 * 512 * 9, 512 * 2048] * 3
+    tea = [torch.randn(sz, device=dev) for sz in sizes]; stu = [torch.randn(sz, device=dev) for sz in sizes]
+    for _ in range(3):
+        ema_update_tensors(tea, stu, 0.999)
+elif which == "eval":
+    from diga_b200.util.metrics import runningScore
+    from diga_b200.util.labels import resize_remap_labels, trainid_lut
+    gt = S.block_labels(4, 1024, 2048, g)
+    pred, _ = D.pseudo_label_two_scale(S.logits((4, 19, 129, 257), g), S.logits((4, 19, 65, 129), g), (1024, 2048), want_conf=False)
+    raw = torch.randint(0, 34, (8, 1024, 2048), device=dev, dtype=torch.uint8)
+    rs = runningScore(19)
+    for _ in range(3):
+        rs.update(gt, pred)
+        resize_remap_labels(raw, (512, 1024), trainid_lut())
+elif which == "presence":
+    from diga_b200.classmix import present_classes
+    sl = S.block_labels(8, 512, 1024, g)
+    for _ in range(3):
+        present_classes(sl)
 elif which == "lossup":
     tea, stu = S.logits((8, 19, 65, 129), g), S.logits((8, 19, 65, 129), g)
     tgt = S.block_labels(4, 512, 1024, g)
