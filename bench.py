@@ -401,6 +401,16 @@ def bench_stages(D, S, dev, peak, world, quick):
         extra={"note": "distillation_loss_upsampled + autograd from [8,19,65,129]: replaces 2 up-samplings (76 B/px written each), "
                        "the 380 B/px KD pair and the up-sampling backward; ALU/MUFU-bound (38 ex2 per pixel-position)"})
     add("cross_entropy2d_fused_upsample_fwd_bwd", 4 * hh * ww, 8 + 2 * C * 4 * (h * w) / (hh * ww), ce_up_step)
+    ohem = D.OhemCrossEntropy(255, 0.7, 100000)
+
+    def ohem_up_step():
+        x = lo_s[:4].detach().requires_grad_(True)
+        loss = ohem(x, ce_t)
+        return loss, torch.autograd.grad(loss, x, grad_outputs=upc)
+
+    add("ohem_cross_entropy_fused_upsample_fwd_bwd", 4 * hh * ww, 8 + 8 + 3 * 4 + 2 * C * 4 * (h * w) / (hh * ww), ohem_up_step,
+        extra={"note": "OhemCrossEntropy (util/loss.py:65-122, Synthia tree) from [4,19,65,129]: pred/loss pass, exact radix "
+                       "select of the min_kept-th probability (3 histogram passes), kept-pixel mean, CE gradient over the kept"})
     add("seg_plus_kd_fused_upsample_fwd_bwd", 8 * hh * ww, lowres_bytes + 4, seg_kd_up_step,
         extra={"note": "self_training.py:348-352 on the shared s_pred_cat_stu: CE on the source half + KD on both views, "
                        "one loss pass + one gradient pass over the stride-8 logits"})

@@ -20,12 +20,12 @@ from .calc_centroids import Class_Features, calc_centroids
 from .classmix import classmix, present_classes_async
 from .pseudolabel import pseudo_label, pseudo_label_two_scale
 from .selection import consensus_select
-from .util.loss import (cross_entropy2d, cross_entropy2d_upsampled, distillation_loss, distillation_loss_and_grad,
+from .util.loss import (OhemCrossEntropy, cross_entropy2d, cross_entropy2d_upsampled, distillation_loss, distillation_loss_and_grad,
                         distillation_loss_upsampled, distillation_loss_upsampled_and_grad,
                         seg_distillation_losses_upsampled, seg_distillation_total_upsampled)
 from .util.utils import process_label, update_teacher_params
 
-__all__ = ["present_classes_async", "Class_Features", "calc_centroids", "classmix", "pseudo_label", "pseudo_label_two_scale",
+__all__ = ["OhemCrossEntropy", "present_classes_async", "Class_Features", "calc_centroids", "classmix", "pseudo_label", "pseudo_label_two_scale",
            "consensus_select", "distillation_loss", "distillation_loss_and_grad", "process_label", "cross_entropy2d",
            "update_teacher_params", "distillation_loss_upsampled", "cross_entropy2d_upsampled",
            "seg_distillation_losses_upsampled", "seg_distillation_total_upsampled", "distillation_loss_upsampled_and_grad"]

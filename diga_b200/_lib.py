@@ -62,6 +62,9 @@ SIGNATURES = {
     "diga_ce_up_fwd_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p, _p]),
     "diga_seg_kd_up_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _f, _f, _p, _p, _p, _p, _p, _p]),
     "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
+    "diga_ohem_up_workspace_bytes": (C.c_size_t, []),
+    "diga_ohem_up_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "diga_ohem_up_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
     "diga_label_resize_remap": (_i, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
     "diga_confusion_matrix": (_i, [_p, _i, _p, _i, _i64, _i64, _p, _p, _p]),
@@ -137,6 +140,11 @@ def loss_up_workspace(n, c, h, w, hh, ww, device: torch.device) -> torch.Tensor:
     """Workspace of the fused up-sampling losses (reduction partials + gradient patches), one per geometry/stream."""
     nbytes = int(lib.diga_loss_up_workspace_bytes(n, c, h, w, hh, ww))
     return _workspace(("loss_up", n, c, h, w, hh, ww), nbytes, device)
+
+
+def ohem_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised OHEM selection state (histogram, rank, reduction partials), one per (device, stream)."""
+    return _workspace("ohem", int(lib.diga_ohem_up_workspace_bytes()), device)
 
 
 def kd_workspace(device: torch.device) -> torch.Tensor:

@@ -20,10 +20,9 @@
 //                columns that share a source column (i0 is monotone in X, so a run is a contiguous range);
 //   the CTA writes its partial low-resolution patch [R rows][K cols][C padded to 4] to a scratch slot of its own;
 //   gather     : a second, tiny kernel adds the <= 2x2 patches that overlap each low-resolution element, in fixed order.
-#include "bilinear.cuh"
 #include <type_traits>
 
-#include "common.cuh"
+#include "lerp_column.cuh"
 
 namespace diga {
 
@@ -89,6 +88,9 @@ struct LossUpArgs {
   const float* denom;
   float up_kd_host;        // used when up_kd == null (single-pass variants)
   float up_ce_host;        // used when up_ce == null
+  const float* sel_pred;   // OHEM (csrc/ohem_up.cu): per-pixel target probability [n_ce,H,W], < 0 = ignored; null = plain CE
+  const float* sel_thr;    // OHEM: device scalar, a pixel is kept iff 0 <= sel_pred < sel_thr[0]
+  int ignore_label;        // OHEM: target value that is masked out (CE: 255 is >= nclass anyway)
   int ry, R, K;
   float* scratch;
   double* partial;
@@ -99,85 +101,6 @@ struct LossUpArgs {
 };
 
 __device__ __forceinline__ int lu_swz(int x) { return x + (x >> 3); }
-
-// Three-input max (sm_100: one FMNMX3 instead of two FMNMX).
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
-// Vertical walk of one column in the log2 domain.  For the current source cell the thread keeps, per class,
-//     top[c] = (row_i0[c] - ref) * log2(e)     dif[c] = (row_i1[c] - row_i0[c]) * log2(e)
-// where row_* are the horizontally interpolated source rows and `ref` is the largest value either row holds in any
-// class, so that every interpolated value  v_c = top[c] + l1 * dif[c]  (ONE FFMA per class and output row) is <= 0 and
-// can go straight into ex2: no per-pixel max, no per-pixel rescaling.  softmax / log-sum-exp / soft-target cross
-// entropy are invariant to the choice of ref; `ref` only has to keep the sums away from underflow, which the caller
-// checks per pixel (it falls back to the exact per-pixel max when a sum drops below 2^-60).
-// The loss path is held to 1e-5, not to the bit pattern of ATen's up-sampler (the label paths keep ColumnInterp).
-template <int C, bool PAD>
-struct LerpColumn {
-  float top[C], dif[C];
-  float ref2 = 0.f;       // reference, log2 units
-
-  // dst[c] = l0s * v[c][k] + l1s * v[c][k + 1] - sub.  `q` points at v[0][k]; one 64-bit pointer bump per class, the
-  // second load is the same register with an immediate offset (PAIR = false: single-column source, w == 1).
-  template <bool PAIR>
-  __device__ __forceinline__ void hrow(float (&dst)[C], const float* __restrict__ q, int64_t class_stride, float l0s, float l1s,
-                                       float sub, int nclass) {
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) {
-        dst[c] = fmaf(l0s, __ldg(q), fmaf(l1s, __ldg(q + (PAIR ? 1 : 0)), -sub));
-        q += class_stride;
-      }
-  }
-  __device__ __forceinline__ float rowmax(const float (&v)[C], int nclass) {
-    float m0 = v[0], m1 = v[0], m2 = v[0];
-#pragma unroll
-    for (int c = 1; c + 1 < C; c += 2) {
-      float& m = ((c >> 1) % 3 == 0) ? m0 : ((c >> 1) % 3 == 1) ? m1 : m2;
-      if (!PAD || c + 1 < nclass) m = fmax3(m, v[c], v[c + 1]);
-      else if (c < nclass) m = fmaxf(m, v[c]);
-    }
-    if constexpr ((C & 1) == 0) {
-      if (!PAD || C - 1 < nclass) m0 = fmaxf(m0, v[C - 1]);
-    }
-    return fmax3(m0, m1, m2);
-  }
-  // rows r0 (-> top) and r1 (-> bottom) of the cell; `fresh` = first cell of the strip, otherwise the old bottom row
-  // (top + dif) becomes the new top row.
-  __device__ __forceinline__ void enter(bool fresh, const float* __restrict__ base, int64_t row_stride, int64_t class_stride, int r0,
-                                        int r1, bool pair, float l0s, float l1s, int nclass) {
-    if (fresh) {
-      if (pair) hrow<true>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
-      else hrow<false>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
-      ref2 = 0.f;
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) top[c] += dif[c];
-    }
-    float m = rowmax(top, nclass);
-    if (r1 != r0) {
-      if (pair) hrow<true>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
-      else hrow<false>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
-      m = fmaxf(m, rowmax(dif, nclass));
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        dif[c] -= top[c];
-        top[c] -= m;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        dif[c] = 0.f;
-        top[c] -= m;
-      }
-    }
-    ref2 += m;
-  }
-  __device__ __forceinline__ float value(float l1, int c) const { return fmaf(l1, dif[c], top[c]); }
-};
 
 #ifndef LU_MINB_LOSS
 #define LU_MINB_LOSS 3      // resident CTAs per SM the loss-only kernels are compiled for (168 registers, no spills; 4 spills and is slower)
@@ -217,6 +140,10 @@ loss_up_kernel(const LossUpArgs a) {
     if constexpr (KD) ckd = (a.up_kd != nullptr ? __ldg(a.up_kd) : a.up_kd_host) * a.inv_count_kd * wkd;
     if (ce_img) cce = (a.up_ce != nullptr ? __ldg(a.up_ce) : a.up_ce_host) / ((a.size_average && a.denom != nullptr) ? __ldg(a.denom) : 1.0f);
   }
+
+  const bool ohem = CE && a.sel_pred != nullptr;
+  const float sel_thr = ohem ? __ldg(a.sel_thr) : 0.f;
+  const float* prow = (ohem && ce_img) ? a.sel_pred + ((int64_t)n * a.H) * a.W + (in_range ? X : a.W - 1) : nullptr;
 
   // ---- CTA geometry: source rows from ylo, source columns xlo..xhi --------------------------------------------------
   const int nvalid = min(kLuBlock, a.W - X0);
@@ -381,7 +308,11 @@ loss_up_kernel(const LossUpArgs a) {
     bool counted = false, valid = false;
     if constexpr (CE) {
       counted = ce_img && in_range && tgt >= 0;                     // loss.py:56  mask = target >= 0
-      valid = counted && tgt < nclass;                              // 255 (any id >= C) is ignored by nll_loss
+      valid = counted && tgt < nclass && tgt != a.ignore_label;     // 255 (any id >= C) is ignored by nll_loss
+      if (ohem && valid) {                                          // OhemCrossEntropy keeps the hard pixels only
+        const float pv = __ldg(prow + (int64_t)Y * a.W);
+        valid = pv >= 0.f && pv < sel_thr;
+      }
       if (valid && a.weight != nullptr) wt = __ldg(a.weight + tgt);
     }
     if constexpr (LOSS) {                                            // accumulated in log2 units (x ln 2 at the end)
@@ -629,6 +560,7 @@ static LossUpArgs fill_args(const LossUpPlan& p, void* workspace, const float* t
   a.scale = scale;
   a.inv_count_kd = (float)(1.0 / ((double)(n / 2 > 0 ? n / 2 : 1) * (double)H * (double)W));
   a.size_average = size_average;
+  a.ignore_label = DIGA_IGNORE_LABEL;
   a.ry = p.ry;
   a.R = p.R;
   a.K = p.K;
@@ -758,6 +690,26 @@ int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, c
   a.loss_ce = loss_ce;
   a.denom_out = denom_out;                                // rewritten with the same value by the loss reduction
   return launch_loss_up<true, true, true, true>(a, p, C, dstudent_low, st);
+}
+
+/* OhemCrossEntropy backward (csrc/ohem_up.cu holds the forward): the CE gradient pass restricted to the kept pixels
+ * (0 <= pred < thr[0]), divided by their number `count[0]`. */
+int diga_ohem_up_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h, int64_t w,
+                     int64_t H, int64_t W, int64_t ignore_label, const float* pred, const float* thr, const float* count,
+                     const float* upstream, float* dlogits_low, void* workspace, diga_stream_t stream) {
+  using namespace diga;
+  if (int rc = check_common("ohem_up_bwd", logits_low, n, C, h, w, H, W, workspace)) return rc;
+  DIGA_REQUIRE(target && pred && thr && count && upstream && dlogits_low, DIGA_ERR_INVALID, "ohem_up_bwd: null pointer");
+  DIGA_REQUIRE(aligned(target, 8) && aligned(weight, 4) && aligned(pred, 4) && aligned(dlogits_low, 4), DIGA_ERR_MISALIGNED,
+               "ohem_up_bwd: misaligned pointer");
+  const LossUpPlan p = make_plan(n, C, h, w, H, W);
+  LossUpArgs a = fill_args(p, workspace, nullptr, logits_low, target, weight, n, n, C, h, w, H, W, 0.f, 1);
+  a.up_ce = upstream;
+  a.denom = count;
+  a.sel_pred = pred;
+  a.sel_thr = thr;
+  a.ignore_label = (int)ignore_label;
+  return launch_loss_up<false, true, false, true>(a, p, C, dlogits_low, (cudaStream_t)stream);
 }
 
 }  // extern "C"

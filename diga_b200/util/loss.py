@@ -293,3 +293,60 @@ def seg_distillation_total_upsampled(teacher_low, student_low, target, lambda_se
     size = _check_low(student_low, target.shape[1:], "seg_distillation_total_upsampled")
     return _SegDistillationTotal.apply(teacher_low, student_low, target, weight, size, scale, size_average, float(lambda_seg),
                                        float(lambda_distil))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# OhemCrossEntropy (G/util/loss.py:65-122; the seg loss of the Synthia tree, S/train_DiGA_syn2city_self_training.py:184)
+# ----------------------------------------------------------------------------------------------------------------------
+class _OhemUpsampled(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, target, weight, ignore_label, thresh, min_kept):
+        s, tg = L.f32c(score.detach()), L.i64c(target)
+        wt = None if weight is None else L.f32c(weight.detach()).to(s.device)
+        n, c, h, w = s.shape
+        hh, ww = tg.shape[1], tg.shape[2]
+        dev = s.device
+        pred = torch.empty((n, hh, ww), dtype=torch.float32, device=dev)
+        losspx = torch.empty((n, hh, ww), dtype=torch.float32, device=dev)
+        loss, count, thr = (torch.empty((), dtype=torch.float32, device=dev) for _ in range(3))
+        L.check(L.lib.diga_ohem_up_fwd(s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, c, h, w, hh, ww, int(ignore_label), float(thresh),
+                                       int(min_kept), pred.data_ptr(), losspx.data_ptr(), loss.data_ptr(), count.data_ptr(),
+                                       thr.data_ptr(), L.ohem_workspace(dev).data_ptr(), L.stream()))
+        ctx.save_for_backward(s, tg, pred, thr, count)
+        ctx.aux = (wt, int(ignore_label))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        s, tg, pred, thr, count = ctx.saved_tensors
+        wt, ignore_label = ctx.aux
+        n, c, h, w = s.shape
+        hh, ww = tg.shape[1], tg.shape[2]
+        g = grad_out.to(dtype=torch.float32, device=s.device).contiguous()
+        ds = torch.empty_like(s)
+        L.check(L.lib.diga_ohem_up_bwd(s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, c, h, w, hh, ww, ignore_label, pred.data_ptr(),
+                                       thr.data_ptr(), count.data_ptr(), g.data_ptr(), ds.data_ptr(),
+                                       L.loss_up_workspace(n, c, h, w, hh, ww, s.device).data_ptr(), L.stream()))
+        return ds, None, None, None, None, None
+
+
+class OhemCrossEntropy(torch.nn.Module):
+    """``util.loss.OhemCrossEntropy`` (G/util/loss.py:65-122): online hard example mining on the target-class probability —
+    keep the pixels whose probability is below ``max(thres, the min_kept-th smallest probability)``, mean CE over them.
+    Same constructor and ``forward(score, target)``; as in the reference, a ``score`` smaller than ``target`` is up-sampled
+    bilinearly (``align_corners=True``) first — here without materialising it, forward or backward."""
+
+    def __init__(self, ignore_label=255, thres=0.7, min_kept=100000, weight=None):
+        super().__init__()
+        self.thresh = thres
+        self.min_kept = max(1, min_kept)
+        self.ignore_label = ignore_label
+        self.weight = weight
+
+    def forward(self, score, target):
+        L.require_cuda(score, target, self.weight, what="OhemCrossEntropy input")
+        if score.dim() != 4 or target.dim() != 3 or score.shape[0] != target.shape[0]:
+            raise ValueError(f"OhemCrossEntropy: expected [N,C,h,w] scores and [N,H,W] targets, got {tuple(score.shape)} and "
+                             f"{tuple(target.shape)}")
+        _check_low(score, target.shape[1:], "OhemCrossEntropy")
+        return _OhemUpsampled.apply(score, target, self.weight, self.ignore_label, self.thresh, self.min_kept)

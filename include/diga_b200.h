@@ -228,6 +228,25 @@ int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64
                        void* workspace, diga_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * OhemCrossEntropy — util/loss.py:65-122 (the segmentation loss of the Synthia tree), from the stride-8 scores
+ *   (`_ohem_forward` up-samples the score to the label size itself, :91-96; H == h, W == w is the plain case).
+ *   pred = softmax(score)[target] over pixels with target != ignore_label; threshold = max(sorted(pred)[min(min_kept, M-1)],
+ *   thresh); loss = mean of -w[t] log_softmax(score)[t] over pixels with pred < threshold.
+ *   fwd: pred, losspx [n,H,W] fp32 (caller-allocated; pred is needed by the backward), loss_out / count_out (number of
+ *        kept pixels) / thr_out device scalars; the order statistic is exact (radix select on the float bits).
+ *        workspace: diga_ohem_up_workspace_bytes() bytes, zero-filled once by the caller (left zeroed).
+ *   bwd: dlogits_low = upstream[0] / count[0] * sum over kept pixels of w[t] (softmax - onehot), through the transposed
+ *        interpolation of the f1 loss kernels; workspace = diga_loss_up_workspace_bytes(n, C, h, w, H, W).
+ * ------------------------------------------------------------------------------------------ */
+size_t diga_ohem_up_workspace_bytes(void);
+int diga_ohem_up_fwd(const float* score_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
+                     int64_t w, int64_t H, int64_t W, int64_t ignore_label, float thresh, int64_t min_kept, float* pred,
+                     float* losspx, float* loss_out, float* count_out, float* thr_out, void* workspace, diga_stream_t stream);
+int diga_ohem_up_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h, int64_t w,
+                     int64_t H, int64_t W, int64_t ignore_label, const float* pred, const float* thr, const float* count,
+                     const float* upstream, float* dlogits_low, void* workspace, diga_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f4 (next row)  EMA teacher update — util/utils.py:103-116
  *   For each of `count` parameter tensors: teacher = alpha * teacher + (1 - alpha) * student (fp32, in place,
  *   separately rounded like the torch expression).  The three tables live in HOST memory (device pointers and

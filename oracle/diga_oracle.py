@@ -340,6 +340,35 @@ def seg_distillation_losses_upsampled(teacher_low, student_low, target, scale=0.
     return loss_semseg, distillation_loss(upsample_bilinear_ac(teacher_low, size), s_pred_cat_stu, scale)   # :289,:352
 
 
+class OhemCrossEntropyOracle(torch.nn.Module):
+    """``OhemCrossEntropy`` restated (G/util/loss.py:65-122; single-score form, ``weights = [1]``)."""
+
+    def __init__(self, ignore_label=255, thres=0.7, min_kept=100000, weight=None):
+        super().__init__()
+        self.thresh = thres                                                                   # :69
+        self.min_kept = max(1, min_kept)                                                      # :70
+        self.ignore_label = ignore_label
+        self.criterion = torch.nn.CrossEntropyLoss(weight=weight, ignore_index=ignore_label, reduction="none")   # :72-76
+
+    def forward(self, score, target):
+        ph, pw = score.size(2), score.size(3)                                                 # :91
+        h, w = target.size(1), target.size(2)
+        if ph != h or pw != w:                                                                # :93-95
+            score = F.interpolate(input=score, size=(h, w), mode="bilinear", align_corners=True)
+        pred = F.softmax(score, dim=1)                                                        # :96
+        pixel_losses = self.criterion(score, target).contiguous().view(-1)                    # :97
+        mask = target.contiguous().view(-1) != self.ignore_label                              # :98
+        tmp_target = target.clone()                                                           # :100-101
+        tmp_target[tmp_target == self.ignore_label] = 0
+        pred = pred.gather(1, tmp_target.unsqueeze(1))                                        # :102
+        pred, ind = pred.contiguous().view(-1,)[mask].contiguous().sort()                     # :103
+        min_value = pred[min(self.min_kept, pred.numel() - 1)]                                # :104
+        threshold = max(min_value, self.thresh)                                               # :105
+        pixel_losses = pixel_losses[mask][ind]                                                # :107
+        pixel_losses = pixel_losses[pred < threshold]                                         # :108
+        return pixel_losses.mean()                                                            # :109
+
+
 def ema_alpha(iteration, stage0=True, mean=False, replace=False):
     """G/util/utils.py:105-112."""
     if stage0 == True:      # noqa: E712

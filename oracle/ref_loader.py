@@ -51,11 +51,11 @@ def load(tree: str = "G") -> types.SimpleNamespace:
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        from util.loss import distillation_loss, cross_entropy2d          # noqa: E402
+        from util.loss import distillation_loss, cross_entropy2d, OhemCrossEntropy          # noqa: E402
         from util.utils import process_label, update_teacher_params       # noqa: E402
         from calc_centroids import Class_Features        # noqa: E402
         from util.metrics import runningScore            # noqa: E402
     load._tree = tree
     return types.SimpleNamespace(distillation_loss=distillation_loss, process_label=process_label,
                                  Class_Features=Class_Features, cross_entropy2d=cross_entropy2d,
-                                 update_teacher_params=update_teacher_params, runningScore=runningScore, tree=tree)
+                                 update_teacher_params=update_teacher_params, runningScore=runningScore, OhemCrossEntropy=OhemCrossEntropy, tree=tree)

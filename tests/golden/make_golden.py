@@ -315,6 +315,21 @@ def main():
     save("city_loader_labels", ids=ids, pseudo=pl, crop_size=np.array(crop), label_copy=ns["label_copy"],
          pseudo_label_copy=ns["pseudo_label_copy"])
 
+    # ---- OhemCrossEntropy (G/util/loss.py:65-122): low-resolution score (the loss up-samples it itself) and full-size score,
+    #      threshold decided by thresh (many easy pixels) and by the min_kept-th order statistic ----------------------------
+    gen_o = torch.Generator().manual_seed(8181)
+    for tag, shape, hw, thres, kept, use_w in (("ohem_low_thresh", (2, 16, 9, 13), (64, 96), 0.7, 1000, False),
+                                               ("ohem_low_minkept", (2, 19, 9, 13), (64, 96), 0.05, 3000, True),
+                                               ("ohem_full", (1, 16, 24, 40), (24, 40), 0.7, 100, False)):
+        sc = (3.0 * torch.randn(shape, generator=gen_o)).requires_grad_(True)
+        tg = _blocky_labels(gen_o, shape[0], hw[0], hw[1], 8, n_cls=shape[1], p_ignore=0.15)
+        wt = (0.5 + torch.rand(shape[1], generator=gen_o)) if use_w else None
+        crit = ref.OhemCrossEntropy(ignore_label=255, thres=thres, min_kept=kept, weight=wt)
+        loss = crit(sc, tg)
+        (loss * 0.5).backward()
+        save(tag, score=sc, target=tg, weight=(wt if use_w else torch.zeros(0)), thres=thres, min_kept=kept, upstream=0.5,
+             loss=loss, grad=sc.grad)
+
 
 if __name__ == "__main__":
     main()

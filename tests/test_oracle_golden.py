@@ -279,3 +279,15 @@ def test_city_loader_labels_match_reference(golden):
         img = rng.integers(0, 256, (h0, w0), dtype=np.uint8)
         ref = np.asarray(Image.fromarray(img).resize((ww, hh), Image.NEAREST))
         assert np.array_equal(img[table(h0, hh)][:, table(w0, ww)], ref), (h0, w0, hh, ww)
+
+
+@pytest.mark.parametrize("name", ["ohem_low_thresh", "ohem_low_minkept", "ohem_full"])
+def test_ohem_matches_reference_bitwise(golden, name):
+    """OhemCrossEntropy (G/util/loss.py:65-122), threshold from `thres` and from the min_kept-th order statistic."""
+    g = golden(name)
+    sc = T(g["score"]).requires_grad_(True)
+    wt = T(g["weight"]) if g["weight"].size else None
+    crit = O.OhemCrossEntropyOracle(255, float(g["thres"]), int(g["min_kept"]), wt)
+    loss = crit(sc, T(g["target"]))
+    (loss * float(g["upstream"])).backward()
+    assert np.array_equal(loss.detach().numpy(), g["loss"]) and np.array_equal(sc.grad.numpy(), g["grad"])
