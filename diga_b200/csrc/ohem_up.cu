@@ -149,30 +149,43 @@ ohem_hist_kernel(const float* __restrict__ pred, int64_t total, int level, OhemS
 // One CTA: find the bin that holds rank k, descend into it, clear the histogram for the next level.
 __global__ void __launch_bounds__(256)
 ohem_pick_kernel(OhemState* __restrict__ st, int level, unsigned int min_kept, float thresh, float* __restrict__ thr_out) {
-  __shared__ unsigned int part[256];
-  __shared__ unsigned int chosen_bin, chosen_rank;
+  __shared__ unsigned int part[256], incl[256];
+  __shared__ unsigned int chosen_bin, chosen_rank, rank_k;
   const int tid = threadIdx.x;
+  constexpr int PER = kOhBins / 256;
   unsigned int mine = 0;
-  for (int i = 0; i < kOhBins / 256; ++i) mine += st->hist[tid * (kOhBins / 256) + i];
+  for (int i = 0; i < PER; ++i) mine += st->hist[tid * PER + i];
   part[tid] = mine;
+  incl[tid] = mine;
   __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {                                 // inclusive prefix sum of the 256 chunk totals
+    const unsigned int add = tid >= o ? incl[tid - o] : 0u;
+    __syncthreads();
+    incl[tid] += add;
+    __syncthreads();
+  }
   if (tid == 0) {
     unsigned int k = st->k;
     if (level == 0) {
-      unsigned int M = 0;
-      for (int i = 0; i < 256; ++i) M += part[i];
+      const unsigned int M = incl[255];
       st->M = M;
       st->empty = (M == 0);
-      k = M == 0 ? 0u : (min_kept < M - 1 ? min_kept : M - 1);       // loss.py:106  min(self.min_kept, pred.numel() - 1)
+      k = M == 0 ? 0u : (min_kept < M - 1 ? min_kept : M - 1);       // loss.py:104  min(self.min_kept, pred.numel() - 1)
     }
-    unsigned int run = 0;
-    int chunk = 0;
-    while (chunk < 255 && run + part[chunk] <= k) run += part[chunk++];
-    int b = chunk * (kOhBins / 256);
-    const int bend = b + kOhBins / 256 - 1;
-    while (b < bend && run + st->hist[b] <= k) run += st->hist[b++];
-    chosen_bin = (unsigned)b;
-    chosen_rank = k - run;
+    rank_k = k;
+    chosen_bin = kOhBins - 1;
+    chosen_rank = 0;
+  }
+  __syncthreads();
+  {
+    const unsigned int k = rank_k, before = incl[tid] - part[tid];
+    if (before <= k && k < incl[tid]) {                               // exactly one chunk holds rank k (when M > 0)
+      unsigned int run = before;
+      int b = tid * PER;
+      while (b < tid * PER + PER - 1 && run + st->hist[b] <= k) run += st->hist[b++];
+      chosen_bin = (unsigned)b;
+      chosen_rank = k - run;
+    }
   }
   __syncthreads();
   for (int i = tid; i < kOhBins; i += 256) st->hist[i] = 0;
@@ -223,18 +236,31 @@ ohem_sum_kernel(const float* __restrict__ pred, const float* __restrict__ losspx
     is_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {
     __threadfence();
+    __shared__ double fs[256], fc[256];
     double a = 0.0, b = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) {                     // fixed order: deterministic
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) {      // fixed partition, fixed order: deterministic
       a += __ldcg(&st->part_sum[i]);
       b += __ldcg(&st->part_cnt[i]);
     }
-    loss_out[0] = (float)a / (float)b;                                 // :111 .mean()  (0 / 0 = NaN like torch on an empty selection)
-    count_out[0] = (float)b;
-    st->ticket = 0;
-    st->prefix = 0;
-    st->k = 0;
+    fs[threadIdx.x] = a;
+    fc[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) {
+        fs[threadIdx.x] += fs[threadIdx.x + o];
+        fc[threadIdx.x] += fc[threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      loss_out[0] = (float)fs[0] / (float)fc[0];                       // :109 .mean()  (0 / 0 = NaN like torch on an empty selection)
+      count_out[0] = (float)fc[0];
+      st->ticket = 0;
+      st->prefix = 0;
+      st->k = 0;
+    }
   }
 }
 

@@ -114,6 +114,20 @@ def main():
         l_ce = D.cross_entropy2d(O.upsample_bilinear_ac(s[:4], hi), tgt)
         return torch.autograd.grad([l_ce, l_kd], s, grad_outputs=[one, up])
 
+    ohem_d, ohem_t = D.OhemCrossEntropy(255, 0.7, 100000), O.OhemCrossEntropyOracle(255, 0.7, 100000)
+
+    def ohem_diga():
+        s = stu[:4].detach().requires_grad_(True)
+        loss = ohem_d(s, tgt)
+        return torch.autograd.grad(loss, s, grad_outputs=one)
+
+    def ohem_torch():
+        s = stu[:4].detach().requires_grad_(True)
+        loss = ohem_t(s, tgt)
+        return torch.autograd.grad(loss, s, grad_outputs=one)
+
+    report("ohem_up_fwd_bwd", timeit(ohem_diga), px // 2)
+    report("ohem_all_torch_eager_chain", timeit(ohem_torch, iters=10, warm=2, graph=False), px // 2)
     report("kd_materialised_torch_upsample_plus_diga_kd", timeit(materialised), px)
     report("kd_all_torch_eager_chain", timeit(eager, iters=10, warm=2), px)
     report("seg_plus_kd_materialised", timeit(materialised_both), px)
