@@ -443,8 +443,12 @@ def bench_stages(D, S, dev, peak, world, quick):
             wts = cf.get_centroid_weight(feat)                                                     # :301
             kept, feat_pseudo = D.consensus_select(tl, wts, (hh, ww))                              # :302-304
             _, mix2, mixlabel = D.classmix(sl, tdata_aug, sdata, kept, rng=rng3)                   # :306-325
-        cf.update_from_features(feat, t_pred, _labels_on_feature_grid(kept, (h, w)), start_mean=False)     # :327-334
-        cf.update_from_features(s_feat, s_pred, _labels_on_feature_grid(sl, (h, w)), start_mean=False)     # :336-341
+        if fused:      # label down-sampling (.float() + F.interpolate(nearest), :328-330, :336-337) folded into the assign kernel
+            cf.update_from_features(feat, t_pred, start_mean=False, labels_full=kept)                      # :327-334
+            cf.update_from_features(s_feat, s_pred, start_mean=False, labels_full=sl)                      # :336-341
+        else:
+            cf.update_from_features(feat, t_pred, _labels_on_feature_grid(kept, (h, w)), start_mean=False)
+            cf.update_from_features(s_feat, s_pred, _labels_on_feature_grid(sl, (h, w)), start_mean=False)
         stu = stu_cat.detach().requires_grad_(True)
         cpm = cross_low.detach().requires_grad_(True)
         if fused:      # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each

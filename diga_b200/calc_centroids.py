@@ -73,19 +73,26 @@ class Class_Features:
         return int(self._objective_vectors.shape[1])
 
     # -- a6 -------------------------------------------------------------------------------------
-    def _masked_means(self, feat_cls, outputs, labels_val):
-        """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C])."""
-        L.require_cuda(feat_cls, outputs, labels_val, what="Class_Features input")
+    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None):
+        """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
+        ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy."""
+        L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
         feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
         n, d, h, w = feat.shape
         c = self.class_numbers
         if out.shape != (n, c, h, w):
             raise ValueError(f"outputs must be [{n},{c},{h},{w}], got {tuple(out.shape)}")
-        lab = None
+        if labels_val is not None and labels_full is not None:
+            raise ValueError("pass either labels_val (down-sampled fp32) or labels_full (int64), not both")
+        lab = full = None
         if labels_val is not None:
             lab = L.f32c(labels_val.detach())
             if lab.shape != (n, 1, h, w):
                 raise ValueError(f"labels_val must be [{n},1,{h},{w}], got {tuple(lab.shape)}")
+        if labels_full is not None:
+            full = L.i64c(labels_full)
+            if full.dim() != 3 or full.shape[0] != n:
+                raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
         dev, hw, st = feat.device, h * w, L.stream()
         cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
         counts = torch.empty((n, c), dtype=torch.int32, device=dev)
@@ -93,7 +100,11 @@ class Class_Features:
         vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
         vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
         valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
-        L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(), st))
+        if full is not None:
+            L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
+                                                       cls.data_ptr(), counts.data_ptr(), st))
+        else:
+            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(), st))
         L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, c, hw, sums.data_ptr(), st))
         L.check(L.lib.diga_centroid_means(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, vec.data_ptr(),
                                           vecsum.data_ptr(), valid.data_ptr(), st))
@@ -137,11 +148,11 @@ class Class_Features:
                                                   self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
                                                   float(self.centroid_momentum), L.stream()))
 
-    def update_from_features(self, feat_cls, outputs, labels_val=None, name='moving_average', start_mean=True):
+    def update_from_features(self, feat_cls, outputs, labels_val=None, name='moving_average', start_mean=True, labels_full=None):
         """Fused a6 -> a7 (not in the reference): equals ``calculate_mean_vector`` followed by
         ``update_objective_SingleVector`` on every returned vector in order, with no host sync."""
         mode = self._mode(name)
-        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val)
+        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val, labels_full)
         n, c, d = vec.shape
         if d != self.feat_dim:
             raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")

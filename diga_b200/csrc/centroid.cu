@@ -28,7 +28,8 @@ int tunable(const char* name, int dflt);
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int nclass, int64_t hw,
-                       uint8_t* __restrict__ cls, int32_t* __restrict__ counts) {
+                       uint8_t* __restrict__ cls, int32_t* __restrict__ counts, const int64_t* __restrict__ labels_full = nullptr,
+                       int w = 0, int HH = 0, int WW = 0, float sy = 0.f, float sx = 0.f) {
   __shared__ int hist[DIGA_MAX_CLASSES];
   if (threadIdx.x < DIGA_MAX_CLASSES) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -48,7 +49,16 @@ centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict
         }
       }
       c = am;
-      if (labels != nullptr) {
+      if (labels_full != nullptr) {
+        // the reference's label down-sampling folded in (self_training.py:327-330, :336-337: .float() + F.interpolate(
+        // mode='nearest') of the [B,H,W] int64 map): ATen's nearest rule src = min((int)floorf(dst * scale), in - 1) with
+        // scale = (float)in / out, then the same gate as below on the fp32-rounded label value.
+        const int y = (int)(p / w), x = (int)(p - (int64_t)y * w);
+        const int Y = min((int)floorf((float)y * sy), HH - 1), X = min((int)floorf((float)x * sx), WW - 1);
+        const float lf = (float)__ldg(labels_full + ((int64_t)img * HH + Y) * WW + X);
+        const bool in_range = lf < (float)nclass;
+        if (!(in_range && (long long)lf == (long long)am)) c = 255;
+      } else if (labels != nullptr) {
         // process_label(labels) * process_label(argmax): the pixel counts for class t iff
         // long(label) == t == argmax, t < C (utils.py:161-162, calc_centroids.py:126-127).
         const float lf = __ldg(labels + img * hw + p);
@@ -591,6 +601,31 @@ int diga_centroid_assign(const float* logits, const float* labels, int64_t n, in
   const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
   if (gx > cap) gx = cap;
   centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(logits, labels, (int)C, hw, cls, counts);
+  DIGA_CHECK_LAUNCH("centroid_assign_kernel");
+  return DIGA_OK;
+}
+
+int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full, int64_t n, int64_t C, int64_t h, int64_t w,
+                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(logits && labels_full && cls && counts, DIGA_ERR_INVALID, "centroid_assign_fullres: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "centroid_assign_fullres: C=%lld outside [1,%d]", (long long)C,
+               DIGA_MAX_CLASSES);
+  DIGA_REQUIRE(n >= 0 && n <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && h < (1 << 24) && w < (1 << 24) && H < (1 << 24) &&
+                   W < (1 << 24),
+               DIGA_ERR_INVALID, "centroid_assign_fullres: bad sizes");
+  DIGA_REQUIRE(aligned(logits, 4) && aligned(labels_full, 8) && aligned(counts, 4), DIGA_ERR_MISALIGNED,
+               "centroid_assign_fullres: misaligned pointer");
+  if (n == 0) return DIGA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t hw = h * w;
+  cudaMemsetAsync(counts, 0, (size_t)n * C * sizeof(int32_t), st);
+  constexpr int BLOCK = 256;
+  int64_t gx = (hw + BLOCK - 1) / BLOCK;
+  const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(
+      logits, nullptr, (int)C, hw, cls, counts, labels_full, (int)w, (int)H, (int)W, (float)H / (float)h, (float)W / (float)w);
   DIGA_CHECK_LAUNCH("centroid_assign_kernel");
   return DIGA_OK;
 }

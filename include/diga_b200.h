@@ -107,6 +107,11 @@ int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const fl
  * ------------------------------------------------------------------------------------------ */
 int diga_centroid_assign(const float* logits, const float* labels, int64_t n, int64_t C, int64_t hw,
                          uint8_t* cls, int32_t* counts, diga_stream_t stream);
+/* assign with the reference's label down-sampling folded in (self_training.py:327-330, :336-337): labels_full is the
+ * [n,H,W] int64 map; pixel (y,x) of the h x w feature grid is gated by labels_full[min(floor(y*H/h), H-1)][min(floor(x*W/w), W-1)]
+ * (F.interpolate(mode='nearest') of the .float() map), same gate as diga_centroid_assign. */
+int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full, int64_t n, int64_t C, int64_t h, int64_t w,
+                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, diga_stream_t stream);
 /* process_label (util/utils.py:158-163): label [B,1,hw] fp32 -> onehot [B,C+1,hw] fp32, ids >= C in channel C.
  * Negative labels are outside the reference's domain (scatter_ would raise) and give an all-zero column. */
 int diga_onehot_labels(const float* label, int64_t B, int64_t C, int64_t hw, float* onehot, diga_stream_t stream);

@@ -189,8 +189,8 @@ def test_self_training_step_fused_call_sites():
         kept, fp = D.consensus_select(to(pseudo), weights, (hh, ww))
         _, out["mix1"] = D.classmix(to(slabel), to(rec), to(saug), rng=random, present=pres)
         _, out["mix2"], out["mixlabel"] = D.classmix(to(slabel), to(tdata_aug), to(sdata), kept, rng=random, present=pres)
-        cf.update_from_features(to(t_feat), to(t_pred), _labels_on_feature_grid(kept, (h, w)), start_mean=False)
-        cf.update_from_features(to(s_feat), to(s_pred), _labels_on_feature_grid(to(slabel), (h, w)), start_mean=False)
+        cf.update_from_features(to(t_feat), to(t_pred), start_mean=False, labels_full=kept)
+        cf.update_from_features(to(s_feat), to(s_pred), start_mean=False, labels_full=to(slabel))
         stu, cpm = to(stu_low).clone().requires_grad_(True), to(cross_low).clone().requires_grad_(True)
         part, _, _ = D.seg_distillation_total_upsampled(to(tea_low), stu, to(slabel), lam_seg, lam_kd, 0.5)
         total = part + lam_seg * D.cross_entropy2d_upsampled(cpm, out["mixlabel"])

@@ -417,6 +417,31 @@ def test_centroid_accum_variants_and_determinism(D):
     assert_normwise(ref.double() * cnt, want, what="class sums")
 
 
+@pytest.mark.parametrize("hi,lo", [((512, 1024), (65, 129)), ((512, 896), (65, 113)), ((64, 96), (8, 12)), ((37, 53), (37, 53))])
+def test_update_from_full_resolution_labels(D, hi, lo):
+    """labels_full= (the [B,H,W] int64 map, nearest down-sampling folded into the assign kernel) == the reference's
+    .float() + F.interpolate(mode='nearest') (self_training.py:327-330) followed by labels_val=, bit for bit."""
+    from diga_b200 import synthetic as S
+    from diga_b200.calc_centroids import _labels_on_feature_grid
+    g = S.gen(15, "cuda")
+    n, c, d = 3, 19, 64
+    feat, out = S.features((n, d, *lo), g), S.logits((n, c, *lo), g)
+    out[:, :5] += 3
+    lab = S.block_labels(n, hi[0], hi[1], g, 16)
+    cen = S.centroids(c, d, g)
+    a, b = D.Class_Features(c, d), D.Class_Features(c, d)
+    for cf in (a, b):
+        cf.objective_vectors = cen.clone()
+        cf.objective_vectors_num = torch.full((c,), 150.0)
+    a.update_from_features(feat, out, _labels_on_feature_grid(lab, lo), start_mean=False)
+    b.update_from_features(feat, out, start_mean=False, labels_full=lab)
+    assert torch.equal(a.objective_vectors, b.objective_vectors) and torch.equal(a.objective_vectors_num, b.objective_vectors_num)
+    if lo[0] * lo[1] > 1000:
+        assert not torch.equal(a.objective_vectors, cen)                  # some class did reach 5 agreeing pixels
+    with pytest.raises(ValueError):
+        b.update_from_features(feat, out, _labels_on_feature_grid(lab, lo), labels_full=lab)
+
+
 # ------------------------------------------------------------------------------------------------ a5 distance
 @pytest.mark.parametrize("name", ["proto_d256", "proto_d64"])
 def test_proto_golden(D, golden, name):

@@ -54,8 +54,12 @@ def st_step(x, fused):
         wts = cf.get_centroid_weight(feat)
         kept, _ = D.consensus_select(tl, wts, (hh, ww))
         _, mix2, mixlabel = D.classmix(sl, x["tdata_aug"], x["sdata"], kept, rng=rng)
-    cf.update_from_features(feat, x["t_pred"], _labels_on_feature_grid(kept, (h, w)), start_mean=False)       # :327-334
-    cf.update_from_features(x["s_feat"], x["s_pred"], _labels_on_feature_grid(sl, (h, w)), start_mean=False)  # :336-341
+    if fused:          # label down-sampling (.float() + F.interpolate(nearest), :328-330, :336-337) folded into the assign kernel
+        cf.update_from_features(feat, x["t_pred"], start_mean=False, labels_full=kept)                          # :327-334
+        cf.update_from_features(x["s_feat"], x["s_pred"], start_mean=False, labels_full=sl)                     # :336-341
+    else:
+        cf.update_from_features(feat, x["t_pred"], _labels_on_feature_grid(kept, (h, w)), start_mean=False)
+        cf.update_from_features(x["s_feat"], x["s_pred"], _labels_on_feature_grid(sl, (h, w)), start_mean=False)
     stu = x["stu_cat"].detach().requires_grad_(True)
     cpm = x["cross_low"].detach().requires_grad_(True)
     if fused:          # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each
