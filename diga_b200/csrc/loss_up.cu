@@ -257,6 +257,10 @@ loss_up_kernel(const LossUpArgs a) {
     // Per-pixel statistics in the log2 domain, relative to the cell reference (see LerpColumn):
     //   es_c = 2^v_c, Ss = sum es_c, (KD) e_c = 2^u_c, St = sum e_c, cross2 = sum e_c v_c.
     // Sums run as four interleaved chains.  EXACT re-bases on the per-pixel max (taken only after an underflow).
+    // In the seg + KD kernels only the first n_ce images carry targets: the per-class target compares / selects (76
+    // instructions per pixel) are compiled out of the body the other images run (`ce_img` is CTA-uniform).
+    auto pixel = [&](auto ce_tag) {
+    constexpr bool CEP = CE && decltype(ce_tag)::value;
     float es[GRAD ? C : 1], et[(GRAD && KD) ? C : 1];
     float Ss = 0.f, St = 0.f, cross2 = 0.f, dtgt = 0.f;
     auto stats = [&](auto exact_tag) {
@@ -288,7 +292,7 @@ loss_up_kernel(const LossUpArgs a) {
             cr4[c & 3] = fmaf(e_t, v, cr4[c & 3]);
             if constexpr (GRAD) et[c] = e_t;
           }
-          if constexpr (CE) {
+          if constexpr (CEP) {
             if (t32 == c) dtgt = v;
           }
           if constexpr (GRAD) es[c] = e_s;
@@ -306,7 +310,7 @@ loss_up_kernel(const LossUpArgs a) {
     if constexpr (KD) inv_t = fast_rcp(St);
     float wt = 1.f;
     bool counted = false, valid = false;
-    if constexpr (CE) {
+    if constexpr (CEP) {
       counted = ce_img && in_range && tgt >= 0;                     // loss.py:56  mask = target >= 0
       valid = counted && tgt < nclass && tgt != a.ignore_label;     // 255 (any id >= C) is ignored by nll_loss
       if (ohem && valid) {                                          // OhemCrossEntropy keeps the hard pixels only
@@ -320,13 +324,13 @@ loss_up_kernel(const LossUpArgs a) {
       if constexpr (KD) {
         if (in_range) acc_kd += wkd * (lse2 - cross2 * inv_t);
       }
-      if constexpr (CE) {
+      if constexpr (CEP) {
         if (valid) acc_ce += wt * (lse2 - dtgt);
         if (counted) acc_cnt += 1.f;
       }
     }
     if constexpr (GRAD) {
-      const float cpx = (CE && valid) ? wt * cce : 0.f;
+      const float cpx = (CEP && valid) ? wt * cce : 0.f;
       const float ga = (ckd + cpx) * fast_rcp(Ss);
       const float gb = ckd * inv_t;
 #pragma unroll
@@ -334,10 +338,17 @@ loss_up_kernel(const LossUpArgs a) {
         if (!PAD || c < nclass) {
           float g = ga * es[c];
           if constexpr (KD) g = fmaf(-gb, et[c], g);
-          if constexpr (CE) g -= (t32 == c) ? cpx : 0.f;
+          if constexpr (CEP) g -= (t32 == c) ? cpx : 0.f;
           Gt[c] = fmaf(yl0, g, Gt[c]);
           Gb[c] = fmaf(yl1, g, Gb[c]);
         }
+    }
+    };
+    if constexpr (CE && KD) {
+      if (ce_img) pixel(std::true_type{});
+      else pixel(std::false_type{});
+    } else {
+      pixel(std::integral_constant<bool, CE>{});
     }
     tgt = tgt_next;
   }
