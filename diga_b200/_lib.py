@@ -52,6 +52,7 @@ SIGNATURES = {
     "diga_proto_prepare": (_i, [_p, _i64, _i64, _p, _p]),
     "diga_proto_distance_prepared": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_consensus_select": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "diga_consensus_select_u8": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "diga_upsample_bilinear": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "diga_pseudo_label_upsampled": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_ce_workspace_bytes": (C.c_size_t, []),

@@ -34,10 +34,35 @@ upsample_bilinear_kernel(const float* __restrict__ in, int64_t planes, int h, in
 // One thread = PX adjacent output pixels x RY consecutive output rows (ColumnInterp keeps the horizontally
 // interpolated source rows of all classes in registers while it walks down).  A warp covers 32*PX adjacent
 // pixels of a row, so the int64 accesses are 128-bit and fully coalesced.  torch.max(dim=1): first index on ties.
-template <int C, bool PAD, int PX, int BLOCK>
+// Label I/O of PX adjacent pixels: int64 (the training step's LongTensors; 128-bit accesses for PX = 2) or uint8 (the
+// offline pseudo-label path, where the maps come from and go to palette PNGs).
+template <typename T, int PX>
+__device__ __forceinline__ void load_px(const T* __restrict__ p, int64_t (&dst)[PX]) {
+  if constexpr (sizeof(T) == 8 && PX == 2) {
+    const longlong2 t = ld_stream_i64x2(reinterpret_cast<const int64_t*>(p));
+    dst[0] = t.x;
+    dst[1] = t.y;
+  } else {
+#pragma unroll
+    for (int v = 0; v < PX; ++v) dst[v] = (int64_t)p[v];
+  }
+}
+template <typename T, int PX>
+__device__ __forceinline__ void store_px(T* __restrict__ p, const int64_t (&src)[PX]) {
+  if constexpr (sizeof(T) == 8 && PX == 2) {
+    st_stream_i64x2(reinterpret_cast<int64_t*>(p), src[0], src[1]);
+  } else if constexpr (sizeof(T) == 1 && PX == 2) {
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)((uint8_t)src[0] | ((uint16_t)(uint8_t)src[1] << 8));
+  } else {
+#pragma unroll
+    for (int v = 0; v < PX; ++v) p[v] = (T)src[v];
+  }
+}
+
+template <int C, bool PAD, int PX, int BLOCK, typename T>
 __global__ void __launch_bounds__(BLOCK)
-consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict__ pseudo, int nclass, int h, int w, int H,
-                        int W, float sh, float sw, int RY, int64_t* __restrict__ kept, int64_t* __restrict__ feat_pseudo) {
+consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseudo, int nclass, int h, int w, int H,
+                        int W, float sh, float sw, int RY, T* __restrict__ kept, T* __restrict__ feat_pseudo) {
   const int64_t img = blockIdx.z;
   const int Y0 = blockIdx.y * RY;
   const int X0 = (blockIdx.x * BLOCK + threadIdx.x) * PX;
@@ -51,16 +76,7 @@ consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict_
   const int Yend = min(Y0 + RY, H);
   // software prefetch of the label loads: one row ahead
   int64_t lab[PX], nxt[PX];
-  auto load_labels = [&](int64_t (&dst)[PX], int Y) {
-    const int64_t o = (img * H + Y) * W + X0;
-    if constexpr (PX == 2) {
-      const longlong2 t = ld_stream_i64x2(pseudo + o);
-      dst[0] = t.x;
-      dst[1] = t.y;
-    } else {
-      dst[0] = ld_stream_i64(pseudo + o);
-    }
-  };
+  auto load_labels = [&](int64_t (&dst)[PX], int Y) { load_px<T, PX>(pseudo + (img * H + Y) * W + X0, dst); };
   load_labels(lab, Y0);
   for (int Y = Y0; Y < Yend; ++Y) {
     if (Y + 1 < Yend) load_labels(nxt, Y + 1);
@@ -78,20 +94,55 @@ consensus_select_kernel(const float* __restrict__ wl, const int64_t* __restrict_
       am[v] = arg;
     }
     const int64_t o = (img * H + Y) * W + X0;
-    if constexpr (PX == 2) {
-      st_stream_i64x2(kept + o, lab[0] == am[0] ? lab[0] : (int64_t)DIGA_IGNORE_LABEL,           // :304
-                      lab[1] == am[1] ? lab[1] : (int64_t)DIGA_IGNORE_LABEL);
-      if (feat_pseudo) st_stream_i64x2(feat_pseudo + o, am[0], am[1]);
-    } else {
-      st_stream_i64(kept + o, lab[0] == am[0] ? lab[0] : (int64_t)DIGA_IGNORE_LABEL);
-      if (feat_pseudo) st_stream_i64(feat_pseudo + o, am[0]);
-    }
+    int64_t keep[PX];
+#pragma unroll
+    for (int v = 0; v < PX; ++v) keep[v] = lab[v] == am[v] ? lab[v] : (int64_t)DIGA_IGNORE_LABEL;                 // :304
+    store_px<T, PX>(kept + o, keep);
+    if (feat_pseudo) store_px<T, PX>(feat_pseudo + o, am);
 #pragma unroll
     for (int v = 0; v < PX; ++v) lab[v] = nxt[v];
   }
 }
 
 }  // namespace diga
+
+template <typename T>
+static int consensus_select_impl(const float* weights_lowres, const T* pseudo, int64_t B, int64_t C, int64_t h, int64_t w, int64_t H,
+                                 int64_t W, T* kept, T* feat_pseudo, cudaStream_t st) {
+  using namespace diga;
+  DIGA_REQUIRE(weights_lowres && pseudo && kept, DIGA_ERR_INVALID, "consensus_select: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "consensus_select: C=%lld outside [1,%d]", (long long)C,
+               DIGA_MAX_CLASSES);
+  DIGA_REQUIRE(B >= 0 && B <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && H <= 65535 && h < (1 << 24) && w < (1 << 24) &&
+                   W < (1 << 24),
+               DIGA_ERR_INVALID, "consensus_select: bad sizes");
+  DIGA_REQUIRE(aligned(weights_lowres, 4) && aligned(pseudo, sizeof(T)) && aligned(kept, sizeof(T)) && aligned(feat_pseudo, sizeof(T)),
+               DIGA_ERR_MISALIGNED, "consensus_select: misaligned pointer");
+  if (B == 0) return DIGA_OK;
+  const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
+  const bool pair = (W % 2) == 0 && aligned(pseudo, 2 * sizeof(T)) && aligned(kept, 2 * sizeof(T)) && aligned(feat_pseudo, 2 * sizeof(T));
+  // Launch shape (tools/tune.py select, profiles/r01_tune_select.jsonl): a thread walks RY output rows of PX adjacent
+  // columns.  Longer walks amortise the two source rows a strip interpolates first but leave too few warps (RY = 64:
+  // 48 us, 128: 80 us); two columns x 16 rows is the best of the sweep (35.7 us).  The kernel is ALU-bound: per pixel
+  // 19 x (bit-exact 2-op interpolation + 3-op arg-max) plus the strip set-up, 190 instructions at 67 % issue.
+  constexpr int BLOCK = 128;
+  const int RY = tunable("select_ry", 16) < 1 ? 1 : tunable("select_ry", 16);
+  const bool two = pair && tunable("select_px", 2) == 2;
+  const unsigned gy = (unsigned)((H + RY - 1) / RY);
+  DIGA_DISPATCH_C(C, {
+    if (two) {
+      dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), gy, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 2, BLOCK, T><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
+                                                                            (int)W, sh, sw, RY, kept, feat_pseudo);
+    } else {
+      dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), gy, (unsigned)B);
+      consensus_select_kernel<kC, kPad, 1, BLOCK, T><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
+                                                                            (int)W, sh, sw, RY, kept, feat_pseudo);
+    }
+  });
+  DIGA_CHECK_LAUNCH("consensus_select_kernel");
+  return DIGA_OK;
+}
 
 extern "C" {
 
@@ -115,40 +166,12 @@ int diga_upsample_bilinear(const float* in, int64_t planes, int64_t h, int64_t w
 
 int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, int64_t B, int64_t C, int64_t h, int64_t w,
                           int64_t H, int64_t W, int64_t* kept, int64_t* feat_pseudo, diga_stream_t stream) {
-  using namespace diga;
-  DIGA_REQUIRE(weights_lowres && pseudo && kept, DIGA_ERR_INVALID, "consensus_select: null pointer");
-  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "consensus_select: C=%lld outside [1,%d]", (long long)C,
-               DIGA_MAX_CLASSES);
-  DIGA_REQUIRE(B >= 0 && B <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && H <= 65535 && h < (1 << 24) && w < (1 << 24) &&
-                   W < (1 << 24),
-               DIGA_ERR_INVALID, "consensus_select: bad sizes");
-  DIGA_REQUIRE(aligned(weights_lowres, 4) && aligned(pseudo, 8) && aligned(kept, 8) && aligned(feat_pseudo, 8),
-               DIGA_ERR_MISALIGNED, "consensus_select: misaligned pointer");
-  if (B == 0) return DIGA_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
-  const bool pair = (W % 2) == 0 && aligned(pseudo, 16) && aligned(kept, 16) && aligned(feat_pseudo, 16);
-  // Launch shape (tools/tune.py select, profiles/r01_tune_select.jsonl): a thread walks RY output rows of PX adjacent
-  // columns.  Longer walks amortise the two source rows a strip interpolates first but leave too few warps (RY = 64:
-  // 48 us, 128: 80 us); two columns x 16 rows is the best of the sweep (35.7 us).  The kernel is ALU-bound: per pixel
-  // 19 x (bit-exact 2-op interpolation + 3-op arg-max) plus the strip set-up, 190 instructions at 67 % issue.
-  constexpr int BLOCK = 128;
-  const int RY = tunable("select_ry", 16) < 1 ? 1 : tunable("select_ry", 16);
-  const bool two = pair && tunable("select_px", 2) == 2;
-  const unsigned gy = (unsigned)((H + RY - 1) / RY);
-  DIGA_DISPATCH_C(C, {
-    if (two) {
-      dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), gy, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 2, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
-                                                                         (int)W, sh, sw, RY, kept, feat_pseudo);
-    } else {
-      dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), gy, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 1, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
-                                                                         (int)W, sh, sw, RY, kept, feat_pseudo);
-    }
-  });
-  DIGA_CHECK_LAUNCH("consensus_select_kernel");
-  return DIGA_OK;
+  return consensus_select_impl<int64_t>(weights_lowres, pseudo, B, C, h, w, H, W, kept, feat_pseudo, (cudaStream_t)stream);
+}
+
+int diga_consensus_select_u8(const float* weights_lowres, const uint8_t* pseudo, int64_t B, int64_t C, int64_t h, int64_t w,
+                             int64_t H, int64_t W, uint8_t* kept, uint8_t* feat_pseudo, diga_stream_t stream) {
+  return consensus_select_impl<uint8_t>(weights_lowres, pseudo, B, C, h, w, H, W, kept, feat_pseudo, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -12,11 +12,13 @@ from . import _lib as L
 
 def consensus_select(pseudo_prob, feat_weights_lowres, out_size=None, want_feat_pseudo=True):
     """``pseudo_prob [B,H,W]`` int64 stored pseudo-labels, ``feat_weights_lowres [B,C,h,w]`` fp32 prototype weights
-    (``Class_Features.get_centroid_weight``).  Returns ``(tlabelv_pseudo, feat_pseudo)``, both int64 ``[B,H,W]``:
+    (``Class_Features.get_centroid_weight``).  Returns ``(tlabelv_pseudo, feat_pseudo)``, both ``[B,H,W]`` in the dtype of ``pseudo_prob`` (int64, or uint8 for the offline
+    pseudo-label path):
     the kept labels (255 where the two views disagree) and the arg-max of the bilinearly up-sampled weights.
     The up-sampled ``[B,C,H,W]`` tensor is never materialised."""
     L.require_cuda(pseudo_prob, feat_weights_lowres, what="consensus_select input")
-    pp = L.i64c(pseudo_prob)
+    u8 = pseudo_prob.dtype == torch.uint8          # offline path: uint8 label maps in, uint8 out (no int64 round trip)
+    pp = pseudo_prob.contiguous() if u8 else L.i64c(pseudo_prob)
     wl = L.f32c(feat_weights_lowres.detach())
     b, hh, ww = pp.shape
     if out_size is not None and (int(out_size[0]), int(out_size[1])) != (hh, ww):
@@ -26,8 +28,8 @@ def consensus_select(pseudo_prob, feat_weights_lowres, out_size=None, want_feat_
     _, c, h, w = wl.shape
     kept = torch.empty_like(pp)
     fp = torch.empty_like(pp) if want_feat_pseudo else None
-    L.check(L.lib.diga_consensus_select(wl.data_ptr(), pp.data_ptr(), b, c, h, w, hh, ww, kept.data_ptr(), L.ptr(fp),
-                                        L.stream()))
+    fn = L.lib.diga_consensus_select_u8 if u8 else L.lib.diga_consensus_select
+    L.check(fn(wl.data_ptr(), pp.data_ptr(), b, c, h, w, hh, ww, kept.data_ptr(), L.ptr(fp), L.stream()))
     return kept, fp
 
 

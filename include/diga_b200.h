@@ -165,6 +165,11 @@ int diga_consensus_select(const float* weights_lowres, const int64_t* pseudo, in
                           int64_t h, int64_t w, int64_t H, int64_t W, int64_t* kept, int64_t* feat_pseudo,
                           diga_stream_t stream);
 
+/* Same on uint8 label maps (the offline pseudo-label path: labels come from diga_pseudo_label* as uint8 and go to palette
+ * PNGs): 1 B/px read, 1-2 B/px written instead of 8 + 8-16. */
+int diga_consensus_select_u8(const float* weights_lowres, const uint8_t* pseudo, int64_t B, int64_t C, int64_t h, int64_t w,
+                             int64_t H, int64_t W, uint8_t* kept, uint8_t* feat_pseudo, diga_stream_t stream);
+
 /* The interpolation routine shared by a4 and the fused a3 variant, materialising:
  * out[planes,H,W] = bilinear(align_corners=True) of in[planes,h,w], bit-identical to torch's CUDA kernel. */
 int diga_upsample_bilinear(const float* in, int64_t planes, int64_t h, int64_t w, int64_t H, int64_t W, float* out,

@@ -510,6 +510,21 @@ def test_consensus_vs_gpu_eager(D):
         assert none is None and torch.equal(kept2, kept)
 
 
+def test_consensus_select_uint8_equals_int64(D):
+    """The uint8 variant (offline pseudo-label path) returns the same labels as the int64 kernel, incl. odd widths."""
+    from diga_b200 import synthetic as S
+    g = S.gen(23, "cuda")
+    for b, c, lo, hi in ((2, 19, (65, 129), (512, 1024)), (1, 16, (9, 13), (37, 53)), (1, 19, (129, 257), (1024, 2048))):
+        wl = torch.softmax(S.logits((b, c, *lo), g), 1)
+        pl = S.block_labels(b, hi[0], hi[1], g, 16, c)
+        k64, f64 = D.consensus_select(pl, wl)
+        k8, f8 = D.consensus_select(pl.to(torch.uint8), wl)
+        assert k8.dtype == torch.uint8 and f8.dtype == torch.uint8
+        assert torch.equal(k8.long(), k64) and torch.equal(f8.long(), f64)
+        k8b, none = D.consensus_select(pl.to(torch.uint8), wl, want_feat_pseudo=False)
+        assert none is None and torch.equal(k8b, k8)
+
+
 def test_consensus_golden(D, golden):
     """Golden from torch's CPU interpolation: only near-ties of the up-sampled weights may differ."""
     g = golden("consensus")

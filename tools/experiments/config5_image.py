@@ -9,5 +9,5 @@ l5a, l5b = S.logits((1, C, 129, 257), g), S.logits((1, C, 65, 129), g)
 for _ in range(4):
     lab, _ = D.pseudo_label_two_scale(l5a, l5b, (1024, 2048), want_conf=False)
     wts = cf.get_centroid_weight(f5)
-    kept = D.consensus_select(lab.long(), wts, want_feat_pseudo=False)
+    kept = D.consensus_select(lab, wts, want_feat_pseudo=False)
 torch.cuda.synchronize()
