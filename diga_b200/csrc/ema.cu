@@ -1,13 +1,15 @@
 // f4 — EMA teacher update as a multi-tensor kernel.
 // Replaces util/utils.py:103-116 of the reference (`update_teacher_params`): a Python loop over ~500 parameter tensors,
-// three tiny launches each.  Here up to 48 tensors share one launch (pointer table passed as a kernel argument).
+// three tiny launches each.  Here up to 512 tensors share one launch: the pointer table travels as a 14 KB kernel argument
+// (CUDA >= 12.1 accepts 32 KB of parameters), so a ResNet-101 teacher is ONE launch and a block finds its tensor by
+// binary search in the block-offset table.
 //   teacher = alpha * teacher + (1 - alpha) * student      (separately rounded mul, mul, add — bit-exact with torch)
 // Traffic: 12 B per parameter element.
 #include "common.cuh"
 
 namespace diga {
 
-constexpr int kEmaTensorsPerLaunch = 48;
+constexpr int kEmaTensorsPerLaunch = 512;
 constexpr int kEmaBlock = 256;
 constexpr int kEmaElemsPerBlock = kEmaBlock * 4 * 4;   // 4 float4 per thread
 
@@ -23,8 +25,12 @@ __device__ __forceinline__ float ema1(float t, float s, float a, float oma) { re
 
 __global__ void __launch_bounds__(kEmaBlock)
 ema_update_kernel(const __grid_constant__ EmaTable tab, float alpha, float one_minus_alpha) {
-  int i = 0;
-  while (i + 1 < tab.count && (int)blockIdx.x >= tab.block_start[i + 1]) ++i;
+  int i = 0, hi = tab.count - 1;                           // largest i with block_start[i] <= blockIdx.x
+  while (i < hi) {
+    const int mid = (i + hi + 1) >> 1;
+    if ((int)blockIdx.x >= tab.block_start[mid]) i = mid;
+    else hi = mid - 1;
+  }
   float* __restrict__ t = tab.teacher[i];
   const float* __restrict__ s = tab.student[i];
   const int64_t n = tab.numel[i];

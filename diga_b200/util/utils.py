@@ -23,7 +23,7 @@ def process_label(label, class_numbers=19):
 
 
 def ema_update_tensors(teacher_tensors, student_tensors, alpha):
-    """``t = alpha * t + (1 - alpha) * s`` for every pair, in place, 48 tensors per kernel launch."""
+    """``t = alpha * t + (1 - alpha) * s`` for every pair, in place, up to 512 tensors per kernel launch."""
     ts, ss = list(teacher_tensors), list(student_tensors)
     if len(ts) != len(ss):
         raise ValueError("ema_update_tensors: teacher and student lists differ in length")
@@ -42,7 +42,7 @@ def ema_update_tensors(teacher_tensors, student_tensors, alpha):
 
 def update_teacher_params(teacher, student, iteration, stage0=True, mean=False, replace=False):
     """``util.utils.update_teacher_params`` (G/util/utils.py:103-116): EMA of the student's parameters into the teacher
-    with ``alpha = min(1 - 1/(iteration+1), 0.999)`` in stage 0, one multi-tensor launch per 48 parameters instead of
+    with ``alpha = min(1 - 1/(iteration+1), 0.999)`` in stage 0, one multi-tensor launch per 512 parameters instead of
     three launches per parameter.  Returns the teacher like the reference (``teacher.cuda()``)."""
     if stage0 == True:          # noqa: E712  (mirrors the reference's flag tests)
         alpha_teacher = min(1 - 1 / (iteration + 1), 0.999)

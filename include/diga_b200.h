@@ -260,7 +260,7 @@ int diga_ohem_up_bwd(const float* logits_low, const int64_t* target, const float
  * f4 (next row)  EMA teacher update — util/utils.py:103-116
  *   For each of `count` parameter tensors: teacher = alpha * teacher + (1 - alpha) * student (fp32, in place,
  *   separately rounded like the torch expression).  The three tables live in HOST memory (device pointers and
- *   element counts) and are consumed before the call returns; 48 tensors per launch.
+ *   element counts) and are consumed before the call returns; 512 tensors per launch.
  * ------------------------------------------------------------------------------------------ */
 int diga_ema_update(float* const* teacher_host, const float* const* student_host, const int64_t* numel_host,
                     int64_t count, double alpha, diga_stream_t stream);

@@ -589,9 +589,9 @@ def test_ema_teacher_update_golden_bit_exact(D, golden):
 
 
 def test_ema_many_tensors_vs_oracle(D):
-    """More tensors than fit one launch (48), odd sizes, unaligned tails."""
+    """More tensors than fit one launch (512), odd sizes, unaligned tails."""
     g = torch.Generator().manual_seed(3)
-    sizes = [1, 3, 4, 5, 63, 64, 65, 1000, 4097, 300000] * 11            # 110 tensors
+    sizes = [1, 3, 4, 5, 63, 64, 65, 1000, 4097, 300000] * 11 + [7, 129, 2048, 4096, 4100] * 90     # 560 tensors
     ts = [torch.randn(n, generator=g) for n in sizes]
     ss = [torch.randn(n, generator=g) for n in sizes]
     alpha = min(1 - 1 / (123 + 1), 0.999)
