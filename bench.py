@@ -718,6 +718,45 @@ def main():
                                     "for the backbone backward; PCIe-bound"}
         del host_t, host_s, bufs
 
+        # Same loss through the patched call site of INTEGRATION.md (distillation_loss_upsampled on the stride-8 logits the
+        # backbone emits, before nn.Upsample): host logits [8,19,65,129] in, loss AND the low-resolution gradient out.
+        # Secondary figure: the headline e2e above stays the unchanged-signature call.
+        lo_shape = (KD_SHAPE[0], KD_SHAPE[1], 65, 129)
+        g2 = S.gen(4321 + rank)
+        h_lt, h_ls = S.logits(lo_shape, g2).pin_memory(), S.logits(lo_shape, g2).pin_memory()
+        h_grad = torch.empty(lo_shape, dtype=torch.float32).pin_memory()
+        ke2 = 200
+        h_loss2 = torch.empty((ke2,), dtype=torch.float32).pin_memory()
+        d_lt, d_ls = torch.empty(lo_shape, device=dev), torch.empty(lo_shape, device=dev)
+
+        def e2e_low(nsteps):
+            for i in range(nsteps):
+                d_lt.copy_(h_lt, non_blocking=True)
+                d_ls.copy_(h_ls, non_blocking=True)
+                x = d_ls.detach().requires_grad_(True)
+                loss = D.distillation_loss_upsampled(d_lt, x, KD_SHAPE[2:], 0.5)
+                (gr,) = torch.autograd.grad(loss, x, grad_outputs=up)
+                h_loss2[i].copy_(loss.detach(), non_blocking=True)
+                h_grad.copy_(gr, non_blocking=True)
+
+        e2e_low(5)
+        torch.cuda.synchronize()
+        barrier(world)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        e2e_low(ke2)
+        b1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        low_ms = max_over_ranks(b0.elapsed_time(b1), world, dev) / ke2
+        e2e["patched_call_site"] = {
+            "value": world * px_step / (low_ms * 1e-3), "unit": "pixel-positions/s", "ms_per_step": low_ms, "steps": ke2,
+            "h2d_bytes_per_step": 2 * h_lt.numel() * 4, "d2h_bytes_per_step": 4 + h_grad.numel() * 4,
+            "note": "distillation_loss_upsampled + autograd.grad on pinned host logits [8,19,65,129] (the tensors before "
+                    "nn.Upsample, self_training.py:344,351): H2D of both maps, D2H of the loss and of the gradient, one stream, "
+                    "eager; includes the up-sampling the reference arm does not time"}
+        del h_lt, h_ls, h_grad, d_lt, d_ls
+
     stages = None
     if not args.no_stages:
         del sets
