@@ -70,6 +70,9 @@ SIGNATURES = {
     "diga_ema_update": (_i, [_p, _p, _p, _i64, _d, _p]),
     "diga_label_resize_remap": (_i, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _p, _p]),
     "diga_confusion_matrix": (_i, [_p, _i, _p, _i, _i64, _i64, _p, _p, _p]),
+    "diga_png_deflate_capacity": (_i64, [_i64, _i64]),
+    "diga_png_deflate_scratch_bytes": (_i64, [_i64, _i64]),
+    "diga_png_deflate": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

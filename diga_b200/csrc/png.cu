@@ -1,0 +1,337 @@
+// f3, writer half — the zlib stream of a pseudo-label PNG, produced on the GPU.
+// Replaces the host-side `Image.save` of pseudolabel_generator.py:45-49,100-105 (PIL + zlib, 17-43 ms per 2048x1024 map
+// on one host core — two orders of magnitude more than every GPU kernel of config 5 together).  The label map stays
+// in HBM; what crosses PCIe is the finished IDAT payload (10-60 KB instead of 2 MB) and the host only frames it
+// (signature, IHDR, PLTE, IDAT + CRC, IEND).  Decoded pixels, mode ('P') and palette equal the reference's files; the
+// bytes differ (as they do between zlib versions).
+//
+// Stream layout (RFC 1950 / 1951 / PNG 1.2):
+//   zlib header 78 01 | ONE fixed-Huffman deflate block (BFINAL=1, BTYPE=01) | pad to byte | Adler-32 (big endian)
+//   scanline y = filter byte 2 (Up) followed by label[y][x] - label[y-1][x] (mod 256; row -1 is zero).
+// A segmentation map filtered that way is zero except along horizontal class edges, so the encoder only needs runs:
+// every run of equal bytes becomes   literal(v)   then   match(len <= 258, distance 1)   tokens.
+//
+// Three launches per batch, no host sync:
+//   rows<false> : one warp per scanline — filter into shared memory, find the run starts (lane-segment scan + warp prefix
+//                 sum into a shared list), one lane per run computes its token bits  -> row bit count, Adler partials
+//   layout      : one CTA per image — exclusive scan of the row bit counts, Adler-32 combine, zero the output span,
+//                 zlib header, trailer, byte length
+//   rows<true>  : same walk, tokens OR-ed into the bit stream at their global bit offset (atomicOr on 32-bit words)
+#include "common.cuh"
+
+namespace diga {
+
+struct PngRowStat {
+  uint32_t bits;      // token bits of the scanline
+  uint32_t sum;       // sum of its filtered bytes
+  uint64_t wsum_off;  // rows<false>: sum of i * byte[i];  after layout: bit offset of the scanline's first token
+};
+
+__constant__ uint16_t kLenBase[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
+                                      31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+
+__device__ __forceinline__ uint32_t rev_bits(uint32_t x, int n) { return __brev(x) >> (32 - n); }
+
+// fixed Huffman literal: 0..143 -> 8 bits 00110000+v, 144..255 -> 9 bits 110010000+(v-144); codes go MSB first
+__device__ __forceinline__ int lit_bits(uint32_t v) { return v < 144 ? 8 : 9; }
+__device__ __forceinline__ uint32_t lit_pattern(uint32_t v) { return v < 144 ? rev_bits(0x30 + v, 8) : rev_bits(0x190 + (v - 144), 9); }
+
+// match of `len` (3..258) at distance 1: length code + extra bits (LSB first) + 5-bit distance code 0
+__device__ __forceinline__ int match_code(int len) {
+  int lo = 0, hi = 28;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)kLenBase[mid] <= len) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int match_bits_of(int idx) { return (idx < 23 ? 7 : 8) + kLenExtra[idx] + 5; }
+__device__ __forceinline__ uint32_t match_pattern(int len, int idx) {
+  const int hb = idx < 23 ? 7 : 8;                                      // codes 257..279: 7 bits, 280..285: 8 bits
+  const uint32_t huff = idx < 23 ? rev_bits(1 + idx, 7) : rev_bits(0xC0 + (idx - 23), 8);
+  return huff | ((uint32_t)(len - kLenBase[idx]) << hb);
+}
+
+__device__ __forceinline__ void put_bits(uint32_t* out, uint64_t pos, uint32_t pattern, int nbits) {
+  const uint64_t word = pos >> 5;
+  const int sh = (int)(pos & 31);
+  const uint64_t p = (uint64_t)pattern << sh;
+  atomicOr(out + word, (uint32_t)p);
+  if (sh + nbits > 32) atomicOr(out + word + 1, (uint32_t)(p >> 32));
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) {
+  const int lane = threadIdx.x & 31;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+template <bool WRITE>
+__global__ void png_rows_kernel(const uint8_t* __restrict__ labels, int H, int W, PngRowStat* __restrict__ stats,
+                                uint8_t* __restrict__ out, int64_t capacity, int smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char png_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int y = blockIdx.x * warps + warp;
+  const int64_t img = blockIdx.y;
+  if (y >= H) return;
+  const int rowlen = W + 1;
+  uint8_t* f = png_smem + (size_t)warp * smem_per_warp;                            // filtered scanline
+  uint16_t* starts = reinterpret_cast<uint16_t*>(f + ((rowlen + 3) & ~3));          // run start positions
+  const uint8_t* cur = labels + (img * H + y) * (int64_t)W;
+  const uint8_t* prv = cur - W;
+
+  // ---- filter (Up) into shared memory, Adler partials --------------------------------------------------------
+  uint32_t s1 = 0;
+  uint64_t s2 = 0;
+  if (lane == 0) {
+    f[0] = 2;
+    s1 = 2;
+  }
+  if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(labels) & 3) == 0)) {
+    for (int x = lane * 4; x < W; x += 128) {
+      const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(cur + x));
+      const uint32_t b = y > 0 ? __ldg(reinterpret_cast<const uint32_t*>(prv + x)) : 0u;
+      const uint32_t d = __vsub4(a, b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t v = (d >> (8 * k)) & 0xffu;
+        f[1 + x + k] = (uint8_t)v;
+        s1 += v;
+        s2 += (uint64_t)(1 + x + k) * v;
+      }
+    }
+  } else {
+    for (int x = lane; x < W; x += 32) {
+      const uint32_t v = (uint32_t)(uint8_t)(__ldg(cur + x) - (y > 0 ? __ldg(prv + x) : (uint8_t)0));
+      f[1 + x] = (uint8_t)v;
+      s1 += v;
+      s2 += (uint64_t)(1 + x) * v;
+    }
+  }
+  __syncwarp();
+
+  // ---- run starts: every lane scans its own segment, a warp prefix sum places them in order -----------------------
+  const int seg = (rowlen + 31) >> 5;
+  const int a0 = lane * seg, a1 = min(a0 + seg, rowlen);
+  uint32_t mine = 0;
+  {
+    int pv = a0 > 0 && a0 < rowlen ? f[a0 - 1] : -1;
+    for (int i = a0; i < a1; ++i) {
+      const int v = f[i];
+      mine += (v != pv);
+      pv = v;
+    }
+  }
+  uint32_t nruns;
+  uint32_t at = warp_excl_scan(mine, nruns);
+  {
+    int pv = a0 > 0 && a0 < rowlen ? f[a0 - 1] : -1;
+    for (int i = a0; i < a1; ++i) {
+      const int v = f[i];
+      if (v != pv) starts[at++] = (uint16_t)i;
+      pv = v;
+    }
+  }
+  __syncwarp();
+
+  // ---- one lane per run: literal + distance-1 matches ------------------------------------------------------------
+  uint32_t* out32 = WRITE ? reinterpret_cast<uint32_t*>(out + img * capacity) : nullptr;
+  const uint64_t row_off = WRITE ? stats[img * H + y].wsum_off : 0;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nruns; base += 32) {
+    const uint32_t r = base + lane;
+    uint32_t bits = 0, v = 0;
+    int nfull = 0, rem = 0, ridx = 0;
+    if (r < nruns) {
+      const int s = starts[r], e = r + 1 < nruns ? (int)starts[r + 1] : rowlen;
+      v = f[s];
+      const int m = e - s - 1;                 // bytes after the literal
+      nfull = m / 258;
+      rem = m - nfull * 258;
+      const int lb = lit_bits(v);
+      bits = lb + nfull * 13;
+      if (rem >= 3) {
+        ridx = match_code(rem);
+        bits += match_bits_of(ridx);
+      } else {
+        bits += rem * lb;
+      }
+    }
+    uint32_t total;
+    const uint32_t excl = warp_excl_scan(bits, total);
+    if (WRITE && r < nruns) {
+      uint64_t pos = row_off + carry + excl;
+      const int lb = lit_bits(v);
+      const uint32_t lp = lit_pattern(v);
+      put_bits(out32, pos, lp, lb);
+      pos += lb;
+      for (int k = 0; k < nfull; ++k) {
+        put_bits(out32, pos, 0xA3u, 13);       // code 285 (len 258) = 11000101 reversed, no extra bits, distance code 0
+        pos += 13;
+      }
+      if (rem >= 3) {
+        put_bits(out32, pos, match_pattern(rem, ridx), match_bits_of(ridx));
+      } else {
+        for (int k = 0; k < rem; ++k) {
+          put_bits(out32, pos, lp, lb);
+          pos += lb;
+        }
+      }
+    }
+    carry += total;
+  }
+
+  if (!WRITE) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      PngRowStat st;
+      st.bits = carry;
+      st.sum = s1;
+      st.wsum_off = s2;
+      stats[img * H + y] = st;
+    }
+  }
+}
+
+constexpr uint32_t kAdlerMod = 65521u;
+constexpr int kLayoutBlock = 1024;
+
+__global__ void __launch_bounds__(kLayoutBlock)
+png_layout_kernel(PngRowStat* __restrict__ stats, int H, int W, uint8_t* __restrict__ out, int64_t capacity,
+                  int64_t* __restrict__ lengths) {
+  __shared__ uint64_t warp_tot[kLayoutBlock / 32];
+  __shared__ uint64_t red[3][kLayoutBlock / 32];
+  __shared__ uint64_t carry_s;
+  const int64_t img = blockIdx.x;
+  PngRowStat* st = stats + img * H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t rowlen = (uint64_t)W + 1;
+  if (threadIdx.x == 0) carry_s = 16 + 3;                  // zlib header (2 bytes) + block header (3 bits)
+  __syncthreads();
+  uint64_t sum_d = 0, sum_g = 0;                            // both kept < kAdlerMod * small
+  for (int y0 = 0; y0 < H; y0 += kLayoutBlock) {
+    const int y = y0 + threadIdx.x;
+    uint64_t bits = 0;
+    if (y < H) {
+      const PngRowStat s = st[y];
+      bits = s.bits;
+      sum_d = (sum_d + s.sum) % kAdlerMod;
+      const uint64_t g = ((((uint64_t)y * rowlen) % kAdlerMod) * (s.sum % kAdlerMod) + s.wsum_off % kAdlerMod) % kAdlerMod;
+      sum_g = (sum_g + g) % kAdlerMod;
+    }
+    uint64_t inc = bits;                                    // block-wide exclusive scan, 64-bit
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint64_t before = carry_s;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (y < H) st[y].wsum_off = before + inc - bits;
+    __syncthreads();
+    if (threadIdx.x == kLayoutBlock - 1) carry_s = before + inc;
+    __syncthreads();
+  }
+  // Adler-32 over the H*(W+1) filtered bytes:  A = 1 + sum d,  B = n + n * sum d - sum g * d_g   (mod 65521)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum_d += __shfl_xor_sync(0xffffffffu, sum_d, o);
+    sum_g += __shfl_xor_sync(0xffffffffu, sum_g, o);
+  }
+  if (lane == 0) {
+    red[0][warp] = sum_d;
+    red[1][warp] = sum_g;
+  }
+  __syncthreads();
+  const uint64_t end_bits = carry_s + 7;                    // + end-of-block code (7 zero bits)
+  const uint64_t deflate_end = (end_bits + 7) >> 3;          // byte offset of the Adler-32 trailer
+  const uint64_t total = deflate_end + 4;
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(out + img * capacity);
+  const uint64_t words = (total + 3) >> 2;
+  for (uint64_t i = threadIdx.x; i < words; i += kLayoutBlock) out32[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t d = 0, g = 0;
+    for (int w = 0; w < kLayoutBlock / 32; ++w) {
+      d += red[0][w];
+      g += red[1][w];
+    }
+    d %= kAdlerMod;
+    g %= kAdlerMod;
+    const uint64_t n = ((uint64_t)H * rowlen) % kAdlerMod;
+    const uint32_t A = (uint32_t)((1 + d) % kAdlerMod);
+    const uint32_t B = (uint32_t)((n + n * d % kAdlerMod + kAdlerMod - g) % kAdlerMod);
+    uint8_t* o = out + img * capacity;
+    out32[0] = 0x00000178u | (3u << 16);                    // 78 01, then BFINAL=1, BTYPE=01 at bit 16
+    o[deflate_end + 0] = (uint8_t)(B >> 8);
+    o[deflate_end + 1] = (uint8_t)(B & 0xff);
+    o[deflate_end + 2] = (uint8_t)(A >> 8);
+    o[deflate_end + 3] = (uint8_t)(A & 0xff);
+    lengths[img] = (int64_t)total;
+  }
+}
+
+}  // namespace diga
+
+extern "C" int64_t diga_png_deflate_capacity(int64_t H, int64_t W) {
+  if (H < 1 || W < 1) return 0;
+  // worst case: every byte a 9-bit literal; + headers, end of block, trailer, rounded up to a multiple of 16 bytes
+  const int64_t bits = H * (W + 1) * 9 + 16 + 3 + 7;
+  return (((bits + 7) / 8 + 4 + 8) + 15) / 16 * 16;
+}
+
+extern "C" int64_t diga_png_deflate_scratch_bytes(int64_t n, int64_t H) {
+  return n < 0 || H < 0 ? 0 : n * H * (int64_t)sizeof(diga::PngRowStat);
+}
+
+extern "C" int diga_png_deflate(const uint8_t* labels, int64_t n, int64_t H, int64_t W, uint8_t* out, int64_t capacity,
+                                void* scratch, int64_t* lengths, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(labels && out && scratch && lengths, DIGA_ERR_INVALID, "png_deflate: null pointer");
+  DIGA_REQUIRE(n >= 0 && H >= 1 && W >= 1 && W <= 65534 && H <= (1 << 24) && n <= 65535, DIGA_ERR_INVALID,
+               "png_deflate: bad sizes n=%lld H=%lld W=%lld", (long long)n, (long long)H, (long long)W);
+  DIGA_REQUIRE(capacity >= diga_png_deflate_capacity(H, W) && capacity % 4 == 0, DIGA_ERR_INVALID,
+               "png_deflate: capacity %lld below diga_png_deflate_capacity", (long long)capacity);
+  DIGA_REQUIRE(aligned(out, 4) && aligned(scratch, 8) && aligned(lengths, 8), DIGA_ERR_MISALIGNED, "png_deflate: misaligned pointer");
+  if (n == 0) return DIGA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  PngRowStat* stats = static_cast<PngRowStat*>(scratch);
+  const int rowlen = (int)W + 1;
+  const int per_warp = (((rowlen + 3) & ~3) + 2 * (rowlen + 1) + 15) & ~15;
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * per_warp;
+  DIGA_REQUIRE(smem <= 200 * 1024, DIGA_ERR_INVALID, "png_deflate: W=%lld needs %zu bytes of shared memory", (long long)W, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
+    if (cudaFuncSetAttribute(png_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(png_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("png_deflate: cannot reserve %zu bytes of shared memory", smem);
+      return DIGA_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  const dim3 grid((unsigned)((H + warps - 1) / warps), (unsigned)n);
+  png_rows_kernel<false><<<grid, warps * 32, smem, st>>>(labels, (int)H, (int)W, stats, nullptr, capacity, per_warp);
+  DIGA_CHECK_LAUNCH("png_rows_kernel<count>");
+  png_layout_kernel<<<(unsigned)n, kLayoutBlock, 0, st>>>(stats, (int)H, (int)W, out, capacity, lengths);
+  DIGA_CHECK_LAUNCH("png_layout_kernel");
+  png_rows_kernel<true><<<grid, warps * 32, smem, st>>>(labels, (int)H, (int)W, stats, out, capacity, per_warp);
+  DIGA_CHECK_LAUNCH("png_rows_kernel<write>");
+  return DIGA_OK;
+}

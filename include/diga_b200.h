@@ -284,6 +284,20 @@ int diga_confusion_matrix(const void* label_true, int true_is_u8, const void* la
 int diga_label_resize_remap(const uint8_t* src, int64_t n, int64_t h0, int64_t w0, const int32_t* ytab, const int32_t* xtab,
                             int64_t H, int64_t W, const uint8_t* lut_host, int64_t* out, diga_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f3 (next row), writer half — pseudolabel_generator.py:45-49, :100-105 (`colorize_mask(...).save(...)`: 'P'-mode PNG)
+ *   The IDAT payload of the PNG, made on the GPU: for each of n uint8 label maps [H, W] the zlib stream (RFC 1950) of the
+ *   scanlines `filter byte 2 (Up) | label[y] - label[y-1]`, one fixed-Huffman deflate block of literal / distance-1 match
+ *   tokens, Adler-32 trailer.  out + i * capacity receives image i's stream, lengths[i] (DEVICE int64) its byte count;
+ *   capacity >= diga_png_deflate_capacity(H, W) (worst case, a multiple of 16); scratch holds
+ *   diga_png_deflate_scratch_bytes(n, H) bytes.  The host only frames the payload (signature, IHDR, PLTE, IDAT + CRC-32,
+ *   IEND).  Decoded pixels, mode and palette equal the reference's files; the compressed bytes differ.
+ * ------------------------------------------------------------------------------------------ */
+int64_t diga_png_deflate_capacity(int64_t H, int64_t W);
+int64_t diga_png_deflate_scratch_bytes(int64_t n, int64_t H);
+int diga_png_deflate(const uint8_t* labels, int64_t n, int64_t H, int64_t W, uint8_t* out, int64_t capacity, void* scratch,
+                     int64_t* lengths, diga_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

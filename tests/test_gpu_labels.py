@@ -1,5 +1,7 @@
 """GPU parity of the label reader (csrc/labels.cu; CityLoader.py:86-96, :113-132 of the reference): bit-exact int64 maps
 against the reference-made golden, the oracle (PIL + numpy) and PIL itself, through PNG files on disk."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -54,3 +56,85 @@ def test_resize_remap_batch_and_errors():
         resize_remap_labels(src.to(DEV).long(), (17, 23))
     with pytest.raises(ValueError):
         resize_remap_labels(src.to(DEV), (17, 23), pseudo_label_lut()[:100])
+
+
+# ------------------------------------------------------------------------------------------------ f3 writer: GPU deflate
+def _png_patterns():
+    rng = np.random.default_rng(5)
+    coarse = rng.integers(0, 19, (9, 13)).astype(np.uint8)
+    coarse[rng.random(coarse.shape) < 0.15] = 255
+    out = {
+        "blocks_odd": np.kron(coarse, np.ones((16, 16), np.uint8))[None, :131, :197],
+        "constant": np.full((2, 40, 600), 7, np.uint8),
+        "noise": rng.integers(0, 256, (2, 33, 70)).astype(np.uint8),
+        "high_values": rng.integers(140, 256, (1, 17, 64)).astype(np.uint8),
+        "one_pixel": np.array([[[200]]], np.uint8),
+        "column": rng.integers(0, 19, (1, 50, 1)).astype(np.uint8),
+        "run_258_edges": np.concatenate([np.full((1, 3, n), 5, np.uint8) for n in (257, 258, 259, 260, 261, 262)], axis=2),
+        "wide_row": np.kron(rng.integers(0, 19, (1, 3, 40)).astype(np.uint8), np.ones((1, 1, 100), np.uint8)),
+        "many_rows": np.kron(rng.integers(0, 19, (1, 300, 2)).astype(np.uint8), np.ones((1, 5, 9), np.uint8)),      # H > 1024
+    }
+    return out
+
+
+@pytest.mark.parametrize("name", ["blocks_odd", "constant", "noise", "high_values", "one_pixel", "column", "run_258_edges",
+                                  "wide_row", "many_rows"])
+def test_png_deflate_stream_bit_exact_vs_oracle(name):
+    """csrc/png.cu against oracle/png_oracle.py: the zlib stream of every image equal byte for byte, and standard zlib
+    inflates it to the Up-filtered scanlines."""
+    import zlib
+    from oracle import png_oracle as P
+    from diga_b200.pseudolabel import png_deflate
+    lab = _png_patterns()[name]
+    payload, lengths = png_deflate(torch.from_numpy(lab).to(DEV))
+    payload, lengths = payload.cpu().numpy(), lengths.cpu().numpy()
+    for i in range(lab.shape[0]):
+        got = payload[i, :lengths[i]].tobytes()
+        assert zlib.decompress(got) == P.filtered_scanlines(lab[i]).tobytes(), f"{name}[{i}] does not inflate to the scanlines"
+        assert got == P.deflate_stream(lab[i]), f"{name}[{i}] differs from the oracle stream"
+
+
+def test_png_deflate_full_resolution_batch_and_errors():
+    """BASELINE config 5 size (1024x2048), a batch of segmentation-like maps plus one noisy map: inflate == scanlines for
+    every image, oracle-equal for the first; buffer reuse (a second call over the same output) stays correct."""
+    import zlib
+    from oracle import png_oracle as P
+    from diga_b200 import synthetic as S
+    from diga_b200.pseudolabel import png_deflate
+    g = S.gen(21, DEV)
+    lab = S.block_labels(3, 1024, 2048, g, 32).to(torch.uint8)
+    noise = torch.randint(0, 19, (1024, 2048), generator=g, device=DEV, dtype=torch.uint8)
+    lab[2] = torch.where(torch.rand((1024, 2048), generator=g, device=DEV) < 0.05, noise, lab[2])
+    for _ in range(2):
+        payload, lengths = png_deflate(lab)
+    host, lens = lab.cpu().numpy(), lengths.cpu().numpy()
+    for i in range(3):
+        got = payload[i, :lens[i]].cpu().numpy().tobytes()
+        assert zlib.decompress(got) == P.filtered_scanlines(host[i]).tobytes()
+    assert payload[0, :lens[0]].cpu().numpy().tobytes() == P.deflate_stream(host[0])
+    assert lens[0] < 64 * 1024 < lens[2]
+    with pytest.raises(RuntimeError):
+        png_deflate(lab.cpu())
+    with pytest.raises(ValueError):
+        png_deflate(lab.long())
+
+
+@pytest.mark.parametrize("encoder,prefix", [("gpu", 256 * 1024), ("gpu", 64), ("pil", 0)])
+def test_pseudo_label_writer_files_decode_like_the_reference(tmp_path, encoder, prefix):
+    """PseudoLabelWriter with the GPU encoder (including the long-stream second copy, forced by a 64-byte prefix) and with
+    Pillow: every file opens as a 'P' image with the Cityscapes palette and the label map as pixel indices — what
+    CityLoader.py:86-95 reads back."""
+    from PIL import Image
+    from diga_b200 import synthetic as S
+    from diga_b200.pseudolabel import CITYSCAPES_PALETTE, PseudoLabelWriter
+    g = S.gen(8, DEV)
+    batches = [S.block_labels(2, 96, 160, g, 16).to(torch.uint8) for _ in range(6)]
+    with PseudoLabelWriter(str(tmp_path), workers=3, slots=2, encoder=encoder, prefix=max(prefix, 1)) as wr:
+        for k, lab in enumerate(batches):
+            wr.submit(lab, [f"x/y/im_{k}_{j}.png" for j in range(2)])
+    assert wr.written == 12 and len(os.listdir(tmp_path)) == 12
+    for k, lab in enumerate(batches):
+        for j in range(2):
+            png = Image.open(os.path.join(tmp_path, f"im_{k}_{j}.png"))
+            assert png.mode == "P" and png.getpalette() == CITYSCAPES_PALETTE
+            assert np.array_equal(np.array(png), lab[j].cpu().numpy())

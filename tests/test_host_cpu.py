@@ -141,3 +141,37 @@ def test_mean_pass_allreduce_world2_gloo(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+# ------------------------------------------------------------------------------------------------ f3 writer: PNG framing
+def _label_patterns():
+    rng = np.random.default_rng(11)
+    coarse = rng.integers(0, 19, (6, 9)).astype(np.uint8)
+    coarse[rng.random(coarse.shape) < 0.15] = 255
+    blocks = np.kron(coarse, np.ones((16, 16), np.uint8))[:90, :131]
+    return {"blocks": blocks, "constant": np.full((40, 600), 7, np.uint8), "noise": rng.integers(0, 256, (33, 70)).astype(np.uint8),
+            "one_pixel": np.array([[200]], np.uint8), "column": rng.integers(0, 19, (50, 1)).astype(np.uint8),
+            "run_258_edges": np.concatenate([np.full((3, n), 5, np.uint8) for n in (257, 258, 259, 260, 261, 262)], axis=1)}
+
+
+@pytest.mark.parametrize("name", ["blocks", "constant", "noise", "one_pixel", "column", "run_258_edges"])
+def test_png_oracle_stream_is_valid_zlib_and_frames_to_the_reference_file(name, tmp_path):
+    """The oracle's token stream (oracle/png_oracle.py) is pinned against the standard decoders: zlib inflates it to the
+    Up-filtered scanlines, and the framed file opens in Pillow to the same mode, palette and pixels as the file the
+    reference's `colorize_mask(...).save(...)` writes (pseudolabel_generator.py:45-49, :104-105)."""
+    import zlib
+    from PIL import Image
+    from oracle import png_oracle as P
+    from diga_b200.pseudolabel import CITYSCAPES_PALETTE, colorize_mask, frame_png
+    lab = _label_patterns()[name]
+    stream = P.deflate_stream(lab)
+    assert zlib.decompress(stream) == P.filtered_scanlines(lab).tobytes()
+    ref_path, got_path = os.path.join(tmp_path, "ref.png"), os.path.join(tmp_path, "got.png")
+    colorize_mask(lab).save(ref_path)
+    with open(got_path, "wb") as f:
+        f.write(frame_png(stream, *lab.shape))
+    Image.open(got_path).verify()
+    ref, got = Image.open(ref_path), Image.open(got_path)
+    assert got.mode == ref.mode == "P" and got.size == ref.size
+    assert got.getpalette() == ref.getpalette() == CITYSCAPES_PALETTE
+    assert np.array_equal(np.array(got), np.array(ref)) and np.array_equal(np.array(got), lab)
