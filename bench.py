@@ -548,6 +548,48 @@ def bench_stages(D, S, dev, peak, world, quick):
         "frac_hbm": mine * ((d * 4 + C * 4) * 129 * 257 + 3 * px5) / (ms5 * 1e-3) / 1e9 / peak,
         "note": "pseudolabel_generator.py:69-85 + the rectification of self_training.py:298-304 per image: fused two-scale "
                 "labels, prototype weights of [1,2048,129,257], consensus selection; no collective (image-sharded)"}
+    # config 5 end to end INCLUDING the files (pseudolabel_generator.py:89-105): the kept maps go to 'P'-mode PNGs on local
+    # disk through PseudoLabelWriter; wall clock from the first kernel to the last closed file.  The GPU encoder runs over
+    # the rank's whole share, the Pillow encoder (what the reference does per image) over a bounded sample.
+    import shutil
+    import tempfile
+    from diga_b200.pseudolabel import PseudoLabelWriter
+
+    def run_config5_png(n_img, encoder, workers):
+        out_dir = tempfile.mkdtemp(prefix="diga_pl_")
+        torch.cuda.synchronize()
+        barrier(world)
+        t0 = time.perf_counter()
+        with PseudoLabelWriter(out_dir, workers=workers, slots=4, encoder=encoder, coalesce=8) as wr:
+            for k in range(n_img):
+                f, la, lb = pool5[k % len(pool5)]
+                lab, _ = D.pseudo_label_two_scale(la, lb, (1024, 2048), want_conf=False)
+                kept, _ = D.consensus_select(lab, cf.get_centroid_weight(f), want_feat_pseudo=False)
+                wr.submit(kept, [f"img_{k}.png"])
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+        names = os.listdir(out_dir)
+        size = sum(os.path.getsize(os.path.join(out_dir, nm)) for nm in names) // max(len(names), 1)
+        assert len(names) == n_img
+        shutil.rmtree(out_dir, ignore_errors=True)
+        return dt, size, wr.bytes_d2h // n_img
+
+    host_workers = min(8, os.cpu_count() or 4)
+    run_config5_png(16, "gpu", host_workers)
+    ms_g, size_g, d2h_g = run_config5_png(mine, "gpu", host_workers)
+    n_pil = min(mine, 96)
+    ms_p, size_p, d2h_p = run_config5_png(n_pil, "pil", host_workers)
+    out["config5_pseudo_labels_whole_set_to_png_files"] = {
+        "images": n_set, "images_per_rank": mine, "ms": ms_g, "images_per_s": n_set / (ms_g * 1e-3),
+        "px_per_s": n_set * px5 / (ms_g * 1e-3), "unit": "px/s (all ranks)", "host_threads": host_workers,
+        "file_bytes_per_image": size_g, "d2h_bytes_per_image": d2h_g,
+        "pillow_encoder": {"images_per_rank": n_pil, "ms_per_image": ms_p / n_pil, "images_per_s": world * n_pil / (ms_p * 1e-3),
+                           "file_bytes_per_image": size_p, "d2h_bytes_per_image": d2h_p},
+        "speedup_vs_pillow_encoder": (ms_p / n_pil) / (ms_g / mine),
+        "note": "config 5 per image + the PNG file: zlib stream made on the GPU (csrc/png.cu: Up filter, run tokens, fixed "
+                "Huffman), 8 maps per encoder call, host threads only frame and write; wall clock incl. file I/O.  The synthetic "
+                "label maps (arg-max of up-sampled random logits) are noise-like, the worst case for a run-length encoder; "
+                "pillow_encoder = the same pipeline with the reference's Image.save on the host threads"}
     del pool5
     return out
 

@@ -17,6 +17,9 @@
 //   layout      : one CTA per image — exclusive scan of the row bit counts, Adler-32 combine, zero the output span,
 //                 zlib header, trailer, byte length
 //   rows<true>  : same walk, tokens OR-ed into the bit stream at their global bit offset (atomicOr on 32-bit words)
+#include <errno.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace diga {
@@ -286,6 +289,91 @@ png_layout_kernel(PngRowStat* __restrict__ stats, int H, int W, uint8_t* __restr
 }
 
 }  // namespace diga
+
+// ---------------------------------------------------------------------------------------------
+// host side: CRC-32 (PNG 1.2 annex D polynomial, slice-by-8) and the file framing
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct CrcTables {
+  uint32_t t[8][256];
+  CrcTables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xff];
+  }
+};
+
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+  static const CrcTables tab;                                // thread-safe initialisation (C++11 magic static)
+  crc = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= crc;
+    crc = tab.t[7][lo & 0xff] ^ tab.t[6][(lo >> 8) & 0xff] ^ tab.t[5][(lo >> 16) & 0xff] ^ tab.t[4][lo >> 24] ^
+          tab.t[3][hi & 0xff] ^ tab.t[2][(hi >> 8) & 0xff] ^ tab.t[1][(hi >> 16) & 0xff] ^ tab.t[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = tab.t[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+  return ~crc;
+}
+
+void put_be32(uint8_t* p, uint32_t v) {
+  p[0] = (uint8_t)(v >> 24);
+  p[1] = (uint8_t)(v >> 16);
+  p[2] = (uint8_t)(v >> 8);
+  p[3] = (uint8_t)v;
+}
+
+bool write_chunk(FILE* f, const char tag[4], const uint8_t* data, size_t n) {
+  uint8_t head[8], tail[4];
+  put_be32(head, (uint32_t)n);
+  memcpy(head + 4, tag, 4);
+  uint32_t crc = crc32_update(0, head + 4, 4);
+  if (n) crc = crc32_update(crc, data, n);
+  put_be32(tail, crc);
+  return fwrite(head, 1, 8, f) == 8 && (n == 0 || fwrite(data, 1, n, f) == n) && fwrite(tail, 1, 4, f) == 4;
+}
+
+}  // namespace
+
+extern "C" int diga_png_write_file(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                                   const uint8_t* palette_host, int64_t palette_bytes) {
+  using namespace diga;
+  DIGA_REQUIRE(path && payload_host && palette_host, DIGA_ERR_INVALID, "png_write_file: null pointer");
+  DIGA_REQUIRE(length > 6 && length < (int64_t(1) << 31) && H >= 1 && W >= 1 && H < (int64_t(1) << 31) && W < (int64_t(1) << 31),
+               DIGA_ERR_INVALID, "png_write_file: bad sizes");
+  DIGA_REQUIRE(palette_bytes >= 3 && palette_bytes <= 768 && palette_bytes % 3 == 0, DIGA_ERR_INVALID,
+               "png_write_file: palette of %lld bytes", (long long)palette_bytes);
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    set_error("png_write_file: cannot open %s: %s", path, strerror(errno));
+    return DIGA_ERR_IO;
+  }
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  uint8_t ihdr[13];
+  put_be32(ihdr, (uint32_t)W);
+  put_be32(ihdr + 4, (uint32_t)H);
+  ihdr[8] = 8;   // bit depth
+  ihdr[9] = 3;   // colour type: palette
+  ihdr[10] = ihdr[11] = ihdr[12] = 0;
+  bool ok = fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr, 13) &&
+            write_chunk(f, "PLTE", palette_host, (size_t)palette_bytes) && write_chunk(f, "IDAT", payload_host, (size_t)length) &&
+            write_chunk(f, "IEND", nullptr, 0);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) {
+    set_error("png_write_file: short write to %s: %s", path, strerror(errno));
+    return DIGA_ERR_IO;
+  }
+  return DIGA_OK;
+}
 
 extern "C" int64_t diga_png_deflate_capacity(int64_t H, int64_t W) {
   if (H < 1 || W < 1) return 0;

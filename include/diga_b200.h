@@ -31,7 +31,8 @@ enum diga_status {
   DIGA_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported class count */
   DIGA_ERR_MISALIGNED = -2,  /* pointer not aligned to its element size */
   DIGA_ERR_CUDA = -3,        /* launch failed; see diga_last_error_string() */
-  DIGA_ERR_WORKSPACE = -4    /* workspace too small */
+  DIGA_ERR_WORKSPACE = -4,   /* workspace too small */
+  DIGA_ERR_IO = -5           /* a host file could not be written (diga_png_write_file) */
 };
 
 enum diga_update_mode { DIGA_UPDATE_MEAN = 0, DIGA_UPDATE_MOVING_AVERAGE = 1 };
@@ -297,6 +298,11 @@ int64_t diga_png_deflate_capacity(int64_t H, int64_t W);
 int64_t diga_png_deflate_scratch_bytes(int64_t n, int64_t H);
 int diga_png_deflate(const uint8_t* labels, int64_t n, int64_t H, int64_t W, uint8_t* out, int64_t capacity, void* scratch,
                      int64_t* lengths, diga_stream_t stream);
+/* Host side of the same row: frame a finished payload (HOST memory, e.g. the pinned staging buffer) as a 'P'-mode PNG
+ * file — signature, IHDR (8 bit, colour type 3), PLTE (palette_bytes = 3 * entries <= 768), IDAT with its CRC-32, IEND —
+ * and write it to `path`.  No CUDA call; safe to call from several host threads at once. */
+int diga_png_write_file(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                        const uint8_t* palette_host, int64_t palette_bytes);
 
 #ifdef __cplusplus
 }

@@ -119,8 +119,8 @@ def test_png_deflate_full_resolution_batch_and_errors():
         png_deflate(lab.long())
 
 
-@pytest.mark.parametrize("encoder,prefix", [("gpu", 256 * 1024), ("gpu", 64), ("pil", 0)])
-def test_pseudo_label_writer_files_decode_like_the_reference(tmp_path, encoder, prefix):
+@pytest.mark.parametrize("encoder,prefix,coalesce", [("gpu", 256 * 1024, 1), ("gpu", 64, 1), ("gpu", 256 * 1024, 5), ("pil", 0, 1)])
+def test_pseudo_label_writer_files_decode_like_the_reference(tmp_path, encoder, prefix, coalesce):
     """PseudoLabelWriter with the GPU encoder (including the long-stream second copy, forced by a 64-byte prefix) and with
     Pillow: every file opens as a 'P' image with the Cityscapes palette and the label map as pixel indices — what
     CityLoader.py:86-95 reads back."""
@@ -129,7 +129,7 @@ def test_pseudo_label_writer_files_decode_like_the_reference(tmp_path, encoder, 
     from diga_b200.pseudolabel import CITYSCAPES_PALETTE, PseudoLabelWriter
     g = S.gen(8, DEV)
     batches = [S.block_labels(2, 96, 160, g, 16).to(torch.uint8) for _ in range(6)]
-    with PseudoLabelWriter(str(tmp_path), workers=3, slots=2, encoder=encoder, prefix=max(prefix, 1)) as wr:
+    with PseudoLabelWriter(str(tmp_path), workers=3, slots=2, encoder=encoder, prefix=max(prefix, 1), coalesce=coalesce) as wr:
         for k, lab in enumerate(batches):
             wr.submit(lab, [f"x/y/im_{k}_{j}.png" for j in range(2)])
     assert wr.written == 12 and len(os.listdir(tmp_path)) == 12

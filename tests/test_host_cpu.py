@@ -175,3 +175,23 @@ def test_png_oracle_stream_is_valid_zlib_and_frames_to_the_reference_file(name, 
     assert got.mode == ref.mode == "P" and got.size == ref.size
     assert got.getpalette() == ref.getpalette() == CITYSCAPES_PALETTE
     assert np.array_equal(np.array(got), np.array(ref)) and np.array_equal(np.array(got), lab)
+
+
+def test_png_write_file_native_framing_matches_python_framing(tmp_path):
+    """diga_png_write_file (host-only C entry point: CRC-32 + chunk framing) writes byte for byte what frame_png builds with
+    the standard library's struct / zlib.crc32, reports unwritable paths, and validates its arguments."""
+    import ctypes
+    from oracle import png_oracle as P
+    from diga_b200 import _lib as L
+    from diga_b200.pseudolabel import CITYSCAPES_PALETTE, frame_png
+    pal = (ctypes.c_ubyte * 768)(*CITYSCAPES_PALETTE)
+    for name, lab in _label_patterns().items():
+        stream = P.deflate_stream(lab)
+        buf = (ctypes.c_ubyte * len(stream)).from_buffer_copy(stream)
+        path = os.path.join(tmp_path, name + ".png")
+        assert L.lib.diga_png_write_file(os.fsencode(path), buf, len(stream), lab.shape[0], lab.shape[1], pal, 768) == 0
+        assert open(path, "rb").read() == frame_png(stream, *lab.shape)
+    assert L.lib.diga_png_write_file(os.fsencode(os.path.join(tmp_path, "no_such_dir", "x.png")), buf, len(stream), 3, 3, pal, 768) == -5
+    assert "cannot open" in L.last_error()
+    assert L.lib.diga_png_write_file(os.fsencode(path), buf, len(stream), 3, 3, pal, 767) == -1
+    assert L.lib.diga_png_write_file(None, buf, len(stream), 3, 3, pal, 768) == -1
