@@ -58,6 +58,11 @@ elif which == "eval":
     for _ in range(3):
         rs.update(gt, pred)
         resize_remap_labels(raw, (512, 1024), trainid_lut())
+elif which == "png":
+    from diga_b200.pseudolabel import png_deflate
+    lab = S.block_labels(8, 1024, 2048, g, 32).to(torch.uint8)
+    for _ in range(3):
+        png_deflate(lab)
 elif which == "presence":
     from diga_b200.classmix import present_classes
     sl = S.block_labels(8, 512, 1024, g)
