@@ -236,7 +236,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "pixel-positions/s", "cores": threads, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "pixel-positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -597,7 +597,28 @@ def bench_stages(D, S, dev, peak, world, quick):
 # --------------------------------------------------------------------------------------------------
 # main arm
 # --------------------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner goes to fd 1 whenever
+    NCCL_DEBUG is VERSION or above), so the real stdout is set aside for the result line and fd 1 is pointed at stderr for
+    everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -616,8 +637,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
     import diga_b200 as D
     from diga_b200 import _lib as L, synthetic as S
@@ -835,7 +854,7 @@ def main():
             "eager_ms_per_step": eager_ms_step,
             "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "stages": stages, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
