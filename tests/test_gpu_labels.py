@@ -138,3 +138,22 @@ def test_pseudo_label_writer_files_decode_like_the_reference(tmp_path, encoder, 
             png = Image.open(os.path.join(tmp_path, f"im_{k}_{j}.png"))
             assert png.mode == "P" and png.getpalette() == CITYSCAPES_PALETTE
             assert np.array_equal(np.array(png), lab[j].cpu().numpy())
+
+
+def test_png_deflate_random_shapes_vs_oracle():
+    """Seeded sweep over shapes / run structures (see the CPU twin in test_host_cpu.py): GPU stream == oracle stream."""
+    from oracle import png_oracle as P
+    from diga_b200.pseudolabel import png_deflate
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        n, h, w = int(rng.integers(1, 4)), int(rng.integers(1, 60)), int(rng.integers(1, 900))
+        n_runs = int(rng.integers(1, 12))
+        row = np.repeat(rng.integers(0, 256, n_runs), rng.integers(1, 300, n_runs))[:w]
+        row = np.pad(row, (0, w - row.size), mode="edge").astype(np.uint8)
+        lab = np.tile(row, (n, h, 1))
+        flip = rng.random((n, h, w)) < rng.choice([0.0, 0.01, 0.2])
+        lab[flip] = rng.integers(0, 256, int(flip.sum()))
+        payload, lengths = png_deflate(torch.from_numpy(lab).to(DEV))
+        payload, lengths = payload.cpu().numpy(), lengths.cpu().numpy()
+        for i in range(n):
+            assert payload[i, :lengths[i]].tobytes() == P.deflate_stream(lab[i]), (n, h, w, i)

@@ -195,3 +195,20 @@ def test_png_write_file_native_framing_matches_python_framing(tmp_path):
     assert "cannot open" in L.last_error()
     assert L.lib.diga_png_write_file(os.fsencode(path), buf, len(stream), 3, 3, pal, 767) == -1
     assert L.lib.diga_png_write_file(None, buf, len(stream), 3, 3, pal, 768) == -1
+
+
+def test_png_oracle_random_run_structures_inflate():
+    """Seeded sweep over shapes and run structures (run lengths around the 258-byte match limit, values on both sides of the
+    8/9-bit literal boundary): the oracle stream always inflates to the filtered scanlines."""
+    import zlib
+    from oracle import png_oracle as P
+    rng = np.random.default_rng(2024)
+    for _ in range(60):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 700))
+        n_runs = int(rng.integers(1, 12))
+        row = np.repeat(rng.integers(0, 256, n_runs), rng.integers(1, 300, n_runs))[:w]
+        row = np.pad(row, (0, w - row.size), mode="edge").astype(np.uint8)
+        lab = np.tile(row, (h, 1))
+        flip = rng.random((h, w)) < rng.choice([0.0, 0.01, 0.2])
+        lab[flip] = rng.integers(0, 256, int(flip.sum()))
+        assert zlib.decompress(P.deflate_stream(lab)) == P.filtered_scanlines(lab).tobytes()
