@@ -6,10 +6,15 @@
 // bytes differ (as they do between zlib versions).
 //
 // Stream layout (RFC 1950 / 1951 / PNG 1.2):
-//   zlib header 78 01 | ONE fixed-Huffman deflate block (BFINAL=1, BTYPE=01) | pad to byte | Adler-32 (big endian)
+//   zlib header 78 01 | ONE deflate block (BFINAL=1, BTYPE=10) with a STATIC code table | pad to byte | Adler-32 (big endian)
 //   scanline y = filter byte 2 (Up) followed by label[y][x] - label[y-1][x] (mod 256; row -1 is zero).
 // A segmentation map filtered that way is zero except along horizontal class edges, so the encoder only needs runs:
 // every run of equal bytes becomes   literal(v)   then   match(len <= 258, distance 1)   tokens.
+// The Huffman table is not computed per image: a filtered 19-class map only holds the bytes 0, +-1..+-18, 255-k and the
+// filter byte, and nearly all matches are 258-byte runs, so ONE table tuned on label maps (tools/make_png_table.py ->
+// png_table.inc: 2 bits for a zero, 4 bits for a 258-byte match instead of 8 and 13 with the fixed code of BTYPE=01) is
+// sent as the block's "dynamic" header (350 constant bits).  Every byte value keeps a code (<= 12 bits), so any uint8 map
+// encodes.  Files come out at 0.4x (blocky maps) to 1.1x (noise-like maps) of Pillow's.
 //
 // Three launches per batch, no host sync:
 //   rows<false> : one warp per scanline — filter into shared memory, find the run starts (lane-segment scan + warp prefix
@@ -34,13 +39,23 @@ __constant__ uint16_t kLenBase[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  
                                       31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __constant__ uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 
-__device__ __forceinline__ uint32_t rev_bits(uint32_t x, int n) { return __brev(x) >> (32 - n); }
+#include "png_table.inc"
 
-// fixed Huffman literal: 0..143 -> 8 bits 00110000+v, 144..255 -> 9 bits 110010000+(v-144); codes go MSB first
-__device__ __forceinline__ int lit_bits(uint32_t v) { return v < 144 ? 8 : 9; }
-__device__ __forceinline__ uint32_t lit_pattern(uint32_t v) { return v < 144 ? rev_bits(0x30 + v, 8) : rev_bits(0x190 + (v - 144), 9); }
+// The look-ups are lane-divergent (one byte value per lane), so every CTA first packs the table into shared memory:
+// literal entry = pattern | bits << 16;  length entry = pattern | code bits << 16 | total bits (code + extra + distance) << 24.
+struct PngLut {
+  uint32_t lit[256];
+  uint32_t len[29];
+};
 
-// match of `len` (3..258) at distance 1: length code + extra bits (LSB first) + 5-bit distance code 0
+__device__ __forceinline__ void png_lut_fill(PngLut& L) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) L.lit[i] = (uint32_t)kPngLitPat[i] | ((uint32_t)kPngLitLen[i] << 16);
+  for (int i = threadIdx.x; i < 29; i += blockDim.x)
+    L.len[i] = (uint32_t)kPngLenPat[i] | ((uint32_t)kPngLenLen[i] << 16) | ((uint32_t)(kPngLenLen[i] + kLenExtra[i] + 1) << 24);
+  __syncthreads();
+}
+
+// match of `len` (3..258) at distance 1: length code + extra bits (LSB first) + the single distance code (one 0 bit)
 __device__ __forceinline__ int match_code(int len) {
   int lo = 0, hi = 28;
   while (lo < hi) {
@@ -50,11 +65,10 @@ __device__ __forceinline__ int match_code(int len) {
   }
   return lo;
 }
-__device__ __forceinline__ int match_bits_of(int idx) { return (idx < 23 ? 7 : 8) + kLenExtra[idx] + 5; }
-__device__ __forceinline__ uint32_t match_pattern(int len, int idx) {
-  const int hb = idx < 23 ? 7 : 8;                                      // codes 257..279: 7 bits, 280..285: 8 bits
-  const uint32_t huff = idx < 23 ? rev_bits(1 + idx, 7) : rev_bits(0xC0 + (idx - 23), 8);
-  return huff | ((uint32_t)(len - kLenBase[idx]) << hb);
+__device__ __forceinline__ int match_bits_of(const PngLut& L, int idx) { return (int)(L.len[idx] >> 24); }
+__device__ __forceinline__ uint32_t match_pattern(const PngLut& L, int len, int idx) {
+  const uint32_t e = L.len[idx];
+  return (e & 0xffffu) | ((uint32_t)(len - kLenBase[idx]) << ((e >> 16) & 0xffu));
 }
 
 __device__ __forceinline__ void put_bits(uint32_t* out, uint64_t pos, uint32_t pattern, int nbits) {
@@ -84,6 +98,8 @@ __global__ void png_rows_kernel(const uint8_t* __restrict__ labels, int H, int W
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int y = blockIdx.x * warps + warp;
   const int64_t img = blockIdx.y;
+  __shared__ PngLut lut;
+  png_lut_fill(lut);
   if (y >= H) return;
   const int rowlen = W + 1;
   uint8_t* f = png_smem + (size_t)warp * smem_per_warp;                            // filtered scanline
@@ -159,11 +175,11 @@ __global__ void png_rows_kernel(const uint8_t* __restrict__ labels, int H, int W
       const int m = e - s - 1;                 // bytes after the literal
       nfull = m / 258;
       rem = m - nfull * 258;
-      const int lb = lit_bits(v);
-      bits = lb + nfull * 13;
+      const int lb = (int)(lut.lit[v] >> 16);
+      bits = lb + nfull * match_bits_of(lut, 28);
       if (rem >= 3) {
         ridx = match_code(rem);
-        bits += match_bits_of(ridx);
+        bits += match_bits_of(lut, ridx);
       } else {
         bits += rem * lb;
       }
@@ -172,16 +188,16 @@ __global__ void png_rows_kernel(const uint8_t* __restrict__ labels, int H, int W
     const uint32_t excl = warp_excl_scan(bits, total);
     if (WRITE && r < nruns) {
       uint64_t pos = row_off + carry + excl;
-      const int lb = lit_bits(v);
-      const uint32_t lp = lit_pattern(v);
+      const int lb = (int)(lut.lit[v] >> 16);
+      const uint32_t lp = lut.lit[v] & 0xffffu;
       put_bits(out32, pos, lp, lb);
       pos += lb;
       for (int k = 0; k < nfull; ++k) {
-        put_bits(out32, pos, 0xA3u, 13);       // code 285 (len 258) = 11000101 reversed, no extra bits, distance code 0
-        pos += 13;
+        put_bits(out32, pos, lut.len[28] & 0xffffu, match_bits_of(lut, 28));   // code 285 (len 258), no extra bits, distance code
+        pos += match_bits_of(lut, 28);
       }
       if (rem >= 3) {
-        put_bits(out32, pos, match_pattern(rem, ridx), match_bits_of(ridx));
+        put_bits(out32, pos, match_pattern(lut, rem, ridx), match_bits_of(lut, ridx));
       } else {
         for (int k = 0; k < rem; ++k) {
           put_bits(out32, pos, lp, lb);
@@ -221,7 +237,7 @@ png_layout_kernel(PngRowStat* __restrict__ stats, int H, int W, uint8_t* __restr
   PngRowStat* st = stats + img * H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t rowlen = (uint64_t)W + 1;
-  if (threadIdx.x == 0) carry_s = 16 + 3;                  // zlib header (2 bytes) + block header (3 bits)
+  if (threadIdx.x == 0) carry_s = 16 + kPngHeaderBits;     // zlib header (2 bytes) + block header with the code table
   __syncthreads();
   uint64_t sum_d = 0, sum_g = 0;                            // both kept < kAdlerMod * small
   for (int y0 = 0; y0 < H; y0 += kLayoutBlock) {
@@ -260,7 +276,7 @@ png_layout_kernel(PngRowStat* __restrict__ stats, int H, int W, uint8_t* __restr
     red[1][warp] = sum_g;
   }
   __syncthreads();
-  const uint64_t end_bits = carry_s + 7;                    // + end-of-block code (7 zero bits)
+  const uint64_t end_bits = carry_s + kPngEobLen;           // + end-of-block code
   const uint64_t deflate_end = (end_bits + 7) >> 3;          // byte offset of the Adler-32 trailer
   const uint64_t total = deflate_end + 4;
   uint32_t* out32 = reinterpret_cast<uint32_t*>(out + img * capacity);
@@ -279,7 +295,13 @@ png_layout_kernel(PngRowStat* __restrict__ stats, int H, int W, uint8_t* __restr
     const uint32_t A = (uint32_t)((1 + d) % kAdlerMod);
     const uint32_t B = (uint32_t)((n + n * d % kAdlerMod + kAdlerMod - g) % kAdlerMod);
     uint8_t* o = out + img * capacity;
-    out32[0] = 0x00000178u | (3u << 16);                    // 78 01, then BFINAL=1, BTYPE=01 at bit 16
+    out32[0] = 0x00000178u;                                 // 78 01
+    for (int k = 0; k < (kPngHeaderBits + 31) / 32; ++k) {   // block header (constant bits) from bit 16
+      const int nb = min(32, kPngHeaderBits - 32 * k);
+      put_bits(out32, 16 + 32 * (uint64_t)k, kPngHeaderWords[k] & 0xffffu, min(nb, 16));
+      if (nb > 16) put_bits(out32, 16 + 32 * (uint64_t)k + 16, kPngHeaderWords[k] >> 16, nb - 16);
+    }
+    put_bits(out32, carry_s, kPngEobPat, kPngEobLen);
     o[deflate_end + 0] = (uint8_t)(B >> 8);
     o[deflate_end + 1] = (uint8_t)(B & 0xff);
     o[deflate_end + 2] = (uint8_t)(A >> 8);
@@ -377,8 +399,8 @@ extern "C" int diga_png_write_file(const char* path, const uint8_t* payload_host
 
 extern "C" int64_t diga_png_deflate_capacity(int64_t H, int64_t W) {
   if (H < 1 || W < 1) return 0;
-  // worst case: every byte a 9-bit literal; + headers, end of block, trailer, rounded up to a multiple of 16 bytes
-  const int64_t bits = H * (W + 1) * 9 + 16 + 3 + 7;
+  // worst case: every byte a literal of the longest code; + headers, end of block, trailer, rounded up to 16 bytes
+  const int64_t bits = H * (W + 1) * diga::kPngMaxLitBits + 16 + diga::kPngHeaderBits + diga::kPngEobLen;
   return (((bits + 7) / 8 + 4 + 8) + 15) / 16 * 16;
 }
 

@@ -94,7 +94,7 @@ def frame_png(idat_payload, height, width, palette=None):
 
 def png_deflate(label_u8):
     """``label_u8 [N,H,W]`` uint8 CUDA tensor -> ``(payload uint8 [N, capacity], lengths int64 [N])``, both on the device:
-    ``payload[i, :lengths[i]]`` is image i's complete zlib stream (Up-filtered scanlines, one fixed-Huffman deflate block,
+    ``payload[i, :lengths[i]]`` is image i's complete zlib stream (Up-filtered scanlines, one deflate block with a static Huffman table,
     Adler-32), ready for :func:`frame_png`.  Three kernel launches for the whole batch, no host sync."""
     L.require_cuda(label_u8, what="pseudo-label map")
     if label_u8.dtype != torch.uint8 or label_u8.dim() != 3:
@@ -245,13 +245,13 @@ class PseudoLabelWriter:
         self.close()
 
 
-def generate_pseudo_labels(student, loader, output_dir, size=(1024, 2048), workers=4, encoder="gpu"):
+def generate_pseudo_labels(student, loader, output_dir, size=(1024, 2048), workers=4, encoder="gpu", coalesce=8):
     """The loop of ``pseudolabel_generator.py:69-105`` with the per-pixel math and the output path replaced:
     two forward passes (full and half resolution, :73-76), fused up-sampling + max + argmax on the GPU, PNGs streamed
     out by :class:`PseudoLabelWriter`.  ``student(x)`` returns ``(_, _, logits, _)`` like the reference ``SegModel``;
-    ``loader`` yields ``(image, _, name)`` batches."""
+    ``loader`` yields ``(image, _, name)`` batches (batch size 1 in the reference; ``coalesce`` maps are encoded per call)."""
     import torch.nn.functional as F
-    with PseudoLabelWriter(output_dir, workers=workers, encoder=encoder) as writer, torch.no_grad():
+    with PseudoLabelWriter(output_dir, workers=workers, encoder=encoder, coalesce=coalesce) as writer, torch.no_grad():
         for index, batch in enumerate(loader):
             image, _, name = batch
             image = image.cuda(non_blocking=True)

@@ -288,7 +288,7 @@ int diga_label_resize_remap(const uint8_t* src, int64_t n, int64_t h0, int64_t w
 /* ------------------------------------------------------------------------------------------
  * f3 (next row), writer half — pseudolabel_generator.py:45-49, :100-105 (`colorize_mask(...).save(...)`: 'P'-mode PNG)
  *   The IDAT payload of the PNG, made on the GPU: for each of n uint8 label maps [H, W] the zlib stream (RFC 1950) of the
- *   scanlines `filter byte 2 (Up) | label[y] - label[y-1]`, one fixed-Huffman deflate block of literal / distance-1 match
+ *   scanlines `filter byte 2 (Up) | label[y] - label[y-1]`, one deflate block with a static Huffman table (tuned on label maps) of literal / distance-1 match
  *   tokens, Adler-32 trailer.  out + i * capacity receives image i's stream, lengths[i] (DEVICE int64) its byte count;
  *   capacity >= diga_png_deflate_capacity(H, W) (worst case, a multiple of 16); scratch holds
  *   diga_png_deflate_scratch_bytes(n, H) bytes.  The host only frames the payload (signature, IHDR, PLTE, IDAT + CRC-32,

@@ -6,14 +6,18 @@ The reference writes its pseudo-labels with ``colorize_mask(label).save(path)`` 
 :100-105``): Pillow's PNG plugin on top of zlib, neither of which is part of ``/root/reference``
 (``requirements.txt``: ``Pillow==8.1.0``; zlib is whatever the Python build links).  What the reference pins is the
 *decoded* file: mode 'P', palette = the Cityscapes trainId colours, pixel index = trainId.  ``csrc/png.cu`` emits a
-particular, much simpler deflate stream (Up filter, one fixed-Huffman block, literal + distance-1 matches); this module
-restates exactly that token stream from the published formats (RFC 1950, RFC 1951, PNG 1.2 §6 / §9) in numpy, so the GPU
-bytes can be checked bit for bit, and pins itself against the standard decoders: ``zlib.decompress`` must return the
+particular, much simpler deflate stream (Up filter, one block with a STATIC Huffman table tuned on label maps, literal +
+distance-1 matches); this module restates exactly that token stream from the published formats (RFC 1950, RFC 1951, PNG
+1.2 §6 / §9) in numpy, so the GPU bytes can be checked bit for bit.  The table itself is data: the code LENGTHS and the
+block-header bits in ``tests/golden/png_table.json`` (written by ``tools/make_png_table.py`` together with the constants
+the kernels index); the codes are derived from the lengths here, independently, by RFC 1951 §3.2.2, and pins itself against the standard decoders: ``zlib.decompress`` must return the
 filtered scanlines, and Pillow must open the framed file to the same pixels / mode / palette as the file Pillow itself
 writes for ``colorize_mask`` (``tests/test_oracle_golden.py``).
 """
 from __future__ import annotations
 
+import json
+import os
 import zlib
 
 import numpy as np
@@ -34,28 +38,49 @@ def filtered_scanlines(label: np.ndarray) -> np.ndarray:
     return out
 
 
+def _table():
+    global _TABLE
+    if _TABLE is None:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "png_table.json")) as f:
+            t = json.load(f)
+        lengths = np.array(t["lit_lengths"], dtype=np.int64)
+        assert lengths.size == 286 and t["dist_lengths"] == [1]
+        # canonical Huffman codes from the lengths alone (RFC 1951 §3.2.2): symbols ordered by (length, symbol) take
+        # consecutive code values; the value is shifted left whenever the length grows
+        codes = np.zeros(286, dtype=np.int64)
+        code, prev = 0, None
+        for sym in sorted(np.flatnonzero(lengths), key=lambda i: (lengths[i], i)):
+            if prev is not None:
+                code = (code + 1) << int(lengths[sym] - lengths[prev])
+            codes[sym] = code
+            prev = sym
+        _TABLE = {"len": lengths, "pat": _rev(codes, lengths), "header": np.array([int(c) for c in t["header_bits"]], dtype=np.uint8)}
+    return _TABLE
+
+
+_TABLE = None
+
+
 def _rev(x: np.ndarray, n: np.ndarray) -> np.ndarray:
     """Huffman codes are packed starting from their most significant bit (RFC 1951 §3.1.1)."""
     r = np.zeros_like(x)
-    for j in range(9):
+    for j in range(16):
         r |= np.where(j < n, ((x >> j) & 1) << np.maximum(n - 1 - j, 0), 0)
     return r
 
 
 def _literal(v: np.ndarray):
-    """Fixed Huffman code of a literal (RFC 1951 §3.2.6): 0..143 -> 8 bits from 00110000, 144..255 -> 9 bits from 110010000."""
-    nb = np.where(v < 144, 8, 9)
-    code = np.where(v < 144, 0x30 + v, 0x190 + (v - 144))
-    return _rev(code, nb), nb
+    t = _table()
+    return t["pat"][v], t["len"][v]
 
 
 def _match(length: np.ndarray):
-    """Length code + extra bits + the 5-bit distance code 0 (distance 1)."""
+    """Length code + extra bits (LSB first) + the single distance code (distance 1): one 0 bit."""
+    t = _table()
     idx = np.searchsorted(LEN_BASE, length, side="right") - 1
-    hb = np.where(idx < 23, 7, 8)                                     # codes 256..279: 7 bits, 280..287: 8 bits
-    code = np.where(idx < 23, 1 + idx, 0xC0 + (idx - 23))
-    pat = _rev(code, hb) | ((length - LEN_BASE[idx]) << hb)
-    return pat, hb + LEN_EXTRA[idx] + 5
+    hb = t["len"][257 + idx]
+    pat = t["pat"][257 + idx] | ((length - LEN_BASE[idx]) << hb)
+    return pat, hb + LEN_EXTRA[idx] + 1
 
 
 def token_stream(label: np.ndarray):
@@ -78,25 +103,32 @@ def token_stream(label: np.ndarray):
     k = np.arange(int(count.sum())) - first[run]
     lit_p, lit_n = _literal(v)
     rem_p, rem_n = _match(np.maximum(rem, 3))
+    full_p, full_n = _match(np.array([258]))
     is_lit = (k == 0) | ((k > nfull[run]) & (rem[run] < 3))
     is_full = (k >= 1) & (k <= nfull[run])
-    pat = np.where(is_lit, lit_p[run], np.where(is_full, 0xA3, rem_p[run]))
-    nb = np.where(is_lit, lit_n[run], np.where(is_full, 13, rem_n[run]))
+    pat = np.where(is_lit, lit_p[run], np.where(is_full, full_p[0], rem_p[run]))
+    nb = np.where(is_lit, lit_n[run], np.where(is_full, full_n[0], rem_n[run]))
     return pat.astype(np.int64), nb.astype(np.int64)
 
 
 def deflate_stream(label: np.ndarray) -> bytes:
-    """zlib stream (RFC 1950) of the filtered scanlines exactly as ``csrc/png.cu`` lays it out."""
+    """zlib stream (RFC 1950) of the filtered scanlines exactly as ``csrc/png.cu`` lays it out: 78 01, the block header
+    (BFINAL=1, BTYPE=10 and the static code table), the tokens, the end-of-block code, zero padding, Adler-32."""
+    t = _table()
     pat, nb = token_stream(label)
-    pos = 16 + 3 + np.cumsum(nb) - nb
-    end = 16 + 3 + int(nb.sum()) + 7                                  # + end-of-block (7 zero bits)
-    nbytes = (end + 7) // 8
+    hdr = t["header"]
+    first = 16 + hdr.size
+    pos = first + np.cumsum(nb) - nb
+    eob_at = first + int(nb.sum())
+    eob_n = int(t["len"][256])
+    nbytes = (eob_at + eob_n + 7) // 8
     bits = np.zeros(nbytes * 8, dtype=np.uint8)
-    for j in range(18):
+    bits[16:first] = hdr
+    for j in range(int(nb.max()) if nb.size else 0):
         sel = nb > j
         bits[pos[sel] + j] = (pat[sel] >> j) & 1
-    bits[16] = 1                                                      # BFINAL
-    bits[17] = 1                                                      # BTYPE = 01 (fixed Huffman), low bit first
+    for j in range(eob_n):
+        bits[eob_at + j] = (int(t["pat"][256]) >> j) & 1
     body = np.packbits(bits, bitorder="little")
     body[0], body[1] = 0x78, 0x01
     adler = zlib.adler32(filtered_scanlines(label).tobytes())
