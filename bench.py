@@ -555,8 +555,12 @@ def bench_stages(D, S, dev, peak, world, quick):
     import tempfile
     from diga_b200.pseudolabel import PseudoLabelWriter
 
+    # tmpfs when there is one: the box's virtual disk throttles on dirty pages (460-790 ms for the same run on /tmp depending
+    # on what was written before, tools/experiments/r01_config5_files.py), which is the VM's write-back, not this pipeline
+    file_root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+
     def run_config5_png(n_img, encoder, workers):
-        out_dir = tempfile.mkdtemp(prefix="diga_pl_")
+        out_dir = tempfile.mkdtemp(prefix="diga_pl_", dir=file_root)
         torch.cuda.synchronize()
         barrier(world)
         t0 = time.perf_counter()
@@ -582,12 +586,12 @@ def bench_stages(D, S, dev, peak, world, quick):
     out["config5_pseudo_labels_whole_set_to_png_files"] = {
         "images": n_set, "images_per_rank": mine, "ms": ms_g, "images_per_s": n_set / (ms_g * 1e-3),
         "px_per_s": n_set * px5 / (ms_g * 1e-3), "unit": "px/s (all ranks)", "host_threads": host_workers,
-        "file_bytes_per_image": size_g, "d2h_bytes_per_image": d2h_g,
+        "file_bytes_per_image": size_g, "d2h_bytes_per_image": d2h_g, "files_on": file_root or tempfile.gettempdir(),
         "pillow_encoder": {"images_per_rank": n_pil, "ms_per_image": ms_p / n_pil, "images_per_s": world * n_pil / (ms_p * 1e-3),
                            "file_bytes_per_image": size_p, "d2h_bytes_per_image": d2h_p},
         "speedup_vs_pillow_encoder": (ms_p / n_pil) / (ms_g / mine),
         "note": "config 5 per image + the PNG file: zlib stream made on the GPU (csrc/png.cu: Up filter, run tokens, fixed "
-                "Huffman), 8 maps per encoder call, host threads only frame and write; wall clock incl. file I/O.  The synthetic "
+                "Huffman), 8 maps per encoder call, host threads only frame and write; wall clock incl. file I/O (tmpfs when available).  The synthetic "
                 "label maps (arg-max of up-sampled random logits) are noise-like, the worst case for a run-length encoder; "
                 "pillow_encoder = the same pipeline with the reference's Image.save on the host threads"}
     del pool5
