@@ -212,3 +212,32 @@ def test_png_oracle_random_run_structures_inflate():
         flip = rng.random((h, w)) < rng.choice([0.0, 0.01, 0.2])
         lab[flip] = rng.integers(0, 256, int(flip.sum()))
         assert zlib.decompress(P.deflate_stream(lab)) == P.filtered_scanlines(lab).tobytes()
+
+
+def test_png_table_constants_match_the_fixture():
+    """csrc/png_table.inc (what the kernels index) and tests/golden/png_table.json (what the oracle derives its codes from)
+    describe the same static Huffman table: the .inc patterns are the bit-reversed canonical codes of the fixture's lengths,
+    the code is complete (Kraft sum 1, which zlib requires of a literal/length code), and the header words spell the
+    fixture's header bits."""
+    import json
+    from oracle import png_oracle as P
+    src = open(os.path.join(ROOT, "diga_b200", "csrc", "png_table.inc")).read()
+
+    def arr(name):
+        body = re.search(name + r"\[\d+\] = \{(.*?)\};", src, flags=re.S).group(1)
+        return [int(tok.rstrip("u"), 0) for tok in body.replace("\n", " ").split(",")]
+
+    fix = json.load(open(os.path.join(ROOT, "tests", "golden", "png_table.json")))
+    lengths = fix["lit_lengths"]
+    assert abs(sum(2.0 ** -n for n in lengths) - 1.0) < 1e-12 and max(lengths[:256]) <= 12
+    t = P._table()
+    assert arr("kPngLitLen") == lengths[:256] and arr("kPngLenLen") == lengths[257:286]
+    assert arr("kPngLitPat") == [int(v) for v in t["pat"][:256]]
+    assert arr("kPngLenPat") == [int(v) for v in t["pat"][257:286]]
+    assert int(re.search(r"kPngEobPat = (\d+)u", src).group(1)) == int(t["pat"][256])
+    assert int(re.search(r"kPngEobLen = (\d+)", src).group(1)) == lengths[256]
+    nbits = int(re.search(r"kPngHeaderBits = (\d+)", src).group(1))
+    words = arr("kPngHeaderWords")
+    assert nbits == len(fix["header_bits"])
+    assert "".join(str((words[i // 32] >> (i % 32)) & 1) for i in range(nbits)) == fix["header_bits"]
+    assert int(re.search(r"kPngMaxLitBits = (\d+)", src).group(1)) == max(lengths[:256])
