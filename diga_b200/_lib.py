@@ -6,6 +6,7 @@ There is no CPU fallback and no alternative backend: if the shared library has n
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -44,6 +45,7 @@ SIGNATURES = {
     "diga_centroid_accum": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "diga_centroid_means": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_centroid_update": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
+    "diga_centroid_update_sharded": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
     "diga_centroid_update_single": (_i, [_p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
     "diga_centroid_reduce_images": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p]),
     "diga_onehot_labels": (_i, [_p, _i64, _i64, _i64, _p, _p]),
@@ -108,13 +110,50 @@ def ptr(t):
 
 
 def stream() -> int:
+    """Raw handle of torch's current stream ON THE CURRENT DEVICE.  Every public wrapper runs under :func:`on_device`, which
+    makes the device of its tensor arguments current first, so this is always a stream of the device the pointers live on."""
     return torch.cuda.current_stream().cuda_stream
 
 
 def require_cuda(*tensors, what="input") -> None:
+    """All given tensors (``None`` skipped) must be CUDA tensors on ONE device."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(f"diga_b200: {what} must be a CUDA tensor (there is no CPU fallback); got {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"diga_b200: {what} tensors live on different devices ({dev} and {t.device})")
+
+
+def _tensor_device(args, kwargs):
+    dev = None
+    for a in (*args, *kwargs.values()):
+        if isinstance(a, (list, tuple)) and a and isinstance(a[0], torch.Tensor):
+            a = a[0]
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError(f"diga_b200: arguments live on different CUDA devices ({dev} and {a.device})")
+    return dev
+
+
+def on_device(fn):
+    """Device guard of the ctypes layer: the kernels are launched on the CURRENT device's current stream, so a wrapper
+    called with tensors of another device (``Class_Features(device='cuda:1')`` while cuda:0 is current) first makes that
+    device current for the duration of the call (``torch.cuda.device``); tensors on two different devices raise."""
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = _tensor_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
 
 
 def f32c(t):

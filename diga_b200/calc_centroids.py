@@ -72,10 +72,18 @@ class Class_Features:
     def feat_dim(self):
         return int(self._objective_vectors.shape[1])
 
+    def _require_state_device(self, t):
+        """The update kernels read the features and write the centroid state in one launch: both must be on one device."""
+        if t.device != self._device:
+            raise RuntimeError(f"Class_Features: the centroids live on {self._device}, the features on {t.device}; "
+                               "construct Class_Features(device=...) on the device that produces the features")
+
     # -- a6 -------------------------------------------------------------------------------------
-    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None):
+    @L.on_device
+    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out=None):
         """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
-        ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy."""
+        ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy.
+        ``out``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
         L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
         feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
         n, d, h, w = feat.shape
@@ -97,9 +105,15 @@ class Class_Features:
         cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
         counts = torch.empty((n, c), dtype=torch.int32, device=dev)
         sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
-        vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
-        vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
-        valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
+        if out is not None:
+            vec, vecsum, valid = out
+            if (tuple(vec.shape), tuple(vecsum.shape), tuple(valid.shape)) != ((n, c, d), (n, c), (n, c)) or \
+                    not (vec.is_contiguous() and vecsum.is_contiguous() and valid.is_contiguous()) or vec.device != dev:
+                raise ValueError(f"out buffers must be contiguous [{n},{c},{d}] / [{n},{c}] / [{n},{c}] tensors on {dev}")
+        else:
+            vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
+            vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
+            valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
         if full is not None:
             L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
                                                        cls.data_ptr(), counts.data_ptr(), st))
@@ -143,15 +157,18 @@ class Class_Features:
         if v.numel() != self.feat_dim:
             raise ValueError(f"vector has {v.numel()} elements, centroids have {self.feat_dim}")
         self._proto_key = None
-        L.check(L.lib.diga_centroid_update_single(v.data_ptr(), int(id), self.class_numbers, self.feat_dim,
-                                                  self._objective_vectors.data_ptr(),
-                                                  self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
-                                                  float(self.centroid_momentum), L.stream()))
+        with torch.cuda.device(self._device):      # the state's device, whatever device is current or held the vector
+            L.check(L.lib.diga_centroid_update_single(v.data_ptr(), int(id), self.class_numbers, self.feat_dim,
+                                                      self._objective_vectors.data_ptr(),
+                                                      self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
+                                                      float(self.centroid_momentum), L.stream()))
 
+    @L.on_device
     def update_from_features(self, feat_cls, outputs, labels_val=None, name='moving_average', start_mean=True, labels_full=None):
         """Fused a6 -> a7 (not in the reference): equals ``calculate_mean_vector`` followed by
         ``update_objective_SingleVector`` on every returned vector in order, with no host sync."""
         mode = self._mode(name)
+        self._require_state_device(feat_cls)
         vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val, labels_full)
         n, c, d = vec.shape
         if d != self.feat_dim:
@@ -161,6 +178,45 @@ class Class_Features:
                                            self._objective_vectors.data_ptr(), self._objective_vectors_num.data_ptr(),
                                            mode, int(bool(start_mean)), float(self.centroid_momentum), L.stream()))
 
+    def _update_sharded(self, gvec, gsum, gvalid, n_total, batch, world, per_shard, name='mean', start_mean=True):
+        """Ordered replay of an all-gathered row buffer (``diga_b200.parallel``): the reference recurrence over the
+        ``n_total`` images of the global loader sequence, rank r holding batches r, r + world, ... of ``batch`` images."""
+        mode = self._mode(name)
+        L.require_cuda(gvec, gsum, gvalid, self._objective_vectors, what="sharded centroid update")
+        c, d = self.class_numbers, self.feat_dim
+        rows = world * per_shard
+        if tuple(gvec.shape) != (rows, c, d) or tuple(gsum.shape) != (rows, c) or tuple(gvalid.shape) != (rows, c):
+            raise ValueError(f"gathered buffers must be [{rows},{c},{d}] / [{rows},{c}] / [{rows},{c}]")
+        self._proto_key = None
+        with torch.cuda.device(self._device):
+            L.check(L.lib.diga_centroid_update_sharded(gvec.data_ptr(), gsum.data_ptr(), gvalid.data_ptr(), int(n_total), int(batch),
+                                                       int(world), int(per_shard), c, d, self._objective_vectors.data_ptr(),
+                                                       self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
+                                                       float(self.centroid_momentum), L.stream()))
+
+    def update_from_features_sharded(self, feat_cls, outputs, labels_val=None, name='moving_average', start_mean=True,
+                                     labels_full=None, group=None):
+        """Multi-rank form of :meth:`update_from_features` for the ONLINE update of the self-training step
+        (self_training.py:327-341): every rank computes the class vectors of its own batch, one all-gather of
+        ``[B, C, D]`` per rank (1.2 MB at B=8, D=2048) exchanges them, and every rank replays the updates in the order
+        rank 0's images, rank 1's images, ... — all ranks keep IDENTICAL centroids, equal to what a single process reaches on
+        the concatenated global batch.  Without an initialised process group this is ``update_from_features``."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.update_from_features(feat_cls, outputs, labels_val, name, start_mean, labels_full)
+        self._mode(name)
+        self._require_state_device(feat_cls)
+        world = dist.get_world_size(group)
+        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val, labels_full)
+        n = vec.shape[0]
+        gathered = []
+        for t in (vec, vecsum, valid):
+            g = torch.empty((world * n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(g, t, group=group)
+            gathered.append(g)
+        self._update_sharded(*gathered, world * n, n, world, n, name, start_mean)
+
+    @L.on_device
     def accumulate_mean_pass(self, acc, feat_cls, outputs, labels_val=None):
         """Multi-GPU 'mean' pass: ``acc [C, D+1]`` += (sum of per-image class means, image count).
         ``diga_b200.parallel.finish_mean_pass`` all-reduces ``acc`` and writes the centroids."""
@@ -172,6 +228,7 @@ class Class_Features:
                                                   acc.data_ptr(), L.stream()))
 
     # -- a5 -------------------------------------------------------------------------------------
+    @L.on_device
     def _proto(self, feat, want_dist, want_weight):
         L.require_cuda(feat, what="Class_Features input")
         f = L.f32c(feat.detach())
@@ -217,6 +274,45 @@ def _labels_on_feature_grid(labels_i64, size):
     return F.interpolate(labels_i64.reshape([b, 1, h, w]).float(), size=tuple(size), mode='nearest')
 
 
+def _sharded_target_pass(class_features, model, target_loader, rank, world, first):
+    """One pass of the target loop (calc_centroids.py:67-78) under ``torchrun``: every rank runs the backbone only on the
+    loader batches ``rank, rank + world, ...`` (all ranks iterate the SAME un-sharded loader, like the reference's), the
+    per-image class vectors are all-gathered once and replayed in loader order (exact mode of ``diga_b200.parallel``): all
+    ranks end the pass with the centroids the single-process loop produces."""
+    from .parallel import ShardedCentroidPass
+    sp = None
+    n_images = len(target_loader.dataset) if hasattr(target_loader, "dataset") else None
+    bsz = getattr(target_loader, "batch_size", None)
+    pending = []
+    for index, batch in enumerate(target_loader):
+        if index % world != rank:
+            continue
+        tdatav = batch[0].cuda()
+        with torch.no_grad():
+            _, _, out, feature_t = model(tdatav)
+            if first:
+                class_features.objective_vectors = torch.zeros([19, feature_t.shape[1]])
+                first = False
+            if sp is None and n_images is not None and bsz:
+                sp = ShardedCentroidPass(class_features, n_images, bsz, 'mean')
+            if sp is not None:
+                sp.add(feature_t, out)
+            else:
+                pending.append(class_features._masked_means(feature_t, out, None))
+    if sp is None:
+        # a loader without len()/batch_size: sizes are only known now; exchange them, then fill the pass buffer
+        sizes = torch.tensor([sum(p[0].shape[0] for p in pending), max([p[0].shape[0] for p in pending] + [0])], device="cuda")
+        tot = sizes.clone()
+        torch.distributed.all_reduce(tot[:1])
+        torch.distributed.all_reduce(sizes[1:], op=torch.distributed.ReduceOp.MAX)
+        if first and int(tot[0]) > 0:
+            raise RuntimeError("calc_centroids: this rank received no batch, cannot infer the feature dimension")
+        sp = ShardedCentroidPass(class_features, int(tot[0]), max(int(sizes[1]), 1), 'mean')
+        for p in pending:
+            sp.add_rows(*p)
+    sp.finish()
+
+
 def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full, target_loader):
     """Reference driver ``calc_centroids.py:17-81``: five passes over the loader, running 'mean' update of the
     class centroids, ``feat_centroids`` written next to ``opt.centroid_dir`` after every pass.
@@ -224,9 +320,15 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
     ``model(x)`` must return ``(_, _, logits, feat)`` like the reference ``SegModel``.  As in the reference the
     target branch is always taken (``opt.source`` is overwritten with ``False``, :27); the source branch is kept
     for completeness (:29-65).  Returns the ``Class_Features`` object (the reference returns ``None``).
+
+    Under ``torchrun`` (an initialised ``torch.distributed`` group of more than one rank) the target loop is image-sharded
+    in the exact mode of ``diga_b200.parallel``: identical ``feat_centroids`` on every rank, bit-equal to the single-process run.
     """
     class_features = Class_Features(numbers=19)
     first = True
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
     for epoch in range(5):
         model.eval(), enc_s.eval(), dec_s2t.eval()
         opt.source = False
@@ -243,6 +345,9 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
                         first = False
                     newlabels = _labels_on_feature_grid(slabelv, out.size()[2:])
                     class_features.update_from_features(feature_s, out, newlabels, 'mean')
+        elif world > 1:
+            _sharded_target_pass(class_features, model, target_loader, rank, world, first)
+            first = False
         else:
             for index, batch in enumerate(target_loader):
                 if index % 100 == 0:
@@ -256,5 +361,6 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
                         first = False
                     class_features.update_from_features(feature_t, out, None, 'mean')
         save_path = os.path.join(os.path.dirname(opt.centroid_dir), "feat_centroids")
-        torch.save(class_features.objective_vectors.cpu(), save_path)
+        if rank == 0:                                       # every rank holds the same tensor; one writer
+            torch.save(class_features.objective_vectors.cpu(), save_path)
     return class_features

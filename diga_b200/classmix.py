@@ -65,6 +65,7 @@ class PresentClasses:
         return self._present
 
 
+@L.on_device
 def present_classes_async(slabel: torch.Tensor) -> PresentClasses:
     """Start the presence pass for ``slabel`` and return its handle (pass it to ``classmix(..., present=handle)``).  Both
     ClassMix blocks of a self-training step use the same ``slabelv`` (:265, :310), so one pass issued when the batch
@@ -72,6 +73,7 @@ def present_classes_async(slabel: torch.Tensor) -> PresentClasses:
     return PresentClasses(slabel)
 
 
+@L.on_device
 def present_classes(slabel: torch.Tensor):
     """Per image, the sorted list of label values present — ``torch.unique(slabel[i]).tolist()`` (:265) — from a
     256-bit device bitmap (32 B per image over PCIe instead of a sort + sync per image)."""
@@ -89,6 +91,7 @@ def select_classes(present, rng=_random):
     return chosen
 
 
+@L.on_device
 def classmix(slabel, a, b, tlabel=None, rng=_random, classes=None, return_mask=True, assume_labelled=False, present=None):
     """ClassMix mask build + blend.
 

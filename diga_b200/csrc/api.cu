@@ -23,6 +23,13 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Index of the current device clamped to [0, 64): key of the per-device caches (cudaFuncSetAttribute is per device).
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 63;
+  return dev;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

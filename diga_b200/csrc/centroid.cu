@@ -478,14 +478,28 @@ __device__ __forceinline__ float rule_apply(const UpdateRule& r, bool mean, floa
   return __fadd_rn(__fmul_rn(obj, r.one_minus_m), __fmul_rn(r.m, v));   // :153-154
 }
 
+// Order in which the rows of vec / vecsum / valid are visited.  Identity (world == 1) for a single process.  For the
+// image-sharded pass (exact mode) the buffer is the all-gather of every rank's rows, [world][per_shard], and
+// rank r holds the loader batches r, r + world, ... (`group` images each): the g-th image of the GLOBAL sequence
+// (calc_centroids.py:67-78 visits images in loader order) sits at row (k % world) * per_shard + (k / world) * group + j
+// with k = g / group, j = g % group.
+struct ImageOrder {
+  int64_t group, world, per_shard;
+};
+__device__ __forceinline__ int64_t order_row(const ImageOrder& o, int64_t g) {
+  if (o.world == 1) return g;
+  const int64_t k = g / o.group, j = g - k * o.group;
+  return (k % o.world) * o.per_shard + (k / o.world) * o.group + j;
+}
+
 // grid (C, ceil(D / BLOCK)): one thread per (class, channel).  The sequential recurrence over images runs in
 // registers (the centroid element is read once and written once); every block of a class replays the same scalar
-// `num` recurrence, block y == 0 stores it.  (A first version with one block per class and global read-modify-writes
+// `num` recurrence.  (A first version with one block per class and global read-modify-writes
 // per image took 37 us for N=8, D=2048 — a third of the accumulation kernel it follows.)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_update_kernel(const float* __restrict__ vec, const float* __restrict__ vecsum, const uint8_t* __restrict__ valid,
-                       int64_t n, int64_t C, int64_t D, float* __restrict__ obj, float* __restrict__ objnum, UpdateRule rule) {
+                       int64_t n, int64_t C, int64_t D, float* __restrict__ obj, const float* __restrict__ objnum, UpdateRule rule) {
   const int64_t c = blockIdx.x;
   const int64_t d = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
   const bool live = d < D;
@@ -503,20 +517,102 @@ centroid_update_kernel(const float* __restrict__ vec, const float* __restrict__ 
   if (live) obj[c * D + d] = o;
 }
 
-// The counts are advanced by a second, tiny launch so that no block of the kernel above can observe a count that
-// another block of the same class has already updated.
-__global__ void centroid_update_num_kernel(const float* __restrict__ vecsum, const uint8_t* __restrict__ valid, int64_t n,
-                                           int64_t C, float* __restrict__ objnum) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Long sequences (a whole pass over the target set: thousands of images, most of them without a valid vector for a
+// given class): the block first compacts, in order, the rows that update class c into a shared-memory list, then walks
+// the list eight rows at a time with the eight loads issued before the eight dependent updates.  The loop above would
+// pay one exposed DRAM latency per image (2975 x 19 x D/256 blocks: milliseconds).
+template <int BLOCK, int CHUNK>
+__global__ void __launch_bounds__(BLOCK)
+centroid_update_long_kernel(const float* __restrict__ vec, const float* __restrict__ vecsum, const uint8_t* __restrict__ valid,
+                            int64_t n, int64_t C, int64_t D, float* __restrict__ obj, const float* __restrict__ objnum,
+                            UpdateRule rule, ImageOrder order) {
+  static_assert(CHUNK % BLOCK == 0, "CHUNK must be a multiple of BLOCK");
+  constexpr int PER = CHUNK / BLOCK;
+  __shared__ int32_t list[CHUNK];
+  __shared__ int warp_tot[BLOCK / 32];
+  const int64_t c = blockIdx.x;
+  const int64_t d = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
+  const bool live = d < D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float num = objnum[c];
-  for (int64_t i = 0; i < n; ++i) {
-    const int64_t nc = i * C + c;
-    if (valid != nullptr && !valid[nc]) continue;
-    if (vecsum[nc] == 0.f) continue;
-    num = fminf(__fadd_rn(num, 1.f), 3000.f);
+  float o = live ? obj[c * D + d] : 0.f;
+  for (int64_t base = 0; base < n; base += CHUNK) {
+    // ordered compaction: thread t owns the PER consecutive sequence positions base + t*PER ..
+    int32_t rows[PER];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int64_t g = base + (int64_t)threadIdx.x * PER + u;
+      rows[u] = -1;
+      if (g < n) {
+        const int64_t r = order_row(order, g);
+        const int64_t nc = r * C + c;
+        if ((valid == nullptr || valid[nc]) && vecsum[nc] != 0.f) {      // :134/:136 skips and :148
+          rows[u] = (int32_t)r;
+          ++mine;
+        }
+      }
+    }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = incl - mine, total = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) {
+      if (w < warp) before += warp_tot[w];
+      total += warp_tot[w];
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (rows[u] >= 0) list[before++] = rows[u];
+    __syncthreads();
+    for (int i = 0; i < total; i += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (live && i + u < total) ? __ldg(vec + ((int64_t)list[i + u] * C + c) * D + d) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (i + u < total) {
+          const bool mean = rule_is_mean(rule, num);
+          o = rule_apply(rule, mean, o, num, v[u]);
+          num = fminf(__fadd_rn(num, 1.f), 3000.f);
+        }
+      }
+    }
+    __syncthreads();          // the list is rebuilt by the next chunk
   }
-  objnum[c] = num;
+  if (live) obj[c * D + d] = o;
+}
+
+// The counts are advanced by a second, tiny launch so that no block of the kernels above can observe a count that
+// another block of the same class has already updated.  One block per class: parallel count of the updating rows,
+// then the `min(num + 1, 3000)` recurrence (:155-156) replayed by one thread, stopping at the clamp.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+centroid_update_num_kernel(const float* __restrict__ vecsum, const uint8_t* __restrict__ valid, int64_t n, int64_t C,
+                           float* __restrict__ objnum) {
+  __shared__ float red[BLOCK / 32];
+  const int64_t c = blockIdx.x;
+  float cnt = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += BLOCK) {
+    const int64_t nc = i * C + c;
+    if ((valid == nullptr || valid[nc]) && vecsum[nc] != 0.f) cnt += 1.f;
+  }
+  const float total = block_sum<BLOCK>(cnt, red);      // integer-valued, exact below 2^24 rows
+  if (threadIdx.x == 0) {
+    float num = objnum[c];
+    for (int64_t k = 0; k < (int64_t)total; ++k) {
+      const float nx = fminf(__fadd_rn(num, 1.f), 3000.f);
+      if (nx == num) break;                            // at the clamp (or beyond fp32's integer range): a fixed point
+      num = nx;
+    }
+    objnum[c] = num;
+  }
 }
 
 template <int BLOCK>
@@ -679,6 +775,30 @@ int diga_centroid_means(const float* sums, const int32_t* counts, int64_t n, int
   return DIGA_OK;
 }
 
+static int launch_centroid_update(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n, int64_t C, int64_t D,
+                                  float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
+                                  diga::ImageOrder order, cudaStream_t st) {
+  using namespace diga;
+  if (n == 0) return DIGA_OK;
+  if (D > 0) {
+    const dim3 grid((unsigned)C, (unsigned)((D + 255) / 256));
+    if (n <= 32 && order.world == 1) {
+      centroid_update_kernel<256><<<grid, 256, 0, st>>>(vec, vecsum, valid, n, C, D, objective_vectors, objective_num,
+                                                        make_rule(mode, start_mean, momentum));
+      DIGA_CHECK_LAUNCH("centroid_update_kernel");
+    } else {
+      centroid_update_long_kernel<256, 1024><<<grid, 256, 0, st>>>(vec, vecsum, valid, n, C, D, objective_vectors, objective_num,
+                                                                   make_rule(mode, start_mean, momentum), order);
+      DIGA_CHECK_LAUNCH("centroid_update_long_kernel");
+    }
+  }
+  // rows outside the visited sequence (padding of a sharded buffer) must not count: the sharded caller zeroes their vecsum
+  const int64_t rows = order.world == 1 ? n : order.world * order.per_shard;
+  centroid_update_num_kernel<256><<<(unsigned)C, 256, 0, st>>>(vecsum, valid, rows, C, objective_num);
+  DIGA_CHECK_LAUNCH("centroid_update_num_kernel");
+  return DIGA_OK;
+}
+
 int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n, int64_t C, int64_t D,
                          float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
                          diga_stream_t stream) {
@@ -686,16 +806,28 @@ int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* v
   DIGA_REQUIRE(vec && vecsum && objective_vectors && objective_num, DIGA_ERR_INVALID, "centroid_update: null pointer");
   DIGA_REQUIRE(mode == DIGA_UPDATE_MEAN || mode == DIGA_UPDATE_MOVING_AVERAGE, DIGA_ERR_INVALID,
                "no such updating way of objective vectors %d", mode);
-  DIGA_REQUIRE(C >= 1 && n >= 0 && D >= 0, DIGA_ERR_INVALID, "centroid_update: bad sizes");
-  if (n == 0) return DIGA_OK;
-  if (D > 0) {
-    centroid_update_kernel<256><<<dim3((unsigned)C, (unsigned)((D + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(
-        vec, vecsum, valid, n, C, D, objective_vectors, objective_num, make_rule(mode, start_mean, momentum));
-    DIGA_CHECK_LAUNCH("centroid_update_kernel");
-  }
-  centroid_update_num_kernel<<<(unsigned)((C + 31) / 32), 32, 0, (cudaStream_t)stream>>>(vecsum, valid, n, C, objective_num);
-  DIGA_CHECK_LAUNCH("centroid_update_num_kernel");
-  return DIGA_OK;
+  DIGA_REQUIRE(C >= 1 && C <= 65535 && n >= 0 && n < (1ll << 31) && D >= 0, DIGA_ERR_INVALID, "centroid_update: bad sizes");
+  return launch_centroid_update(vec, vecsum, valid, n, C, D, objective_vectors, objective_num, mode, start_mean, momentum,
+                                ImageOrder{1, 1, n}, (cudaStream_t)stream);
+}
+
+int diga_centroid_update_sharded(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n_total, int64_t group,
+                                 int64_t world, int64_t per_shard, int64_t C, int64_t D, float* objective_vectors,
+                                 float* objective_num, int mode, int start_mean, double momentum, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(vec && vecsum && objective_vectors && objective_num, DIGA_ERR_INVALID, "centroid_update_sharded: null pointer");
+  DIGA_REQUIRE(mode == DIGA_UPDATE_MEAN || mode == DIGA_UPDATE_MOVING_AVERAGE, DIGA_ERR_INVALID,
+               "no such updating way of objective vectors %d", mode);
+  DIGA_REQUIRE(C >= 1 && C <= 65535 && D >= 0 && n_total >= 0 && group >= 1 && world >= 1 && per_shard >= 0 &&
+                   world * per_shard < (1ll << 31),
+               DIGA_ERR_INVALID, "centroid_update_sharded: bad sizes");
+  // every image of the global sequence must have a row: rank r holds ceil((K - r) / world) batches, K = ceil(n_total / group)
+  const int64_t batches = (n_total + group - 1) / group;
+  DIGA_REQUIRE(((batches + world - 1) / world) * group <= per_shard || n_total == 0, DIGA_ERR_INVALID,
+               "centroid_update_sharded: per_shard=%lld rows cannot hold %lld batches of %lld images over %lld ranks",
+               (long long)per_shard, (long long)batches, (long long)group, (long long)world);
+  return launch_centroid_update(vec, vecsum, valid, n_total, C, D, objective_vectors, objective_num, mode, start_mean, momentum,
+                                ImageOrder{group, world, per_shard}, (cudaStream_t)stream);
 }
 
 int diga_centroid_update_single(const float* vector, int64_t id, int64_t C, int64_t D, float* objective_vectors,

@@ -15,6 +15,7 @@ namespace diga {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+int device_slot();   // current device, clamped to [0, 64): key of per-device launch-configuration caches
 
 #define DIGA_REQUIRE(cond, code, ...)     \
   do {                                    \

@@ -62,10 +62,13 @@ extern "C" int diga_ema_update(float* const* teacher_host, const float* const* s
   DIGA_REQUIRE(count >= 0 && (count == 0 || (teacher_host && student_host && numel_host)), DIGA_ERR_INVALID,
                "ema_update: null table");
   const float a = (float)alpha, oma = (float)(1.0 - alpha);   // Python evaluates (1 - alpha) in double; torch rounds both to fp32
-  for (int64_t first = 0; first < count; first += kEmaTensorsPerLaunch) {
+  // `first` advances to wherever the inner loop stopped: empty tensors are skipped without taking a table slot, so a
+  // fixed stride of kEmaTensorsPerLaunch would visit (and update) the tensors past the stride twice.
+  for (int64_t first = 0; first < count;) {
     EmaTable tab;
     int nt = 0, blocks = 0;
-    for (int64_t i = first; i < count && nt < kEmaTensorsPerLaunch; ++i) {
+    int64_t i = first;
+    for (; i < count && nt < kEmaTensorsPerLaunch; ++i) {
       DIGA_REQUIRE(numel_host[i] >= 0, DIGA_ERR_INVALID, "ema_update: negative size");
       if (numel_host[i] == 0) continue;
       DIGA_REQUIRE(teacher_host[i] && student_host[i], DIGA_ERR_INVALID, "ema_update: null tensor %lld", (long long)i);
@@ -77,6 +80,7 @@ extern "C" int diga_ema_update(float* const* teacher_host, const float* const* s
       blocks += (int)((numel_host[i] + kEmaElemsPerBlock - 1) / kEmaElemsPerBlock);
       ++nt;
     }
+    first = i;
     if (nt == 0) continue;
     tab.block_start[nt] = blocks;
     tab.count = nt;

@@ -426,7 +426,8 @@ extern "C" int diga_png_deflate(const uint8_t* labels, int64_t n, int64_t H, int
   while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
   const size_t smem = (size_t)warps * per_warp;
   DIGA_REQUIRE(smem <= 200 * 1024, DIGA_ERR_INVALID, "png_deflate: W=%lld needs %zu bytes of shared memory", (long long)W, smem);
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {0};            // the attribute is per device
+  size_t& configured = configured_dev[device_slot()];
   if (smem > 48 * 1024 && configured < smem) {
     if (cudaFuncSetAttribute(png_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(png_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -543,7 +543,8 @@ int proto_umma_launch(const float* feat, const float* centroids, int64_t n, int6
     const int rc = proto_umma_prepare(centroids, D, C, workspace, st);
     if (rc != DIGA_OK) return rc;
   }
-  static bool configured = false;
+  static bool configured_dev[64] = {false};          // the attribute is per device
+  bool& configured = configured_dev[device_slot()];
   if (!configured) {
     if (cudaFuncSetAttribute(proto_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();

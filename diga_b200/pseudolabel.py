@@ -25,6 +25,7 @@ CITYSCAPES_PALETTE = [128, 64, 128, 244, 35, 232, 70, 70, 70, 102, 102, 156, 190
 CITYSCAPES_PALETTE = CITYSCAPES_PALETTE + [0] * (256 * 3 - len(CITYSCAPES_PALETTE))
 
 
+@L.on_device
 def pseudo_label(logits, logits_ds=None, want_conf=True, want_int64=False):
     """``logits`` (and optional ``logits_ds``): ``[N,C,H,W]`` fp32.  Returns ``(label uint8 [N,H,W], conf fp32
     [N,H,W] or None)`` (plus an int64 copy of the labels when ``want_int64``).  ``label`` is what the reference
@@ -45,6 +46,7 @@ def pseudo_label(logits, logits_ds=None, want_conf=True, want_int64=False):
     return (lab, conf, lab64) if want_int64 else (lab, conf)
 
 
+@L.on_device
 def pseudo_label_two_scale(logits, logits_ds=None, size=(1024, 2048), want_conf=True):
     """``pseudolabel_generator.py:77-85`` from the stride-8 logits: ``logits [N,C,h1,w1]`` (full-resolution pass)
     and ``logits_ds [N,C,h2,w2]`` (half-resolution pass) are bilinearly up-sampled (align_corners) to ``size``
@@ -92,6 +94,7 @@ def frame_png(idat_payload, height, width, palette=None):
                      _png_chunk(b"IEND", b"")))
 
 
+@L.on_device
 def png_deflate(label_u8):
     """``label_u8 [N,H,W]`` uint8 CUDA tensor -> ``(payload uint8 [N, capacity], lengths int64 [N])``, both on the device:
     ``payload[i, :lengths[i]]`` is image i's complete zlib stream (Up-filtered scanlines, one deflate block with a static Huffman table,
@@ -155,6 +158,7 @@ class PseudoLabelWriter:
                 f.result()                                  # the staging buffers are free again
         return slot
 
+    @L.on_device
     def submit(self, label_u8, names):
         """``label_u8 [N,H,W]`` uint8 CUDA tensor, ``names``: N file names (``name.split('/')[-1]`` is used, :102)."""
         L.require_cuda(label_u8, what="pseudo-label map")

@@ -10,6 +10,7 @@ import torch
 from . import _lib as L
 
 
+@L.on_device
 def consensus_select(pseudo_prob, feat_weights_lowres, out_size=None, want_feat_pseudo=True):
     """``pseudo_prob [B,H,W]`` int64 stored pseudo-labels, ``feat_weights_lowres [B,C,h,w]`` fp32 prototype weights
     (``Class_Features.get_centroid_weight``).  Returns ``(tlabelv_pseudo, feat_pseudo)``, both ``[B,H,W]`` in the dtype of ``pseudo_prob`` (int64, or uint8 for the offline
@@ -33,6 +34,7 @@ def consensus_select(pseudo_prob, feat_weights_lowres, out_size=None, want_feat_
     return kept, fp
 
 
+@L.on_device
 def upsample_bilinear(x, size):
     """``nn.Upsample(size, mode='bilinear', align_corners=True)`` with the interpolation routine the fused kernels
     use (bit-identical to torch's CUDA kernel); exists so that the routine can be tested on its own."""

@@ -56,6 +56,7 @@ def _device_tables(in_size, out_size, device):
     return t
 
 
+@L.on_device
 def resize_remap_labels(src_u8: torch.Tensor, size=None, lut: np.ndarray = None) -> torch.Tensor:
     """``src_u8`` ``[N,h0,w0]`` (or ``[h0,w0]``) uint8 CUDA tensor of decoded PNG values -> int64 ``[N,H,W]``:
     PIL-NEAREST resize to ``size`` = (H, W) (``None``: keep) followed by the 256-entry id look-up."""

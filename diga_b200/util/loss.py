@@ -44,6 +44,7 @@ class _DistillationLoss(torch.autograd.Function):
         return None, ds, None
 
 
+@L.on_device
 def distillation_loss(teacher_out, student_out, scale=0.5):
     """``util.loss.distillation_loss`` (G/util/loss.py:125; default ``scale`` is 0.25 in the Synthia tree).
 
@@ -54,6 +55,7 @@ def distillation_loss(teacher_out, student_out, scale=0.5):
     return _DistillationLoss.apply(teacher_out, student_out, scale)
 
 
+@L.on_device
 def distillation_loss_and_grad(teacher_out, student_out, scale=0.5, grad_scale=1.0):
     """Single-pass variant (not in the reference): returns ``(loss, grad_scale * dloss/dstudent)``.
 
@@ -98,6 +100,7 @@ class _CrossEntropy2d(torch.autograd.Function):
         return dx, None, None, None
 
 
+@L.on_device
 def cross_entropy2d(input, target, weight=None, size_average=True):
     """``util.loss.cross_entropy2d`` (G/util/loss.py:48-62): pixel-wise cross entropy with ``ignore_index=255``;
     pixels with a negative target are dropped; ``size_average`` divides by the number of pixels with target >= 0
@@ -193,6 +196,7 @@ def _check_low(student_low, size, what):
     return hh, ww
 
 
+@L.on_device
 def distillation_loss_upsampled(teacher_low, student_low, size, scale=0.5):
     """``distillation_loss(upsample(teacher_low), upsample(student_low), scale)`` with ``upsample =
     nn.Upsample(size, mode='bilinear', align_corners=True)`` (self_training.py:289,:351-352), neither up-sampled tensor
@@ -205,6 +209,7 @@ def distillation_loss_upsampled(teacher_low, student_low, size, scale=0.5):
     return _LossesUpsampled.apply(teacher_low, student_low, None, None, size, scale, True)[1]
 
 
+@L.on_device
 def cross_entropy2d_upsampled(input_low, target, weight=None, size_average=True):
     """``cross_entropy2d(upsample(input_low), target, weight, size_average)`` with the up-sampling to ``target``'s
     resolution fused (self_training.py:344,:348-349,:355).  ``input_low [N,C,h,w]`` fp32, ``target [N,H,W]`` int64."""
@@ -216,6 +221,7 @@ def cross_entropy2d_upsampled(input_low, target, weight=None, size_average=True)
     return _LossesUpsampled.apply(None, input_low, target, weight, size, 0.0, size_average)[0]
 
 
+@L.on_device
 def seg_distillation_losses_upsampled(teacher_low, student_low, target, scale=0.5, weight=None, size_average=True):
     """The two losses that share ``s_pred_cat_stu`` in the self-training step (self_training.py:348-352) from ONE pass over
     the stride-8 logits: returns ``(cross_entropy2d(upsample(student_low[:B]), target), distillation_loss(upsample(
@@ -229,6 +235,7 @@ def seg_distillation_losses_upsampled(teacher_low, student_low, target, scale=0.
     return _LossesUpsampled.apply(teacher_low, student_low, target, weight, size, scale, size_average)
 
 
+@L.on_device
 def distillation_loss_upsampled_and_grad(teacher_low, student_low, size, scale=0.5, grad_scale=1.0):
     """Single-pass variant: ``(loss, grad_scale * dloss/dstudent_low)`` for call sites that know ``lambda_distil``."""
     L.require_cuda(teacher_low, student_low, what="distillation_loss_upsampled_and_grad input")
@@ -279,6 +286,7 @@ class _SegDistillationTotal(torch.autograd.Function):
         return None, ds * g_total.to(dtype=torch.float32, device=ds.device), None, None, None, None, None, None, None
 
 
+@L.on_device
 def seg_distillation_total_upsampled(teacher_low, student_low, target, lambda_seg=1.0, lambda_distil=0.25, scale=0.5,
                                      weight=None, size_average=True):
     """``total = lambda_seg * seg_loss(upsample(student_low[:B]), target) + lambda_distil * distillation_loss(upsample(
@@ -343,6 +351,7 @@ class OhemCrossEntropy(torch.nn.Module):
         self.ignore_label = ignore_label
         self.weight = weight
 
+    @L.on_device
     def forward(self, score, target):
         L.require_cuda(score, target, self.weight, what="OhemCrossEntropy input")
         if score.dim() != 4 or target.dim() != 3 or score.shape[0] != target.shape[0]:

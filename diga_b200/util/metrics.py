@@ -40,10 +40,11 @@ class runningScore(object):
         lt, lp = self._as_labels(label_trues), self._as_labels(label_preds)
         if lt.numel() != lp.numel():
             raise ValueError(f"runningScore.update: {lt.numel()} ground-truth labels vs {lp.numel()} predictions")
-        L.require_cuda(lt, lp, what="runningScore.update input")
-        L.check(L.lib.diga_confusion_matrix(lt.data_ptr(), int(lt.dtype == torch.uint8), lp.data_ptr(),
-                                            int(lp.dtype == torch.uint8), lt.numel(), self.n_classes, self._hist.data_ptr(),
-                                            self._flags.data_ptr(), L.stream()))
+        L.require_cuda(lt, lp, self._hist, what="runningScore.update input")     # one device: the matrix's
+        with torch.cuda.device(self.device):
+            L.check(L.lib.diga_confusion_matrix(lt.data_ptr(), int(lt.dtype == torch.uint8), lp.data_ptr(),
+                                                int(lp.dtype == torch.uint8), lt.numel(), self.n_classes, self._hist.data_ptr(),
+                                                self._flags.data_ptr(), L.stream()))
 
     @property
     def confusion_matrix(self):

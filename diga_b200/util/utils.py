@@ -9,6 +9,7 @@ import torch
 from .. import _lib as L
 
 
+@L.on_device
 def process_label(label, class_numbers=19):
     """``[B,1,H,W]`` float labels -> ``[B,class_numbers+1,H,W]`` fp32 one-hot; ids >= class_numbers go to the
     last channel (G/util/utils.py:158-163; the Synthia tree's default is 16)."""
@@ -22,6 +23,7 @@ def process_label(label, class_numbers=19):
     return out
 
 
+@L.on_device
 def ema_update_tensors(teacher_tensors, student_tensors, alpha):
     """``t = alpha * t + (1 - alpha) * s`` for every pair, in place, up to 512 tensors per kernel launch."""
     ts, ss = list(teacher_tensors), list(student_tensors)

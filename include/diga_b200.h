@@ -132,6 +132,15 @@ int diga_centroid_means(const float* sums, const int32_t* counts, int64_t n, int
 int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n, int64_t C,
                          int64_t D, float* objective_vectors, float* objective_num, int mode, int start_mean,
                          double momentum, diga_stream_t stream);
+/* Image-sharded exact replay (calc_centroids.py:20-23,67-78,147-164): vec/vecsum/valid are the all-gather
+ * of every rank's rows, [world][per_shard] x C (x D); rank r holds loader batches r, r+world, ... of `group` images each.
+ * The n_total images are visited in GLOBAL loader order (image g = batch g/group, position g%group), so every rank
+ * reproduces the single-process sequence bit for bit, beyond the 3000 clamp and across passes.  Rows that no image maps to
+ * (padding of the shorter shards) must carry vecsum == 0. */
+int diga_centroid_update_sharded(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n_total,
+                                 int64_t group, int64_t world, int64_t per_shard, int64_t C, int64_t D,
+                                 float* objective_vectors, float* objective_num, int mode, int start_mean,
+                                 double momentum, diga_stream_t stream);
 /* single vector form (the reference's per-call API): class `id`, vector [D]. */
 int diga_centroid_update_single(const float* vector, int64_t id, int64_t C, int64_t D, float* objective_vectors,
                                 float* objective_num, int mode, int start_mean, double momentum,

@@ -1,12 +1,12 @@
-"""Import the *real* reference functions from ``/root/reference`` (build container only).
+"""Import the *real* reference functions: from ``$DIGA_REF``, ``/root/reference`` (build container) or the git-ignored
+staging copy ``baseline/_ref/`` that ``oracle/make_ref.py`` writes and ``gpurun`` ships to the GPU box.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/diga_oracle.py``).  The reference tree does not exist on
-the GPU box and its sources are never copied into this repo, so this loader is used for two
-things that both happen here, in the build container:
+TEST / BENCH INFRASTRUCTURE ONLY (see ``oracle/diga_oracle.py``).  Reference sources are never tracked by this repo and
+never imported by ``diga_b200/``.  Users:
 
-* ``tests/golden/make_golden.py`` — generate the committed golden fixtures;
-* ``tests/test_oracle_golden.py`` — pin ``diga_oracle`` against the live reference (skipped when
-  ``/root/reference`` is absent).
+* ``tests/golden/make_golden.py`` — generate the committed golden fixtures (build container);
+* ``tests/test_oracle_golden.py`` — pin ``diga_oracle`` against the live reference (skipped when no tree is found);
+* ``bench.py --impl reference`` / ``cpu_baseline`` — time the reference's own CPU implementation (``kind: "reference"``).
 
 Shims: the reference imports ``kornia`` and ``matplotlib`` at module
 top (unused by the hot path) and hard-codes ``.cuda()``; on a CUDA-less host that call is made a
@@ -20,11 +20,24 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("DIGA_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
 TREES = {
     "G": "domain_adaptation/GTA5",
     "S": "domain_adaptation/Synthia",
 }
+
+
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("DIGA_REF"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, TREES["G"], "calc_centroids.py")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available(tree: str = "G") -> bool:

@@ -455,7 +455,9 @@ def test_proto_golden(D, golden, name):
 
 
 @pytest.mark.parametrize("n,d,h,w,c", [(2, 2048, 65, 129, 19), (1, 256, 65, 113, 19), (3, 512, 33, 65, 16),
-                                       (1, 2048, 16, 128, 19), (1, 100, 7, 5, 19), (2, 256, 64, 128, 19)])
+                                       (1, 2048, 16, 128, 19), (1, 100, 7, 5, 19), (2, 256, 64, 128, 19),
+                                       (1, 2048, 129, 257, 19), (1, 256, 129, 257, 19),      # BASELINE config 5: one image
+                                       (2, 2048, 129, 257, 19)])                             # ... and the pair the writer batches
 def test_proto_vs_oracle(D, n, d, h, w, c):
     from diga_b200 import synthetic as S
     g = S.gen(17, "cuda")

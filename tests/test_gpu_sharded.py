@@ -1,0 +1,412 @@
+"""GPU parity of the multi-GPU centroid path and of the BASELINE config shapes round 1 left untested.
+
+* sum mode  : ``accumulate_mean_pass`` (``diga_centroid_reduce_images``) + ``finish_mean_pass`` vs the sequential reference
+  loop (calc_centroids.py:67-78, :147-164) restated by ``oracle.centroid_pass``;
+* exact mode: ``ShardedCentroidPass`` / ``diga_centroid_update_sharded`` — the all-gathered row buffer of W "virtual ranks"
+  built on one GPU must replay to the bits of the sequential single-process update, beyond the 3000 clamp and over several
+  passes; the real 2-rank NCCL run of both modes is spawned through ``torch.distributed.run`` when two GPUs are visible;
+* config shapes: a5 at [1,2048,129,257] / [1,256,129,257], a6 at [1,2048,65,129], u8 consensus selection at
+  129x257 -> 1024x2048 against the GPU-eager oracle, KD at the reference's own [6,19,512,896].
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import diga_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-5
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def assert_normwise(got, want, rtol=RTOL, what=""):
+    got, want = got.detach().double().cpu(), torch.as_tensor(want).detach().double().cpu()
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    assert err <= rtol * max(scale, 1e-30), f"{what}: max|diff| {err:.3e} > {rtol} * max|ref| {scale:.3e}"
+
+
+def assert_rel(got, want, rtol=RTOL, what=""):
+    got, want = float(got), float(want)
+    assert abs(got - want) <= rtol * abs(want), f"{what}: {got!r} vs {want!r}"
+
+
+@pytest.fixture(scope="module")
+def D():
+    import diga_b200
+    return diga_b200
+
+
+def _inputs(n, d, h, w, c, g, labels=False, boost=2.0):
+    from diga_b200 import synthetic as S
+    feat = S.features((n, d, h, w), g)
+    out = S.logits((n, c, h, w), g)
+    out[:, : max(2, c // 3)] += boost
+    lab = None
+    if labels:
+        lab = out.argmax(1, keepdim=True).float()
+        flip = torch.rand((n, 1, h, w), generator=g, device=g.device) < 0.3
+        lab[flip] = 255.0
+    return feat, out, lab
+
+
+def _oracle_pass(batches, c, d, cf=None):
+    """calc_centroids.py:67-78 over in-memory batches with optional labels (oracle evaluated where the tensors live)."""
+    cf = cf or O.ClassFeaturesOracle(c, d)
+    for feat, out, lab in batches:
+        vectors, ids = cf.calculate_mean_vector(feat, out, lab)
+        for v, i in zip(vectors, ids):
+            cf.update_objective_SingleVector(i, v.detach().cpu().numpy(), "mean")
+    return cf
+
+
+# ------------------------------------------------------------------------------------------------ sum mode (one all-reduce)
+@pytest.mark.parametrize("n,d,h,w,labels", [(8, 2048, 65, 129, False), (1, 2048, 65, 129, False), (3, 256, 65, 113, True),
+                                            (2, 64, 9, 11, True)])
+def test_mean_pass_sum_mode_vs_sequential_oracle(D, n, d, h, w, labels):
+    """accumulate_mean_pass over several batches + finish_mean_pass == the reference's sequential 'mean' updates."""
+    from diga_b200 import parallel as P, synthetic as S
+    g = S.gen(99, "cuda")
+    c = 19
+    batches = [_inputs(n, d, h, w, c, g, labels) for _ in range(3)]
+    cf = D.Class_Features(c, d)
+    acc = P.new_mean_accumulator(c, d, dev())
+    for feat, out, lab in batches:
+        cf.accumulate_mean_pass(acc, feat, out, lab)
+    vectors, num = P.finish_mean_pass(acc)
+    ref = _oracle_pass(batches, c, d)
+    assert torch.equal(num.cpu(), ref.objective_vectors_num)
+    for k in range(c):
+        assert_normwise(vectors[k], ref.objective_vectors[k], what=f"centroid {k}")
+    # with the Class_Features handle the result is written back and a second pass continues from it (num + n <= 3000: exact)
+    cf2 = D.Class_Features(c, d)
+    for half in (batches[:1], batches[1:]):
+        acc.zero_()
+        for feat, out, lab in half:
+            cf2.accumulate_mean_pass(acc, feat, out, lab)
+        P.finish_mean_pass(acc, cf2)
+    assert torch.equal(cf2.objective_vectors_num.cpu(), ref.objective_vectors_num)
+    for k in range(c):
+        assert_normwise(cf2.objective_vectors[k], ref.objective_vectors[k], what=f"continued centroid {k}")
+
+
+def test_mean_pass_all_invalid_image_and_zero_sum_vector(D):
+    """An image whose labels gate every pixel out contributes nothing; a class whose mean vector sums to exactly zero is
+    skipped (calc_centroids.py:148) and does not advance the count."""
+    from diga_b200 import parallel as P, synthetic as S
+    g = S.gen(5, "cuda")
+    n, d, h, w, c = 3, 64, 17, 19, 19
+    feat, out, lab = _inputs(n, d, h, w, c, g, labels=True)
+    lab[1] = 255.0                                             # image 1: nothing survives the label gate
+    am = out.argmax(1)
+    feat[0].masked_fill_((am[0] == 2).unsqueeze(0), 0.0)       # image 0, class 2: every selected feature is 0 -> vector sum 0
+    assert int(((am[0] == 2) & (lab[0, 0] == 2)).sum()) >= 5
+    cf = D.Class_Features(c, d)
+    acc = P.new_mean_accumulator(c, d, dev())
+    cf.accumulate_mean_pass(acc, feat, out, lab)
+    vectors, num = P.finish_mean_pass(acc)
+    ref = _oracle_pass([(feat, out, lab)], c, d)
+    assert torch.equal(num.cpu(), ref.objective_vectors_num)
+    for k in range(c):
+        assert_normwise(vectors[k], ref.objective_vectors[k], what=f"centroid {k}")
+    _, ids = cf.calculate_mean_vector(feat[1:2], out[1:2], lab[1:2])
+    assert ids == []
+
+
+# ------------------------------------------------------------------------------------------------ exact mode
+def _sequential(D, batches, c, d, passes, name="mean", start_mean=True, start=None):
+    cf = D.Class_Features(c, d)
+    if start is not None:
+        cf.objective_vectors, cf.objective_vectors_num = start[0].clone(), start[1].clone()
+    for _ in range(passes):
+        for feat, out, lab in batches:
+            cf.update_from_features(feat, out, lab, name, start_mean)
+    return cf
+
+
+@pytest.mark.parametrize("world,batch,n_images", [(1, 1, 37), (2, 1, 37), (8, 1, 37), (4, 3, 37), (8, 8, 30), (3, 2, 5)])
+def test_sharded_replay_equals_sequential_bitwise(D, world, batch, n_images):
+    """W virtual ranks fill their own ShardedCentroidPass buffers (batches[r::W]); the concatenation of the buffers is what
+    the all-gather delivers; diga_centroid_update_sharded over it must equal the sequential update BIT FOR BIT."""
+    from diga_b200 import parallel as P, synthetic as S
+    g = S.gen(2024, "cuda")
+    c, d, h, w = 19, 96, 9, 13
+    nb = -(-n_images // batch)
+    batches = [_inputs(min(batch, n_images - k * batch), d, h, w, c, g, labels=(k % 2 == 0)) for k in range(nb)]
+    seq = _sequential(D, batches, c, d, passes=2)
+    cf = D.Class_Features(c, d)
+    shards = []
+    for r in range(world):
+        # a virtual rank: the same buffers a real rank r of `world` would fill
+        shards.append(P.ShardedCentroidPass(cf, n_images, batch, rank=r, world=world))
+    for _ in range(2):
+        for sp in shards:
+            assert list(sp.my_batches()) == P.shard_indices(nb, sp.rank, world)
+            for k in sp.my_batches():
+                sp.add(*batches[k][:2], batches[k][2])
+        per = shards[0].per_shard
+        gathered = [torch.cat([getattr(sp, name) for sp in shards]) for name in ("vec", "vecsum", "valid")]
+        cf._update_sharded(*gathered, n_images, batch, world, max(per, 1), "mean", True)
+        for sp in shards:
+            sp.reset()
+    assert torch.equal(cf.objective_vectors_num, seq.objective_vectors_num)
+    assert torch.equal(cf.objective_vectors, seq.objective_vectors), "sharded replay differs from the sequential update"
+    # the host mirror of the device row order
+    rows = P.global_row_order(n_images, batch, world, max(per, 1))
+    assert len(set(rows)) == n_images and max(rows) < world * max(per, 1)
+
+
+def test_exact_mode_beyond_clamp_five_passes_vs_oracle(D):
+    """The reference runs 5 passes (calc_centroids.py:20-23) and clamps the count at 3000 (:156,:161): after the clamp the
+    'mean' update is an order-dependent recursion.  Exact mode must track the sequential oracle through it; sum mode is the
+    documented approximation (its error against the exact result is reported, and must be small but non-zero)."""
+    from diga_b200 import parallel as P, synthetic as S
+    g = S.gen(7, "cuda")
+    c, d, h, w, n_img = 19, 32, 6, 8, 640
+    feats = S.features((n_img, d, h, w), g)
+    outs = S.logits((n_img, c, h, w), g)
+    outs[:, :3] += 4.0                                                   # classes 0..2 are valid in (nearly) every image
+    cf = D.Class_Features(c, d)
+    sp = P.ShardedCentroidPass(cf, n_img, batch=8)
+    cf_sum = D.Class_Features(c, d)
+    acc = P.new_mean_accumulator(c, d, dev())
+    ref = O.ClassFeaturesOracle(c, d)
+    for _ in range(5):
+        acc.zero_()
+        for k in sp.my_batches():
+            sl = slice(8 * k, 8 * k + 8)
+            sp.add(feats[sl], outs[sl])
+            cf_sum.accumulate_mean_pass(acc, feats[sl], outs[sl])
+        sp.finish()
+        P.finish_mean_pass(acc, cf_sum)
+        ref = O.centroid_pass([feats], [outs], c, d, cf=ref)             # one call = all images in order
+    assert ref.objective_vectors_num.max().item() == 3000.0              # the clamp was reached (5 x 640 > 3000)
+    assert torch.equal(cf.objective_vectors_num.cpu(), ref.objective_vectors_num)
+    for k in range(c):
+        assert_normwise(cf.objective_vectors[k], ref.objective_vectors[k], what=f"exact-mode centroid {k} after 5 passes")
+    # and bit-equal to the sequential device update
+    seq = _sequential(D, [(feats[8 * k:8 * k + 8], outs[8 * k:8 * k + 8], None) for k in range(n_img // 8)], c, d, passes=5)
+    assert torch.equal(cf.objective_vectors, seq.objective_vectors) and torch.equal(cf.objective_vectors_num, seq.objective_vectors_num)
+    # sum mode: same counts, vectors close (uniform instead of recency weights beyond the clamp)
+    assert torch.equal(cf_sum.objective_vectors_num, cf.objective_vectors_num)
+    err = (cf_sum.objective_vectors - cf.objective_vectors).abs().max().item() / cf.objective_vectors.abs().max().item()
+    assert err < 5e-2, f"sum-mode approximation error {err:.3e}"
+
+
+def test_online_sharded_update_without_process_group_is_the_plain_update(D):
+    from diga_b200 import synthetic as S
+    g = S.gen(11, "cuda")
+    feat, out, lab = _inputs(2, 64, 9, 11, 19, g, labels=True)
+    a, b = D.Class_Features(19, 64), D.Class_Features(19, 64)
+    a.update_from_features(feat, out, lab, "moving_average", True)
+    b.update_from_features_sharded(feat, out, lab, "moving_average", True)
+    assert torch.equal(a.objective_vectors, b.objective_vectors) and torch.equal(a.objective_vectors_num, b.objective_vectors_num)
+
+
+def test_long_update_kernel_matches_short_kernel(D):
+    """n > 32 images per call takes the list-compaction kernel; it must agree bit for bit with 1-image calls (EMA mode with
+    start_mean: the rule switches from 'mean' to EMA at num == 100 inside the sequence)."""
+    from diga_b200 import synthetic as S
+    g = S.gen(3, "cuda")
+    n, d, h, w, c = 150, 48, 5, 7, 19
+    feat, out, _ = _inputs(n, d, h, w, c, g)
+    one = D.Class_Features(c, d)
+    for i in range(n):
+        one.update_from_features(feat[i:i + 1], out[i:i + 1], None, "moving_average", True)
+    many = D.Class_Features(c, d)
+    many.update_from_features(feat, out, None, "moving_average", True)
+    assert one.objective_vectors_num.max().item() > 100
+    assert torch.equal(one.objective_vectors_num, many.objective_vectors_num)
+    assert torch.equal(one.objective_vectors, many.objective_vectors)
+
+
+NCCL_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+import diga_b200 as D
+from diga_b200 import parallel as P, synthetic as S
+from oracle import diga_oracle as O
+c, d, h, w, n_img, batch = 19, 256, 33, 65, 46, 4
+g = S.gen(77, dev)                                   # same seed on every rank: every rank can see the whole synthetic set
+nb = -(-n_img // batch)
+feats = [S.features((min(batch, n_img - k * batch), d, h, w), g) for k in range(nb)]
+outs = [S.logits((f.shape[0], c, h, w), g) for f in feats]
+for o in outs: o[:, :6] += 3
+# single-rank sequential oracle over the union (the reference loop, calc_centroids.py:67-78, :157-161)
+ref = O.ClassFeaturesOracle(c, d)
+for _ in range(2):
+    ref = O.centroid_pass(feats, outs, c, d, cf=ref)
+# exact mode, two passes
+cf = D.Class_Features(c, d)
+sp = P.ShardedCentroidPass(cf, n_img, batch)
+for _ in range(2):
+    for k in sp.my_batches():
+        sp.add(feats[k], outs[k])
+    sp.finish()
+num = cf.objective_vectors_num.cpu()
+assert torch.equal(num, ref.objective_vectors_num), (num, ref.objective_vectors_num)
+err = (cf.objective_vectors.cpu() - ref.objective_vectors).abs().max().item()
+scale = ref.objective_vectors.abs().max().item()
+assert err <= 1e-5 * scale, ("exact", err, scale)
+# ... and bit-equal to the sequential device path, and identical on all ranks
+seq = D.Class_Features(c, d)
+for _ in range(2):
+    for f, o in zip(feats, outs):
+        seq.update_from_features(f, o, None, "mean")
+assert torch.equal(seq.objective_vectors, cf.objective_vectors)
+other = [torch.empty_like(cf.objective_vectors) for _ in range(world)]
+dist.all_gather(other, cf.objective_vectors)
+assert all(torch.equal(o, other[0]) for o in other)
+# sum mode, first pass from empty centroids: exact below the clamp
+cf2 = D.Class_Features(c, d)
+acc = P.new_mean_accumulator(c, d, dev)
+for k in P.shard_indices(nb, rank, world):
+    cf2.accumulate_mean_pass(acc, feats[k], outs[k])
+vectors, num2 = P.finish_mean_pass(acc, cf2)
+ref1 = O.centroid_pass(feats, outs, c, d)
+assert torch.equal(num2.cpu(), ref1.objective_vectors_num)
+err = (vectors.cpu() - ref1.objective_vectors).abs().max().item()
+assert err <= 1e-5 * ref1.objective_vectors.abs().max().item(), ("sum", err)
+# online EMA, sharded: every rank's own batch, replayed rank-major on all ranks == one process over the concatenated batch
+gl = S.gen(500 + rank, dev)
+f_r, o_r = S.features((2, d, h, w), gl), S.logits((2, c, h, w), gl)
+cf3 = D.Class_Features(c, d)
+cf3.objective_vectors, cf3.objective_vectors_num = ref.objective_vectors.clone(), torch.full((c,), 150.0)
+cf3.update_from_features_sharded(f_r, o_r, None, "moving_average", False)
+fs, os_ = [torch.empty_like(f_r) for _ in range(world)], [torch.empty_like(o_r) for _ in range(world)]
+dist.all_gather(fs, f_r); dist.all_gather(os_, o_r)
+one = D.Class_Features(c, d)
+one.objective_vectors, one.objective_vectors_num = ref.objective_vectors.clone(), torch.full((c,), 150.0)
+one.update_from_features(torch.cat(fs), torch.cat(os_), None, "moving_average", False)
+assert torch.equal(one.objective_vectors, cf3.objective_vectors) and torch.equal(one.objective_vectors_num, cf3.objective_vectors_num)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+@pytest.mark.parametrize("world", [2])
+def test_two_rank_nccl_exact_and_sum_modes(tmp_path, world):
+    """Real NCCL run: `world` ranks over disjoint shards == the single-rank sequential oracle (counts equal, vectors 1e-5;
+    exact mode bit-equal to the sequential device path).  Needs `world` visible GPUs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(NCCL_WORKER)
+    port = 29700 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-4000:]
+    assert res.stdout.count("ok") >= world
+
+
+def test_device_guard_non_current_device(D):
+    """Tensors on cuda:1 while cuda:0 is current: the wrappers switch to the tensors' device for the call."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from diga_b200 import synthetic as S
+    d1 = torch.device("cuda", 1)
+    g = S.gen(1, d1)
+    assert torch.cuda.current_device() == 0
+    t, s = S.logits((2, 19, 16, 24), g), S.logits((2, 19, 16, 24), g)
+    so = s.clone().requires_grad_(True)
+    lo = O.distillation_loss(t, so)
+    lo.backward()
+    sg = s.clone().requires_grad_(True)
+    lg = D.distillation_loss(t, sg)
+    lg.backward()
+    assert lg.device == d1 and torch.cuda.current_device() == 0
+    assert_rel(lg.item(), lo.item())
+    assert_normwise(sg.grad, so.grad)
+    cf = D.Class_Features(19, 64, device=d1)
+    feat, out, _ = _inputs(2, 64, 9, 11, 19, g)
+    cf.update_from_features(feat, out, None, "mean")
+    ref = _oracle_pass([(feat, out, None)], 19, 64)
+    assert torch.equal(cf.objective_vectors_num.cpu(), ref.objective_vectors_num)
+    with pytest.raises(RuntimeError):
+        D.distillation_loss(t, s.to("cuda:0"))
+    with pytest.raises(RuntimeError):
+        D.Class_Features(19, 64).update_from_features(feat, out, None, "mean")      # state on cuda:0, features on cuda:1
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config shapes
+def test_kd_reference_shape_6x19x512x896(D):
+    """The reference's own training shape (B=3 per view at 512x896); oracle = its op chain on the GPU."""
+    from diga_b200 import synthetic as S
+    g = S.gen(6, "cuda")
+    t, s = S.logits((6, 19, 512, 896), g), S.logits((6, 19, 512, 896), g)
+    so = s.clone().requires_grad_(True)
+    lo = O.distillation_loss(t, so, 0.5)
+    (lo * 0.25).backward()
+    sg = s.clone().requires_grad_(True)
+    lg = D.distillation_loss(t, sg, 0.5)
+    (lg * 0.25).backward()
+    assert_rel(lg.item(), lo.item(), what="loss")
+    assert_normwise(sg.grad, so.grad, what="grad")
+    assert_normwise(sg.grad, O.distillation_grad_closed_form(t, s, 0.5, 0.25), what="grad vs fp64 closed form")
+
+
+@pytest.mark.parametrize("n,d,h,w", [(1, 2048, 65, 129), (8, 2048, 65, 129)])
+def test_centroid_pass_config4_shape(D, n, d, h, w):
+    """a6 + a7 at config 4's shape; the oracle runs on the GPU tensors (same op chain the reference would run there)."""
+    from diga_b200 import synthetic as S
+    g = S.gen(44, "cuda")
+    c = 19
+    batches = [_inputs(n, d, h, w, c, g) for _ in range(2)]
+    gcf = D.Class_Features(c, d)
+    ref = O.ClassFeaturesOracle(c, d)
+    for feat, out, _ in batches:
+        vec, ids = ref.calculate_mean_vector(feat, out)
+        gvec, gids = gcf.calculate_mean_vector(feat, out)
+        assert gids == ids
+        for a, b in zip(gvec, vec):
+            assert_normwise(a.reshape(-1), b.reshape(-1), what="mean vector")
+        for v, i in zip(vec, ids):
+            ref.update_objective_SingleVector(i, v.detach().cpu().numpy(), "mean")
+        gcf.update_from_features(feat, out, None, "mean")
+    assert torch.equal(gcf.objective_vectors_num.cpu(), ref.objective_vectors_num)
+    for k in range(c):
+        assert_normwise(gcf.objective_vectors[k], ref.objective_vectors[k], what=f"centroid {k}")
+
+
+def test_consensus_select_uint8_vs_gpu_eager_oracle(D):
+    """The uint8 kernel (config 5 and the PNG stage) against the reference op chain on the GPU — not against the int64
+    kernel — at 129x257 -> 1024x2048 and at an odd geometry."""
+    from diga_b200 import synthetic as S
+    g = S.gen(31, "cuda")
+    for b, c, lo, hi in ((1, 19, (129, 257), (1024, 2048)), (2, 19, (65, 129), (512, 1024)), (1, 16, (9, 13), (37, 53))):
+        wl = torch.softmax(S.logits((b, c, *lo), g), 1)
+        pl = S.block_labels(b, hi[0], hi[1], g, 16, c)
+        kept_o, fp_o = O.consensus_select(pl, wl, hi)
+        k8, f8 = D.consensus_select(pl.to(torch.uint8), wl)
+        assert k8.dtype == torch.uint8 and f8.dtype == torch.uint8
+        assert int((f8.long() != fp_o).sum()) == 0, "u8 feat_pseudo differs from the GPU eager reference"
+        assert torch.equal(k8.long(), kept_o)
+
+
+def test_ema_more_than_512_tensors_with_empty_ones(D):
+    """> 512 tensors with empty ones in between: every tensor is updated exactly once."""
+    from diga_b200.util.utils import ema_update_tensors
+    g = torch.Generator().manual_seed(5)
+    sizes = ([0, 5, 0, 130, 7] * 130)[:640]
+    ts = [torch.randn(n, generator=g) for n in sizes]
+    ss = [torch.randn(n, generator=g) for n in sizes]
+    alpha = 0.999
+    want = [alpha * t + (1 - alpha) * s for t, s in zip(ts, ss)]
+    tg, sg = [t.to(dev()) for t in ts], [s.to(dev()) for s in ss]
+    ema_update_tensors(tg, sg, alpha)
+    for a, b in zip(tg, want):
+        assert np.array_equal(a.cpu().numpy().view(np.uint32), b.numpy().view(np.uint32))

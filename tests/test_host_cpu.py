@@ -126,6 +126,85 @@ print("rank", rank, "ok")
 '''
 
 
+WORKER_EXACT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from diga_b200.parallel import ShardedCentroidPass, global_row_order, finish_mean_pass, new_mean_accumulator
+from oracle import diga_oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+C, Dm, n_img, batch = 19, 12, 23, 3
+g = torch.Generator().manual_seed(1)
+nb = -(-n_img // batch)
+feats = [torch.randn((min(batch, n_img - k * batch), Dm, 6, 7), generator=g) for k in range(nb)]
+outs = [3 * torch.randn((f.shape[0], C, 6, 7), generator=g) for f in feats]
+for o in outs: o[:, :4] += 3
+
+def rows_of(cf, feat, out):
+    """what the a6 kernels deliver per image: vec [n,C,D], vecsum [n,C], valid [n,C] (CPU oracle stands in for them)"""
+    n = feat.shape[0]
+    vec, vs, ok = torch.zeros(n, C, Dm), torch.zeros(n, C), torch.zeros(n, C, dtype=torch.uint8)
+    for i in range(n):
+        vectors, ids = cf.calculate_mean_vector(feat[i:i + 1], out[i:i + 1])
+        for v, t in zip(vectors, ids):
+            vec[i, t], vs[i, t], ok[i, t] = v.reshape(-1), v.sum(), 1
+    return vec, vs, ok
+
+ref = O.ClassFeaturesOracle(C, Dm)                    # the single-process loop over the union, three passes, low clamp
+state = O.ClassFeaturesOracle(C, Dm)
+sp = ShardedCentroidPass(state, n_img, batch)
+assert (sp.rank, sp.world) == (rank, world)
+for _ in range(3):
+    ref = O.centroid_pass(feats, outs, C, Dm, cf=ref)
+    for k in sp.my_batches():
+        sp.add_rows(*rows_of(state, feats[k], outs[k]))
+    gvec, gsum, gvalid = sp.gather()                   # the exchange under test (all_gather_into_tensor over gloo)
+    for r in global_row_order(n_img, batch, world, sp.per_shard):     # the replay order the device kernel uses
+        for t in range(C):
+            if gvalid[r, t]:
+                state.update_objective_SingleVector(t, gvec[r, t].numpy(), "mean")
+    sp.reset()
+assert torch.equal(state.objective_vectors_num, ref.objective_vectors_num)
+assert torch.equal(state.objective_vectors, ref.objective_vectors), "ordered replay of the gathered rows != sequential loop"
+
+# sum mode continued from a state and across the clamp: finish_mean_pass(acc, cf) == closed form of its documented rule
+class St: pass
+st = St(); st.objective_vectors = torch.ones(C, Dm); st.objective_vectors_num = torch.full((C,), 2990.0)
+acc = new_mean_accumulator(C, Dm, "cpu")
+acc[:, :Dm] = 10.0 * (rank + 1); acc[:, Dm] = 10.0            # each rank: 10 vectors per class whose sum is 10*(rank+1)
+vec, num = finish_mean_pass(acc, st)
+n = 10.0 * world; mean = sum(10.0 * (r + 1) for r in range(world)) / n
+m = 10.0; k = n - m
+obj1 = (1.0 * 2990.0 + mean * m) / 3000.0
+rho = (3000.0 / 3001.0) ** k
+want = obj1 * rho + (1 - rho) * mean
+assert torch.allclose(vec, torch.full((C, Dm), want), rtol=1e-6), (vec[0, 0].item(), want)
+assert torch.equal(num, torch.full((C,), 3000.0)) and st.objective_vectors is vec
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exact_mode_gather_and_order_gloo(tmp_path, world):
+    """Exact mode host logic on CPU ranks: shard assignment, all-gather of the row buffers, global replay order —
+    N ranks == the sequential single-process loop bit for bit over three passes; plus the documented rule of the sum mode
+    when it continues from a state across the 3000 clamp."""
+    script = tmp_path / "worker_exact.py"
+    script.write_text(WORKER_EXACT)
+    port = 29900 + (os.getpid() % 90) + world
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
 def test_mean_pass_allreduce_world2_gloo(tmp_path):
     """N ranks over disjoint image shards + one all-reduce == the sequential single-rank running mean."""
     script = tmp_path / "worker.py"
