@@ -80,10 +80,10 @@ class Class_Features:
 
     # -- a6 -------------------------------------------------------------------------------------
     @L.on_device
-    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out=None):
+    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out_rows=None):
         """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
         ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy.
-        ``out``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
+        ``out_rows``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
         L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
         feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
         n, d, h, w = feat.shape
@@ -105,11 +105,11 @@ class Class_Features:
         cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
         counts = torch.empty((n, c), dtype=torch.int32, device=dev)
         sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
-        if out is not None:
-            vec, vecsum, valid = out
+        if out_rows is not None:
+            vec, vecsum, valid = out_rows
             if (tuple(vec.shape), tuple(vecsum.shape), tuple(valid.shape)) != ((n, c, d), (n, c), (n, c)) or \
                     not (vec.is_contiguous() and vecsum.is_contiguous() and valid.is_contiguous()) or vec.device != dev:
-                raise ValueError(f"out buffers must be contiguous [{n},{c},{d}] / [{n},{c}] / [{n},{c}] tensors on {dev}")
+                raise ValueError(f"out_rows buffers must be contiguous [{n},{c},{d}] / [{n},{c}] / [{n},{c}] tensors on {dev}")
         else:
             vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
             vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)

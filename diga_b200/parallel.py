@@ -154,7 +154,7 @@ class ShardedCentroidPass:
         """a6 of this rank's next batch (``calculate_mean_vector``, calc_centroids.py:120-145), written straight into the
         pass buffer; no host sync."""
         rows = self._next_rows(feat_cls.shape[0])
-        self.cf._masked_means(feat_cls, outputs, labels_val, labels_full, out=(self.vec[rows], self.vecsum[rows], self.valid[rows]))
+        self.cf._masked_means(feat_cls, outputs, labels_val, labels_full, out_rows=(self.vec[rows], self.vecsum[rows], self.valid[rows]))
 
     def gather(self):
         """The exchange: all-gather of the three row buffers -> ``[world * per_shard, ...]`` on every rank."""

@@ -213,17 +213,25 @@ def test_online_sharded_update_without_process_group_is_the_plain_update(D):
 
 
 def test_long_update_kernel_matches_short_kernel(D):
-    """n > 32 images per call takes the list-compaction kernel; it must agree bit for bit with 1-image calls (EMA mode with
-    start_mean: the rule switches from 'mean' to EMA at num == 100 inside the sequence)."""
-    from diga_b200 import synthetic as S
+    """n > 32 rows per call takes the list-compaction kernel; on the SAME per-image vectors it must agree bit for bit with
+    one-row calls of the short kernel (EMA mode with start_mean: the rule switches from 'mean' to EMA at num == 100 inside
+    the sequence)."""
+    from diga_b200 import _lib as L, synthetic as S
     g = S.gen(3, "cuda")
-    n, d, h, w, c = 150, 48, 5, 7, 19
-    feat, out, _ = _inputs(n, d, h, w, c, g)
-    one = D.Class_Features(c, d)
+    n, d, h, w, c = 150, 48, 9, 11, 19
+    feat, out = S.features((n, d, h, w), g), S.logits((n, c, h, w), g)
+    out[:, :3] += 6.0                                   # three classes own (nearly) every image: their count passes 100
+    one, many = D.Class_Features(c, d), D.Class_Features(c, d)
+    vec, vecsum, valid = many._masked_means(feat, out, None)
+
+    def update(cf, rows):
+        L.check(L.lib.diga_centroid_update(vec[rows].data_ptr(), vecsum[rows].data_ptr(), valid[rows].data_ptr(), rows.stop - rows.start,
+                                           c, d, cf.objective_vectors.data_ptr(), cf.objective_vectors_num.data_ptr(),
+                                           L.UPDATE_MOVING_AVERAGE, 1, 1e-4, L.stream()))
+
     for i in range(n):
-        one.update_from_features(feat[i:i + 1], out[i:i + 1], None, "moving_average", True)
-    many = D.Class_Features(c, d)
-    many.update_from_features(feat, out, None, "moving_average", True)
+        update(one, slice(i, i + 1))
+    update(many, slice(0, n))
     assert one.objective_vectors_num.max().item() > 100
     assert torch.equal(one.objective_vectors_num, many.objective_vectors_num)
     assert torch.equal(one.objective_vectors, many.objective_vectors)
