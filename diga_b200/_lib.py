@@ -40,9 +40,11 @@ SIGNATURES = {
     "diga_pseudo_label": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_class_presence": (_i, [_p, _i64, _i64, _p, _p, _p]),
     "diga_classmix_blend": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
-    "diga_centroid_assign": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
-    "diga_centroid_assign_fullres": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
-    "diga_centroid_accum": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p]),
+    "diga_centroid_clsw_bytes": (_i64, [_i64, _i64]),
+    "diga_centroid_clsw_build": (_i, [_p, _i64, _i64, _i64, _p, _p]),
+    "diga_centroid_assign": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_centroid_assign_fullres": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_centroid_accum": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "diga_centroid_means": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "diga_centroid_update": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
     "diga_centroid_update_sharded": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),

@@ -103,6 +103,7 @@ class Class_Features:
                 raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
         dev, hw, st = feat.device, h * w, L.stream()
         cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
+        clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev)
         counts = torch.empty((n, c), dtype=torch.int32, device=dev)
         sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
         if out_rows is not None:
@@ -116,10 +117,12 @@ class Class_Features:
             valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
         if full is not None:
             L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
-                                                       cls.data_ptr(), counts.data_ptr(), st))
+                                                       cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), st))
         else:
-            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(), st))
-        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, c, hw, sums.data_ptr(), st))
+            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(),
+                                               clsw.data_ptr(), st))
+        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, c, hw,
+                                          sums.data_ptr(), st))
         L.check(L.lib.diga_centroid_means(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, vec.data_ptr(),
                                           vecsum.data_ptr(), valid.data_ptr(), st))
         return vec, vecsum, valid

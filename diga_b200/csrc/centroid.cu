@@ -25,16 +25,40 @@ int tunable(const char* name, int dflt);
 // ------------------------------------------------------------------------------------------------
 // assign
 // ------------------------------------------------------------------------------------------------
+// Phase-shifted class words for the 128-bit accumulation kernel.  That kernel reads a channel row from the 128-byte line
+// below its first element, i.e. shifted by s floats (s = 0..31), so the four pixels of its aligned quad t are
+// 4t-s .. 4t-s+3: which bytes of the class map belong to one quad depends on s mod 4.  M_phi (phi = 0..3) is the class map
+// delayed by phi bytes behind kClswFront words of padding, so quad t of a row with shift s reads ONE aligned 32-bit word,
+// word kClswFront + t - (s >> 2) of M_(s & 3).  Pixels outside the row and gated-out pixels (255) carry the value `nclass`,
+// the index of a dummy accumulator slot — the accumulation loop needs no bounds or validity test at all.
+constexpr int kClswFront = 8;                          // words of front padding: covers t < (s >> 2), s <= 31
+__host__ __device__ inline int64_t clsw_words(int64_t hw) { return kClswFront + (hw + 6) / 4 + 1; }
+__device__ __forceinline__ void clsw_put(uint8_t* m, int64_t wp, int64_t p, int c) {
+#pragma unroll
+  for (int phi = 0; phi < 4; ++phi) m[phi * wp * 4 + 4 * kClswFront + p + phi] = (uint8_t)c;
+}
+__device__ __forceinline__ void clsw_pads(uint8_t* m, int64_t wp, int64_t hw, int nclass, int tid, int nthreads) {
+  for (int phi = 0; phi < 4; ++phi) {
+    uint8_t* mp = m + phi * wp * 4;
+    const int64_t head = 4 * kClswFront + phi, tail0 = 4 * kClswFront + hw + phi, total = wp * 4;
+    for (int64_t j = tid; j < head + (total - tail0); j += nthreads) mp[j < head ? j : tail0 + (j - head)] = (uint8_t)nclass;
+  }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int nclass, int64_t hw,
-                       uint8_t* __restrict__ cls, int32_t* __restrict__ counts, const int64_t* __restrict__ labels_full = nullptr,
+                       uint8_t* __restrict__ cls, int32_t* __restrict__ counts, uint32_t* __restrict__ clsw,
+                       const int64_t* __restrict__ labels_full = nullptr,
                        int w = 0, int HH = 0, int WW = 0, float sy = 0.f, float sx = 0.f) {
   __shared__ int hist[DIGA_MAX_CLASSES];
   if (threadIdx.x < DIGA_MAX_CLASSES) hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t img = blockIdx.y;
   const float* lg = logits + img * nclass * hw;
+  const int64_t wp = clsw_words(hw);
+  uint8_t* mw = clsw ? reinterpret_cast<uint8_t*>(clsw + img * 4 * wp) : nullptr;
+  if (mw && blockIdx.x == 0) clsw_pads(mw, wp, hw, nclass, threadIdx.x, BLOCK);
   for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < hw; base += (int64_t)gridDim.x * BLOCK) {
     const int64_t p = base + threadIdx.x;
     int c = 255;
@@ -66,6 +90,7 @@ centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict
         if (!(in_range && (long long)lf == (long long)am)) c = 255;
       }
       cls[img * hw + p] = (uint8_t)c;
+      if (mw) clsw_put(mw, wp, p, c == 255 ? nclass : c);
     }
     // warp-aggregated histogram: one shared atomic per distinct class per warp
     const unsigned peers = __match_any_sync(0xffffffffu, c);
@@ -248,11 +273,15 @@ centroid_accum_kernel(const float* __restrict__ feat, const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Row stride RS (a power of two) such that rows d and d+RS start at the same phase within a 128-byte line
 // (RS*hw % 32 == 0), falling back to 16-byte phase equality (RS*hw % 4 == 0); 0 if D cannot be tiled by 4*RS rows.
-static int quad_row_stride(int64_t hw, int64_t D) {
+// `unit_out`: the alignment unit found (32 or 4 floats); the phase of row q is (q*hw) mod unit.
+static int quad_row_stride(int64_t hw, int64_t D, int* unit_out = nullptr) {
   for (int unit = 32; unit >= 4; unit /= 8) {       // 32 floats = one line, then 4 floats = one 128-bit access
     int rs = unit;
     while (rs > 1 && ((rs / 2) * hw) % unit == 0) rs /= 2;
-    if (D % (4 * rs) == 0) return rs;
+    if (D % (4 * rs) == 0) {
+      if (unit_out) *unit_out = unit;
+      return rs;
+    }
   }
   return 0;
 }
@@ -332,7 +361,7 @@ __device__ __forceinline__ void quad_apply(const QuadBatch<U>& b, float4* my, in
 template <int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32)
 centroid_accum_quad_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ cls, int nclass, int64_t n, int64_t D,
-                           int64_t hw, int RS, float* __restrict__ sums) {
+                           int64_t hw, int RS, int unit_mask, float* __restrict__ sums) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* acc = reinterpret_cast<float4*>(smem_raw);   // [WARPS][nclass][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -346,7 +375,7 @@ centroid_accum_quad_kernel(const float* __restrict__ feat, const uint8_t* __rest
     const int64_t g = item - img * groups;
     const int64_t blk = g / RS, q = g - blk * RS;        // rows blk*4*RS + q + j*RS, j = 0..3
     const int64_t d0 = blk * 4 * RS + q;
-    const int s = (int)((q * hw) & (RS - 1));             // common alignment phase (floats) of the four rows
+    const int s = (int)((q * hw) & unit_mask);            // common alignment phase (floats) of the four rows
     const int64_t T = (hw + s + 3) >> 2;
     const uint8_t* cl = cls + img * hw;
     const float* rows[4];
@@ -381,6 +410,324 @@ centroid_accum_quad_kernel(const float* __restrict__ feat, const uint8_t* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// accum, lean 128-bit variant (round 2).  Same decomposition as the quad kernel above — CTA = (image, four channel rows
+// that share an alignment phase), lane = four adjacent pixels, lane-private float4 accumulators — with everything that is
+// not a load or an add taken out of the loop:
+//   * the class bytes of a quad arrive as ONE aligned 32-bit word (phase-shifted class words, see clsw_words) in which
+//     out-of-row and gated-out pixels name a dummy accumulator slot: no bounds test, no validity test, no byte loads;
+//   * quads past the end of the row re-read the last full quad against an all-dummy class word (clamped address), the
+//     <= 3 pixels left over behind the last full quad are added by a scalar tail — the 128-bit loads never leave the row
+//     of the LAST channel, so nothing is read beyond the tensor;
+//   * the first batch of the NEXT work item is requested before the cross-warp reduction of the current one, so the
+//     memory pipe does not drain at every item boundary;
+//   * the per-class reduction uses a 4-value butterfly (6 shuffles instead of 20) and skips classes absent from the
+//     image (per-image counts from the assign kernel), as does the clearing of the accumulators.
+// ncu of the round-1 kernel: 374 warp instructions per 4 KB batch, issue slots 41 % busy with every warp waiting on a
+// load; this loop issues ~100.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldg128_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// Sum of a float4 over the 32 lanes with 6 shuffles: lanes 0-7 end with the x total, 8-15 y, 16-23 z, 24-31 w.
+__device__ __forceinline__ float warp_sum4(const float4& v, int lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  float a = hi16 ? v.z : v.x, b = hi16 ? v.w : v.y;
+  a += __shfl_xor_sync(0xffffffffu, hi16 ? v.x : v.z, 16);
+  b += __shfl_xor_sync(0xffffffffu, hi16 ? v.y : v.w, 16);
+  float k = hi8 ? b : a;
+  k += __shfl_xor_sync(0xffffffffu, hi8 ? a : b, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
+struct LeanUnit {            // one quad of one lane: 4 rows x 4 adjacent pixels + their 4 class bytes
+  float4 x[4];
+  uint32_t cw;
+  bool in_row;               // false: the lane is past the end of the row (clamped re-read, counts for the dummy class)
+};
+
+struct LeanItem {
+  const float4* row[4];   // the four rows, shifted back by s floats (to the 16-byte / 128-byte boundary below their start)
+  const uint32_t* cw;     // class word of quad t at cw[t]
+  int T;                  // full quads in the row
+};
+
+__device__ __forceinline__ void lean_load(LeanUnit& u, const LeanItem& it, int t, uint32_t dummy4) {
+  const unsigned tt = (unsigned)min(t, it.T - 1);  // lanes past the end re-read the last quad against a dummy class word
+  u.cw = __ldg(it.cw + tt);                        // (selected against the dummy word at apply time: no wait here)
+  u.in_row = t < it.T;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u.x[j] = ldg128_stream(reinterpret_cast<const float*>(it.row[j] + tt));
+}
+
+__device__ __forceinline__ void f4_add_if(float4& a, const float4& b, bool p) {
+  if (p) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+}
+
+// Branch-free form: the four accumulator cells are read first (four independent LDS), every pixel's column is folded
+// into the FIRST pixel of the quad that has the same class (predicated adds), and only first occurrences are written
+// back — the written cells are distinct, so the four read-modify-writes no longer form a dependent chain.
+__device__ __forceinline__ void lean_apply_merged(const LeanUnit& u, uint32_t my, uint32_t dummy4) {
+  const uint32_t cw = u.in_row ? u.cw : dummy4;
+  const uint32_t c0 = cw & 0xffu, c1 = (cw >> 8) & 0xffu, c2 = (cw >> 16) & 0xffu, c3 = cw >> 24;
+  const uint32_t a0 = my + (c0 << 9), a1 = my + (c1 << 9), a2 = my + (c2 << 9), a3 = my + (c3 << 9);
+  float4 s0 = lds128(a0), s1 = lds128(a1), s2 = lds128(a2), s3 = lds128(a3);
+  // pixel i as a column over the four rows
+  float4 v0 = make_float4(u.x[0].x, u.x[1].x, u.x[2].x, u.x[3].x), v1 = make_float4(u.x[0].y, u.x[1].y, u.x[2].y, u.x[3].y);
+  float4 v2 = make_float4(u.x[0].z, u.x[1].z, u.x[2].z, u.x[3].z), v3 = make_float4(u.x[0].w, u.x[1].w, u.x[2].w, u.x[3].w);
+  const bool e01 = c0 == c1, e02 = c0 == c2, e03 = c0 == c3, e12 = c1 == c2, e13 = c1 == c3, e23 = c2 == c3;
+  f4_add_if(v2, v3, e23);                      // fold from the back so that chains (c1 == c2 == c3) accumulate
+  f4_add_if(v1, v3, e13 && !e23);
+  f4_add_if(v1, v2, e12);
+  f4_add_if(v0, v3, e03 && !e13 && !e23);
+  f4_add_if(v0, v2, e02 && !e12);
+  f4_add_if(v0, v1, e01);
+  s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+  s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+  s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+  s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
+  sts128(a0, s0);
+  if (!e01) sts128(a1, s1);
+  if (!(e02 || e12)) sts128(a2, s2);
+  if (!(e03 || e13 || e23)) sts128(a3, s3);
+}
+
+// MODE 0: four sequential read-modify-writes; 1: + one-RMW fast path when the four pixels share a class (a per-lane
+// branch: pays on single-class maps, costs on mixed ones); 2: the branch-free merged form above; 3 (default): as 0 but
+// pixels of the dummy class branch around their RMW and the dummy slot is dropped (19 instead of 20 slots: four CTAs then
+// fit the 164 KB shared-memory carve-out, which leaves the L1 that buffers the in-flight loads 92 KB instead of 60).
+template <int MODE>
+__device__ __forceinline__ void lean_apply(const LeanUnit& u, uint32_t my, uint32_t dummy4) {
+  if constexpr (MODE == 2) {
+    lean_apply_merged(u, my, dummy4);
+    return;
+  }
+  constexpr bool SPLAT = MODE == 1;
+  const uint32_t cw = u.in_row ? u.cw : dummy4;
+  if constexpr (MODE == 3) {                   // no dummy slot: pixels of the dummy class are predicated off
+    const uint32_t dummy = dummy4 & 0xffu;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t c = (cw >> (8 * i)) & 0xffu;
+      if (c != dummy) {
+        const uint32_t a = my + (c << 9);
+        float4 v = lds128(a);
+        v.x += f4_get(u.x[0], i);
+        v.y += f4_get(u.x[1], i);
+        v.z += f4_get(u.x[2], i);
+        v.w += f4_get(u.x[3], i);
+        sts128(a, v);
+      }
+    }
+    return;
+  }
+  if (SPLAT && cw == (cw & 0xffu) * 0x01010101u) {      // the four pixels share a class: one read-modify-write
+    const uint32_t a = my + ((cw & 0xffu) << 9);
+    float4 v = lds128(a);
+    v.x += (u.x[0].x + u.x[0].y) + (u.x[0].z + u.x[0].w);
+    v.y += (u.x[1].x + u.x[1].y) + (u.x[1].z + u.x[1].w);
+    v.z += (u.x[2].x + u.x[2].y) + (u.x[2].z + u.x[2].w);
+    v.w += (u.x[3].x + u.x[3].y) + (u.x[3].z + u.x[3].w);
+    sts128(a, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = my + (((cw >> (8 * i)) & 0xffu) << 9);
+      float4 v = lds128(a);
+      v.x += f4_get(u.x[0], i);
+      v.y += f4_get(u.x[1], i);
+      v.z += f4_get(u.x[2], i);
+      v.w += f4_get(u.x[3], i);
+      sts128(a, v);
+    }
+  }
+}
+
+// P = quads per lane and batch.  RING = false (default): a batch of P quads (4*P 128-bit loads) is requested, then
+// consumed, then the next batch is requested — ptxas puts every LDG.128 of the loop on ONE scoreboard and a scoreboard
+// wait returns only when ALL its loads have landed, so any scheme that re-requests a unit right after consuming it
+// (RING = true, the register ring this kernel started with; also the double buffer of the round-1 kernel) still pays a
+// full memory latency per UNIT: the wait for the oldest unit also waits for the one requested a moment ago.  Measured
+// (profiles/r02_accum_sweep.jsonl): ring 0.73, batches 0.8x.  Latency is hidden across warps, not inside one.
+template <int WARPS, int P, int MINB, int MODE, bool RING>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+centroid_accum_lean_kernel(const float* __restrict__ feat, const uint32_t* __restrict__ clsw, const uint8_t* __restrict__ cls,
+                           const int32_t* __restrict__ counts, int nclass, int64_t n, int64_t D, int64_t hw, int RS, int unit_mask,
+                           float* __restrict__ sums) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int STRIDE = WARPS * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slots = MODE == 3 ? nclass : nclass + 1;              // + the dummy slot
+  const uint32_t acc0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t my = acc0 + (uint32_t)((warp * slots * 32 + lane) * 16);   // slot c of this lane: my + c * 512
+  const uint32_t dummy4 = (uint32_t)nclass * 0x01010101u;
+  const int64_t groups = D / 4, items = n * groups, wp = clsw_words(hw);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto setup = [&](int64_t item, LeanItem& it, int64_t& img, int64_t& d0, int& s) {
+    img = item / groups;
+    const int64_t g = item - img * groups;
+    const int64_t blk = g / RS, q = g - blk * RS;                 // rows blk*4*RS + q + j*RS, j = 0..3
+    d0 = blk * 4 * RS + q;
+    s = (int)((q * hw) & unit_mask);                              // common alignment phase (floats) of the four rows
+    const float* r0 = feat + (img * D + d0) * hw - s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) it.row[j] = reinterpret_cast<const float4*>(r0 + (int64_t)j * RS * hw);
+    it.cw = clsw + (img * 4 + (s & 3)) * wp + kClswFront - (s >> 2);
+    it.T = (int)((hw + s) >> 2);
+  };
+
+  int64_t item = blockIdx.x;
+  if (item >= items) return;
+  LeanItem it;
+  int64_t img, d0;
+  int s;
+  setup(item, it, img, d0, s);
+  LeanUnit ring[P];
+  const int first = warp * 32 + lane;
+#pragma unroll
+  for (int k = 0; k < P; ++k) lean_load(ring[k], it, first + k * STRIDE, dummy4);   // (rounds past the row: dummy words)
+
+  while (true) {
+    // classes present in this image (per-image counts): absent ones are neither cleared nor reduced nor written
+    uint32_t present = 0xffffffffu;
+    if (counts != nullptr) present = __ballot_sync(0xffffffffu, lane < nclass && __ldg(counts + img * nclass + lane) > 0);
+    for (int c = 0; c < nclass; ++c)
+      if ((present >> c) & 1u) sts128(my + (c << 9), zero);
+    if (MODE != 3) sts128(my + (nclass << 9), zero);
+    // (own lane-private cells only: no barrier needed before the main loop)
+
+    const int rounds = (it.T + STRIDE - 1) / STRIDE;                // CTA-uniform
+    if constexpr (RING) {
+      for (int r = 0; r < rounds; r += P) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          if (r + k < rounds) {
+            lean_apply<MODE>(ring[k], my, dummy4);
+            if (r + k + P < rounds) lean_load(ring[k], it, first + (r + k + P) * STRIDE, dummy4);
+          }
+        }
+      }
+    } else {
+      for (int r = 0; r < rounds; r += P) {
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+          if (r + k < rounds) lean_apply<MODE>(ring[k], my, dummy4);
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+          if (r + P + k < rounds) lean_load(ring[k], it, first + (r + P + k) * STRIDE, dummy4);
+      }
+    }
+    // the (hw + s) & 3 pixels behind the last full quad
+    const int rem = (int)((hw + s) & 3);
+    if (warp == 0 && lane < rem) {
+      const int64_t p = hw - rem + lane;
+      const int c = cls[img * hw + p];
+      if (c < nclass) {
+        const float* f = feat + (img * D + d0) * hw + p;
+        const int64_t row_stride = (int64_t)RS * hw;
+        const uint32_t ad = my + (c << 9);
+        float4 v = lds128(ad);
+        v.x += __ldg(f);
+        v.y += __ldg(f + row_stride);
+        v.z += __ldg(f + 2 * row_stride);
+        v.w += __ldg(f + 3 * row_stride);
+        sts128(ad, v);
+      }
+    }
+    // next item: request its first P rounds now, consume them after the reduction below
+    const int64_t out_base = (img * nclass) * D + d0;
+    const int64_t next = item + gridDim.x;
+    const bool more = next < items;
+    if (more) {
+      setup(next, it, img, d0, s);
+#pragma unroll
+      for (int k = 0; k < P; ++k) lean_load(ring[k], it, first + k * STRIDE, dummy4);
+    }
+    __syncthreads();
+    for (int c = warp; c < nclass; c += WARPS) {
+      if (!((present >> c) & 1u)) continue;
+      float4 t = zero;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const float4 v = lds128(acc0 + (uint32_t)(((w * slots + c) * 32 + lane) * 16));
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      const float tot = warp_sum4(t, lane);
+      if ((lane & 7) == 0) sums[out_base + (int64_t)c * D + (int64_t)(lane >> 3) * RS] = tot;
+    }
+    if (!more) break;
+    item = next;
+    __syncthreads();
+  }
+}
+
+// class words from a plain u8 class map (callers that did not get them from the assign kernel)
+__global__ void centroid_clsw_build_kernel(const uint8_t* __restrict__ cls, int nclass, int64_t hw, uint32_t* __restrict__ clsw) {
+  const int64_t wp = clsw_words(hw);
+  const int64_t img = blockIdx.z;
+  const int phi = blockIdx.y;
+  const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= wp) return;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int64_t p = wi * 4 + b - 4 * kClswFront - phi;
+    int c = nclass;
+    if (p >= 0 && p < hw) {
+      c = cls[img * hw + p];
+      if (c >= nclass) c = nclass;
+    }
+    word |= (uint32_t)c << (8 * b);
+  }
+  clsw[(img * 4 + phi) * wp + wi] = word;
+}
+
+template <int WARPS, int P, int MINB, int MODE, bool RING = false>
+static int launch_accum_lean(const float* feat, const uint32_t* clsw, const uint8_t* cls, const int32_t* counts, int nclass,
+                             int64_t n, int64_t D, int64_t hw, float* sums, cudaStream_t st) {
+  auto kern = centroid_accum_lean_kernel<WARPS, P, MINB, MODE, RING>;
+  const size_t smem = (size_t)WARPS * (nclass + (MODE == 3 ? 0 : 1)) * 32 * sizeof(float4);
+  static size_t configured_dev[64] = {0};
+  static int blocks_dev[64] = {0};
+  const int slot = device_slot();
+  if (configured_dev[slot] != smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("centroid_accum: cannot reserve %zu bytes of shared memory", smem);
+      return DIGA_ERR_CUDA;
+    }
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, WARPS * 32, smem);
+    blocks_dev[slot] = b > 0 ? b : 1;
+    configured_dev[slot] = smem;
+  }
+  int unit = 0;
+  const int RS = quad_row_stride(hw, D, &unit);
+  const int64_t items = n * (D / 4);
+  const int64_t full = (int64_t)sm_count() * blocks_dev[slot];
+  const int64_t grid = tunable("accum_balance", 1) ? balanced_grid(items, blocks_dev[slot]) : (items < full ? items : full);
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, clsw, cls, counts, nclass, n, D, hw, RS, unit - 1, sums);
+  DIGA_CHECK_LAUNCH("centroid_accum_lean_kernel");
+  return DIGA_OK;
+}
+
 template <int WARPS, int U>
 static int launch_accum_quad(const float* feat, const uint8_t* cls, int nclass, int64_t n, int64_t D, int64_t hw, float* sums,
                              cudaStream_t st) {
@@ -399,10 +746,11 @@ static int launch_accum_quad(const float* feat, const uint8_t* cls, int nclass, 
     blocks_per_sm = b > 0 ? b : 1;
     configured = smem;
   }
-  const int RS = quad_row_stride(hw, D);
+  int unit = 0;
+  const int RS = quad_row_stride(hw, D, &unit);
   const int64_t items = n * (D / 4);
   const int64_t grid = tunable("accum_balance", 1) ? balanced_grid(items, blocks_per_sm) : (items < (int64_t)sm_count() * blocks_per_sm ? items : (int64_t)sm_count() * blocks_per_sm);
-  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, cls, nclass, n, D, hw, RS, sums);
+  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, cls, nclass, n, D, hw, RS, unit - 1, sums);
   DIGA_CHECK_LAUNCH("centroid_accum_quad_kernel");
   return DIGA_OK;
 }
@@ -679,14 +1027,31 @@ static UpdateRule make_rule(int mode, int start_mean, double momentum) {
 
 extern "C" {
 
+int64_t diga_centroid_clsw_bytes(int64_t n, int64_t hw) {
+  if (n < 0 || hw < 0) return 0;
+  return n * 4 * diga::clsw_words(hw) * (int64_t)sizeof(uint32_t);
+}
+
+int diga_centroid_clsw_build(const uint8_t* cls, int64_t n, int64_t C, int64_t hw, uint32_t* clsw, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(cls && clsw, DIGA_ERR_INVALID, "centroid_clsw_build: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES && n >= 0 && n <= 65535 && hw >= 0, DIGA_ERR_INVALID, "centroid_clsw_build: bad sizes");
+  DIGA_REQUIRE(aligned(clsw, 4), DIGA_ERR_MISALIGNED, "centroid_clsw_build: misaligned pointer");
+  if (n == 0) return DIGA_OK;
+  const int64_t wp = clsw_words(hw);
+  centroid_clsw_build_kernel<<<dim3((unsigned)((wp + 255) / 256), 4, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(cls, (int)C, hw, clsw);
+  DIGA_CHECK_LAUNCH("centroid_clsw_build_kernel");
+  return DIGA_OK;
+}
+
 int diga_centroid_assign(const float* logits, const float* labels, int64_t n, int64_t C, int64_t hw, uint8_t* cls,
-                         int32_t* counts, diga_stream_t stream) {
+                         int32_t* counts, uint32_t* clsw, diga_stream_t stream) {
   using namespace diga;
   DIGA_REQUIRE(logits && cls && counts, DIGA_ERR_INVALID, "centroid_assign: null pointer");
   DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "centroid_assign: C=%lld outside [1,%d]", (long long)C,
                DIGA_MAX_CLASSES);
   DIGA_REQUIRE(n >= 0 && n <= 65535 && hw >= 0, DIGA_ERR_INVALID, "centroid_assign: bad sizes");
-  DIGA_REQUIRE(aligned(logits, 4) && aligned(labels, 4) && aligned(counts, 4), DIGA_ERR_MISALIGNED,
+  DIGA_REQUIRE(aligned(logits, 4) && aligned(labels, 4) && aligned(counts, 4) && aligned(clsw, 4), DIGA_ERR_MISALIGNED,
                "centroid_assign: misaligned pointer");
   if (n == 0) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -696,13 +1061,13 @@ int diga_centroid_assign(const float* logits, const float* labels, int64_t n, in
   int64_t gx = (hw + BLOCK - 1) / BLOCK;
   const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
   if (gx > cap) gx = cap;
-  centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(logits, labels, (int)C, hw, cls, counts);
+  centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(logits, labels, (int)C, hw, cls, counts, clsw);
   DIGA_CHECK_LAUNCH("centroid_assign_kernel");
   return DIGA_OK;
 }
 
 int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full, int64_t n, int64_t C, int64_t h, int64_t w,
-                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, diga_stream_t stream) {
+                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, uint32_t* clsw, diga_stream_t stream) {
   using namespace diga;
   DIGA_REQUIRE(logits && labels_full && cls && counts, DIGA_ERR_INVALID, "centroid_assign_fullres: null pointer");
   DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "centroid_assign_fullres: C=%lld outside [1,%d]", (long long)C,
@@ -710,7 +1075,7 @@ int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full
   DIGA_REQUIRE(n >= 0 && n <= 65535 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && h < (1 << 24) && w < (1 << 24) && H < (1 << 24) &&
                    W < (1 << 24),
                DIGA_ERR_INVALID, "centroid_assign_fullres: bad sizes");
-  DIGA_REQUIRE(aligned(logits, 4) && aligned(labels_full, 8) && aligned(counts, 4), DIGA_ERR_MISALIGNED,
+  DIGA_REQUIRE(aligned(logits, 4) && aligned(labels_full, 8) && aligned(counts, 4) && aligned(clsw, 4), DIGA_ERR_MISALIGNED,
                "centroid_assign_fullres: misaligned pointer");
   if (n == 0) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -721,26 +1086,42 @@ int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full
   const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
   if (gx > cap) gx = cap;
   centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(
-      logits, nullptr, (int)C, hw, cls, counts, labels_full, (int)w, (int)H, (int)W, (float)H / (float)h, (float)W / (float)w);
+      logits, nullptr, (int)C, hw, cls, counts, clsw, labels_full, (int)w, (int)H, (int)W, (float)H / (float)h, (float)W / (float)w);
   DIGA_CHECK_LAUNCH("centroid_assign_kernel");
   return DIGA_OK;
 }
 
-int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_t D, int64_t C, int64_t hw, float* sums,
-                        diga_stream_t stream) {
+int diga_centroid_accum(const float* feat, const uint8_t* cls, const int32_t* counts, const uint32_t* clsw, int64_t n, int64_t D,
+                        int64_t C, int64_t hw, float* sums, diga_stream_t stream) {
   using namespace diga;
   DIGA_REQUIRE(feat && cls && sums, DIGA_ERR_INVALID, "centroid_accum: null pointer");
   DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES, DIGA_ERR_INVALID, "centroid_accum: C=%lld outside [1,%d]", (long long)C,
                DIGA_MAX_CLASSES);
   DIGA_REQUIRE(n >= 0 && D >= 0 && hw >= 0, DIGA_ERR_INVALID, "centroid_accum: bad sizes");
-  DIGA_REQUIRE(aligned(feat, 4) && aligned(sums, 4), DIGA_ERR_MISALIGNED, "centroid_accum: misaligned pointer");
+  DIGA_REQUIRE(aligned(feat, 4) && aligned(sums, 4) && aligned(counts, 4) && aligned(clsw, 4), DIGA_ERR_MISALIGNED,
+               "centroid_accum: misaligned pointer");
   if (n == 0 || D == 0) return DIGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int variant = tunable("accum_variant", 0);
   const int RS = quad_row_stride(hw, D);
   const bool quad_ok = RS > 0 && aligned(feat, 128) && hw >= 4;
-  // Default: the 128-bit kernel (4 warps, 2 quads in flight twice) — the best all-round shape in the sweeps
-  // (profiles/r01_tune_accum.jsonl); the scalar kernels take the shapes it cannot tile (variants 1..7 force them).
+  // Default: the lean 128-bit kernel when the caller supplies the phase-shifted class words (diga_centroid_assign /
+  // diga_centroid_clsw_build), else the round-1 128-bit kernel on the plain byte map; the scalar kernels take the shapes
+  // neither can tile (variants 1..7 force them, 8..12 the round-1 128-bit shapes, 13.. the lean shapes).
+  if (quad_ok && clsw != nullptr && (variant == 0 || variant >= 13)) {
+    const int nc = (int)C;
+    switch (variant) {
+      case 13: return launch_accum_lean<4, 4, 4, 1, true>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);   // register ring
+      case 14: return launch_accum_lean<4, 4, 4, 1>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);         // splat fast path
+      case 15: return launch_accum_lean<4, 3, 5, 0>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);
+      case 16: return launch_accum_lean<4, 4, 4, 2>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);         // merged RMWs
+      case 17: return launch_accum_lean<4, 4, 4, 0>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);         // dummy slot
+      case 18: return launch_accum_lean<2, 4, 8, 0>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);
+      case 19: return launch_accum_lean<8, 4, 2, 0>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);
+      case 20: return launch_accum_lean<3, 4, 5, 3>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);
+      default: return launch_accum_lean<4, 4, 4, 3>(feat, clsw, cls, counts, nc, n, D, hw, sums, st);
+    }
+  }
   if (quad_ok && (variant == 0 || variant >= 8)) {
     switch (variant) {
       case 8: return launch_accum_quad<4, 1>(feat, cls, (int)C, n, D, hw, sums, st);

@@ -106,18 +106,26 @@ int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const fl
  *   means : vec[n][c][d] = (sums/hw) / (counts/hw); valid[n][c] = counts >= 5;
  *           vecsum[n][c] = sum_d vec (for the reference's `vector.sum() == 0` skip).
  * ------------------------------------------------------------------------------------------ */
+/* clsw (optional, may be NULL): phase-shifted class words for the 128-bit accumulation kernel, diga_centroid_clsw_bytes(n, hw)
+ * bytes — four copies of the class map delayed by 0..3 bytes so that an aligned quad of any channel row reads its four
+ * class bytes as one aligned word; out-of-row and gated-out pixels name a dummy class C.  Written by the assign calls, or
+ * from a plain class map by diga_centroid_clsw_build. */
+int64_t diga_centroid_clsw_bytes(int64_t n, int64_t hw);
+int diga_centroid_clsw_build(const uint8_t* cls, int64_t n, int64_t C, int64_t hw, uint32_t* clsw, diga_stream_t stream);
 int diga_centroid_assign(const float* logits, const float* labels, int64_t n, int64_t C, int64_t hw,
-                         uint8_t* cls, int32_t* counts, diga_stream_t stream);
+                         uint8_t* cls, int32_t* counts, uint32_t* clsw, diga_stream_t stream);
 /* assign with the reference's label down-sampling folded in (self_training.py:327-330, :336-337): labels_full is the
  * [n,H,W] int64 map; pixel (y,x) of the h x w feature grid is gated by labels_full[min(floor(y*H/h), H-1)][min(floor(x*W/w), W-1)]
  * (F.interpolate(mode='nearest') of the .float() map), same gate as diga_centroid_assign. */
 int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full, int64_t n, int64_t C, int64_t h, int64_t w,
-                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, diga_stream_t stream);
+                                 int64_t H, int64_t W, uint8_t* cls, int32_t* counts, uint32_t* clsw, diga_stream_t stream);
 /* process_label (util/utils.py:158-163): label [B,1,hw] fp32 -> onehot [B,C+1,hw] fp32, ids >= C in channel C.
  * Negative labels are outside the reference's domain (scatter_ would raise) and give an all-zero column. */
 int diga_onehot_labels(const float* label, int64_t B, int64_t C, int64_t hw, float* onehot, diga_stream_t stream);
-int diga_centroid_accum(const float* feat, const uint8_t* cls, int64_t n, int64_t D, int64_t C, int64_t hw,
-                        float* sums, diga_stream_t stream);
+/* counts (optional): the per-image class counts of the assign call — classes absent from an image are then skipped and
+ * their sums left unwritten (diga_centroid_means reads sums only where counts > 0).  clsw (optional): see above. */
+int diga_centroid_accum(const float* feat, const uint8_t* cls, const int32_t* counts, const uint32_t* clsw, int64_t n,
+                        int64_t D, int64_t C, int64_t hw, float* sums, diga_stream_t stream);
 int diga_centroid_means(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw,
                         float* vec, float* vecsum, uint8_t* valid, diga_stream_t stream);
 

@@ -398,7 +398,7 @@ def test_centroid_accum_variants_and_determinism(D):
     out = S.logits((2, 19, 65, 129), g)
     ref = None
     try:
-        for variant in range(13):
+        for variant in range(21):
             L.set_tunable("accum_variant", variant)
             cf = D.Class_Features(19, 256)
             v1, s1, ok1 = cf._masked_means(feat, out, None)
