@@ -37,6 +37,7 @@ KD_SHAPE = (8, C, 512, 1024)          # config 2: B=4 per view
 KD_BYTES_FWD = 2 * C * 4              # teacher + student read
 KD_BYTES_BWD = 3 * C * 4              # teacher + student read, dstudent written
 UPSTREAM = 0.25
+METRIC = "pixels/sec (symmetric KD loss fwd+bwd; per-row figures for pseudo-label+selection and centroids in roofline.rows)"
 
 
 def load_peaks():
@@ -120,6 +121,34 @@ def max_over_ranks(x: float, world: int, device) -> float:
     return float(t.item())
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and therefore the first touch of its pinned host buffers and its launch thread) to the CPUs of the
+    NUMA node the GPU hangs off.  Best effort: returns {"node": n, "cpus": k} or {"node": None, ...} when sysfs has no answer."""
+    info = {"node": None, "cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"node": node, "cpus": len(allowed)}
+    except Exception:                                             # noqa: BLE001  (no NVML / sysfs: leave the affinity alone)
+        pass
+    return info
+
+
 def time_loop(fn, iters, warmup, world=1, device=None, graph=False):
     """CUDA-event timing of ``iters`` calls, barrier + synchronize on both sides, max over ranks -> ms per call.
     ``graph=True`` captures one call (a sync-free public-API call) in a CUDA graph and times its replays, which removes
@@ -155,20 +184,44 @@ def time_loop(fn, iters, warmup, world=1, device=None, graph=False):
 
 
 # --------------------------------------------------------------------------------------------------
-# the reference arm / CPU baseline: oracle port on the host cores
+# the reference arm / CPU baseline: the reference's OWN CPU code on the host cores (baseline/_ref, staged by
+# oracle/make_ref.py), the oracle port when that tree is absent
 # --------------------------------------------------------------------------------------------------
-def cpu_kd_step(t, s, g):
+CONFIG = {"workload": "config 2: symmetric KD loss fwd+bwd (distillation_loss + autograd), logits [8,19,512,1024] "
+                      "(two views x batch 4) per GPU, fp32",
+          "shape": list(KD_SHAPE), "pixel_positions_per_step_per_gpu": KD_SHAPE[0] * KD_SHAPE[2] * KD_SHAPE[3]}
+
+
+def cpu_functions():
+    """(namespace, kind): the reference's own functions when a reference tree is reachable ($DIGA_REF, /root/reference or
+    the staged baseline/_ref), else the oracle port.  CPU only: ``.cuda()`` is made a no-op for the importing process, which
+    is why the CPU legs run in their own process (``--impl reference`` / ``--cpu-baseline-json``)."""
+    import types
     from oracle import diga_oracle as O
+    try:
+        from oracle import ref_loader as R
+        if R.available("G"):
+            torch.Tensor.cuda = lambda self, *a, **k: self          # the reference hard-codes .cuda() (utils.py:160, calc_centroids.py:95,168)
+            torch.nn.Module.cuda = lambda self, *a, **k: self
+            ns = R.load("G")
+            return types.SimpleNamespace(distillation_loss=ns.distillation_loss, Class_Features=ns.Class_Features,
+                                         where=R.REF_ROOT), "reference"
+    except Exception as e:                                          # noqa: BLE001  (any import problem -> the port)
+        sys.stderr.write(f"bench: reference tree not usable ({type(e).__name__}: {e}); timing the oracle port\n")
+    return types.SimpleNamespace(distillation_loss=O.distillation_loss,
+                                 Class_Features=lambda numbers=19: O.ClassFeaturesOracle(numbers), where="oracle/diga_oracle.py"), "port"
+
+
+def cpu_kd_step(fn, t, s, g):
     s = s.detach().requires_grad_(True)
-    loss = O.distillation_loss(t, s, 0.5)
+    loss = fn(t, s, 0.5)
     (grad,) = torch.autograd.grad(loss, s, grad_outputs=g)
     return loss, grad
 
 
-def cpu_kd_inputs(n2):
+def cpu_kd_inputs():
     gen = torch.Generator().manual_seed(1234)
-    shape = (n2,) + KD_SHAPE[1:]
-    return 3.0 * torch.randn(shape, generator=gen), 3.0 * torch.randn(shape, generator=gen), torch.tensor(UPSTREAM)
+    return 3.0 * torch.randn(KD_SHAPE, generator=gen), 3.0 * torch.randn(KD_SHAPE, generator=gen), torch.tensor(UPSTREAM)
 
 
 def use_all_host_threads() -> int:
@@ -178,63 +231,114 @@ def use_all_host_threads() -> int:
     return torch.get_num_threads()
 
 
-def cpu_baseline(budget_s=20.0):
-    """Oracle port of config 2 on the host cores: bounded sample (about ``budget_s`` seconds of CPU work)."""
-    threads = use_all_host_threads()
-    t, s, g = cpu_kd_inputs(2)
-    t0 = time.perf_counter()
-    cpu_kd_step(t, s, g)
-    probe = time.perf_counter() - t0                      # [2,19,512,1024] incl. first-touch
-    n2 = 8 if probe * 4 * 3 <= budget_s else (4 if probe * 2 * 3 <= budget_s else 2)
-    if n2 != 2:
-        t, s, g = cpu_kd_inputs(n2)
-        cpu_kd_step(t, s, g)
+def best_of(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
     best = float("inf")
-    reps = 0
-    t_end = time.perf_counter() + budget_s
-    while reps < 3 or (time.perf_counter() < t_end and reps < 10):
+    for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_kd_step(t, s, g)
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def config1_cpu_stages(ref, threads):
+    """BASELINE config 1: the reference CPU path of a3, a5 + a4 and a6 + a7 for ONE 512x256 image (H=256, W=512, features
+    33x65), D in {256, 2048}, all host threads and one thread, best of 5.  a5/a6/a7 run the reference's own
+    Class_Features methods; a3 and a4 are inline script blocks (pseudolabel_generator.py:77-85, self_training.py:298-304),
+    timed through their line-for-line restatement in oracle/diga_oracle.py."""
+    from oracle import diga_oracle as O
+    gen = torch.Generator().manual_seed(1234)
+    hh, ww, h, w = 256, 512, 33, 65
+    lf, lds = 3.0 * torch.randn((1, C, h, w), generator=gen), 3.0 * torch.randn((1, C, 17, 33), generator=gen)
+    pseudo = torch.randint(0, C, (1, hh, ww), generator=gen)
+    out = 3.0 * torch.randn((1, C, h, w), generator=gen)
+    stages = []
+
+    def timed(name, px, unit, fn, rows):
+        rec = {"stage": name, "units": px, "unit": unit, "rows": rows}
+        for label, nthr in (("all_threads", threads), ("one_thread", 1)):
+            torch.set_num_threads(nthr)
+            sec = best_of(fn)
+            rec[f"cpu_ms_{label}"] = sec * 1e3
+            rec[f"cpu_units_per_s_{label}"] = px / sec
+        torch.set_num_threads(threads)
+        stages.append(rec)
+
+    timed("a3 pseudo-label (2 up-samplings, max, softmax, numpy argmax + max, uint8)", hh * ww, "px",
+          lambda: O.pseudo_label_to_uint8(O.pseudo_label_two_scale(lf, lds, (hh, ww))[0]), "pseudolabel_generator.py:77-85,92")
+    for d in (256, 2048):
+        feat = torch.randn((1, d, h, w), generator=gen)
+        cf = ref.Class_Features(numbers=C)
+        cf.objective_vectors = 0.5 * torch.randn((C, d), generator=gen)
+        cf.objective_vectors_num = torch.zeros((C,))
+
+        def rectify():
+            return O.consensus_select(pseudo, cf.get_centroid_weight(feat), (hh, ww))
+
+        def centroids():
+            vectors, ids = cf.calculate_mean_vector(feat, out)
+            for t in range(len(ids)):
+                cf.update_objective_SingleVector(ids[t], vectors[t].detach().cpu().numpy(), "mean")
+
+        timed(f"a5 + a4 prototype weights + consensus selection, D={d}", hh * ww, "px", rectify,
+              "calc_centroids.py:166-176 + self_training.py:298-304")
+        timed(f"a6 + a7 calculate_mean_vector + running mean update, D={d}", h * w, "feature-px", centroids,
+              "calc_centroids.py:120-164, loop :75-78")
+    return stages
+
+
+def cpu_baseline(budget_s=25.0):
+    """The CPU arm on THIS box's host cores: config 2 (the headline workload, full [8,19,512,1024] steps, best within a
+    bounded budget) and the config-1 stages.  Runs in a process of its own (see cpu_functions)."""
+    threads = use_all_host_threads()
+    ref, kind = cpu_functions()
+    t, s, g = cpu_kd_inputs()
+    cpu_kd_step(ref.distillation_loss, t, s, g)                  # first touch + thread pool start-up
+    best, reps = float("inf"), 0
+    t_end = time.perf_counter() + budget_s
+    while reps < 3 or (time.perf_counter() < t_end and reps < 12):
+        t0 = time.perf_counter()
+        cpu_kd_step(ref.distillation_loss, t, s, g)
         best = min(best, time.perf_counter() - t0)
         reps += 1
-    px = n2 * KD_SHAPE[2] * KD_SHAPE[3]
-    return {"value": px / best, "unit": "pixel-positions/s", "cores": threads, "kind": "port",
-            "sample": f"oracle (torch CPU op chain of util/loss.py:125-143 + autograd) on [{n2},19,512,1024], "
-                      f"best of {reps}, {threads} threads of {os.cpu_count()} logical cores"}
+    px = KD_SHAPE[0] * KD_SHAPE[2] * KD_SHAPE[3]
+    del t, s
+    what = "the reference's own util/loss.py:125-143 (imported from " + ref.where + ")" if kind == "reference" else \
+        "oracle port of util/loss.py:125-143 (no reference tree on this box)"
+    return {"value": px / best, "unit": "pixel-positions/s", "cores": threads, "kind": kind,
+            "sample": f"{what} + autograd on the full [8,19,512,1024] step, best of {reps} steps after one warm-up, "
+                      f"{threads} threads of {os.cpu_count()} logical cores",
+            "ms_per_step": best * 1e3,
+            "stages": config1_cpu_stages(ref, threads)}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of config 2 on all host threads, the SAME workload and
+    config dict as the GPU arm (full [8,19,512,1024] per step; W warm-ups, K timed steps)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     threads = use_all_host_threads()
-    t, s, g = cpu_kd_inputs(2)
-    t0 = time.perf_counter()
-    cpu_kd_step(t, s, g)
-    probe = time.perf_counter() - t0
-    total_steps = args.steps + args.warmup
-    n2 = 8
-    while n2 > 2 and probe * (n2 / 2) * total_steps > 150.0:
-        n2 //= 2
-    t, s, g = cpu_kd_inputs(n2)
-    for _ in range(args.warmup):
-        cpu_kd_step(t, s, g)
+    ref, kind = cpu_functions()
+    t, s, g = cpu_kd_inputs()
+    for _ in range(max(args.warmup, 1)):
+        cpu_kd_step(ref.distillation_loss, t, s, g)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_kd_step(t, s, g)
+        cpu_kd_step(ref.distillation_loss, t, s, g)
     dt = time.perf_counter() - t0
-    px = n2 * KD_SHAPE[2] * KD_SHAPE[3]
+    px = KD_SHAPE[0] * KD_SHAPE[2] * KD_SHAPE[3]
     value = px * args.steps / dt
-    sample = (f"oracle port (torch CPU op chain of util/loss.py:125-143 + autograd) on [{n2},19,512,1024] per step, "
-              f"{threads} threads of {os.cpu_count()} logical cores")
-    line = {"impl": "reference", "metric": "pixels/sec (symmetric KD loss fwd+bwd)", "value": value,
+    what = ("the reference's own distillation_loss (util/loss.py:125-143, imported from " + ref.where + ")") if kind == "reference" \
+        else "oracle port of util/loss.py:125-143"
+    line = {"impl": "reference", "metric": METRIC, "value": value,
             "unit": "pixel-positions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 2: symmetric KD fwd+bwd, logits [8,19,512,1024] (B=4 per view), fp32",
-                       "sample_shape": [n2, 19, 512, 1024]},
-            "cpu_baseline": {"value": value, "unit": "pixel-positions/s", "cores": threads, "kind": "port",
-                             "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": "pixel-positions/s", "cores": threads, "kind": kind,
+                             "sample": f"{what} + autograd, full [8,19,512,1024] per step, {threads} threads of "
+                                       f"{os.cpu_count()} logical cores"},
             "e2e": {"value": value, "unit": "pixel-positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_line(line)
 
@@ -242,11 +346,83 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # secondary stages (the other rows of SURVEY.md §8), per rank
 # --------------------------------------------------------------------------------------------------
-def bench_stages(D, S, dev, peak, world, quick):
+def accum_kernel_rows(L, S, dev, peak):
+    """The a6 accumulation KERNEL alone (diga_centroid_accum through the C ABI, event pair per launch) at config 4's batched
+    shape [8,2048,65,129], for i.i.d. classes (worst case of the shared-memory accumulators) and 4x4-block maps."""
+    g = S.gen(77 + dist_env()[0], dev)
+    n, d, h, w = 8, 2048, 65, 129
+    hw = h * w
+    feats = [S.features((n, d, h, w), g) for _ in range(3)]
+    rows = []
+    for pattern in ("iid", "blocks4"):
+        out = S.logits((n, C, h, w), g)
+        if pattern == "blocks4":
+            lab = S.block_labels(n, h, w, g, 4, C, 0.0)
+            out = out + 12.0 * torch.nn.functional.one_hot(lab, C).permute(0, 3, 1, 2).float()
+        cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
+        clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev)
+        counts = torch.empty((n, C), dtype=torch.int32, device=dev)
+        sums = torch.empty((n, C, d), dtype=torch.float32, device=dev)
+        st = L.stream()
+        L.check(L.lib.diga_centroid_assign(out.data_ptr(), None, n, C, hw, cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), st))
+
+        def launch(i):
+            L.check(L.lib.diga_centroid_accum(feats[i % 3].data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, C, hw,
+                                              sums.data_ptr(), st))
+
+        for i in range(3):
+            launch(i)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            launch(i)
+            b.record()
+        torch.cuda.synchronize()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        rows.append(("a6", f"centroid_accum_lean_kernel ({'i.i.d. classes' if pattern == 'iid' else '4x4-block class maps'})", "hbm",
+                     "feature-px", n * hw, d * 4 + 1, ms, "CUDA event pair per launch, C-ABI launches queued back to back, 3 rotating 550 MB inputs",
+                     "accum_dram_bytes_per_launch" if pattern == "iid" else None))
+    return rows
+
+
+def config1_gpu_stages(D, S, dev):
+    """The GPU stages at BASELINE config 1's shapes (ONE 512x256 image: launch-latency territory), keyed like the CPU stages."""
+    from diga_b200.util.loss import distillation_loss  # noqa: F401
+    g = S.gen(1234, dev)
+    hh, ww, h, w = 256, 512, 33, 65
+    lf, lds = S.logits((1, C, h, w), g), S.logits((1, C, 17, 33), g)
+    pseudo = torch.randint(0, C, (1, hh, ww), device=dev, generator=g)
+    out = S.logits((1, C, h, w), g)
+    res = {}
+
+    def put(name, fn):
+        res[name] = {"gpu_ms": time_loop(fn, 50, 5, graph=True), "gpu_eager_ms": time_loop(fn, 50, 5),
+                     "gpu_how": "public API, CUDA-graph replay (gpu_ms) and eager call (gpu_eager_ms)"}
+
+    put("a3 pseudo-label (2 up-samplings, max, softmax, numpy argmax + max, uint8)",
+        lambda: D.pseudo_label_two_scale(lf, lds, (hh, ww), want_conf=False))
+    for d in (256, 2048):
+        feat = S.features((1, d, h, w), g)
+        cf = D.Class_Features(C, d)
+        cf.objective_vectors = S.centroids(C, d, g)
+        put(f"a5 + a4 prototype weights + consensus selection, D={d}",
+            lambda cf=cf, feat=feat: D.consensus_select(pseudo, cf.get_centroid_weight(feat), (hh, ww)))
+        put(f"a6 + a7 calculate_mean_vector + running mean update, D={d}",
+            lambda cf=cf, feat=feat: cf.update_from_features(feat, out, None, "mean"))
+    return res
+
+
+N_SET = 2975            # Cityscapes train: the target set of calc_centroids.py / pseudolabel_generator.py (BASELINE configs 4, 5)
+
+
+def bench_stages(D, S, dev, peak, world):
+    """Every other row of SURVEY.md §8 through its public API call.  Workload sizes are fixed (never tied to --steps):
+    20 timed calls after 5 warm-ups per stage; the whole-set stages always run the full 2975-image set."""
     import random
     from diga_b200 import parallel as P
     g = S.gen(4321 + dist_env()[0], dev)
-    iters, warm = (10, 3) if quick else (30, 5)
+    iters, warm = 20, 5
     out = {}
 
     def add(name, px, bytes_per_px, fn, unit="px", extra=None, sync_free=True):
@@ -486,7 +662,7 @@ def bench_stages(D, S, dev, peak, world, quick):
     # max over ranks ------------------------------------------------------------------------------------------------------
     del feat
     torch.cuda.empty_cache()
-    n_set = 2975 if not quick else 600
+    n_set = N_SET
     mine = len(P.shard_indices(n_set, dist_env()[0], world))
 
     def time_once(fn):
@@ -518,6 +694,7 @@ def bench_stages(D, S, dev, peak, world, quick):
 
     ms4 = time_once(run_config4)
     out["config4_calc_centroids_whole_set"] = {
+        "mode": "sum (one all-reduce of [19, D+1]; equals the reference's running mean for the first pass, num + n <= 3000)",
         "images": n_set, "images_per_rank": mine, "ms": ms4, "images_per_s": n_set / (ms4 * 1e-3),
         "px_per_s": n_set * h * w / (ms4 * 1e-3), "unit": "feature-px/s (all ranks)",
         "image_px_per_s": n_set * hh * ww / (ms4 * 1e-3), "algo_bytes_per_px": d * 4 + C * 4 + 1,
@@ -525,7 +702,38 @@ def bench_stages(D, S, dev, peak, world, quick):
         "frac_hbm": mine * h * w * (d * 4 + C * 4 + 1) / (ms4 * 1e-3) / 1e9 / peak, "allreduce_bytes": C * (d + 1) * 4,
         "note": "calc_centroids.py:67-78 over the rank's share, batches of 8 x [2048,65,129], one NCCL all-reduce at the end; "
                 "eager launches (the loop is the public API), events around the whole share"}
-    del pool4
+    # config 4, EXACT mode (SURVEY.md §8e option i): per-image class vectors kept, ONE all-gather of [images, 19, D] per pass
+    # (463 MB at 2975 x 19 x 2048), ordered replay of the reference recurrence on every rank — bit-identical to the
+    # single-process loop beyond the 3000 clamp and across the reference's five passes (calc_centroids.py:20-23)
+    cf_exact = D.Class_Features(C, d)
+    sp = P.ShardedCentroidPass(cf_exact, n_set, batch=b)
+    gather_ms = [0.0]
+
+    def run_config4_exact(n_img_unused):
+        for k in sp.my_batches():
+            f, o = pool4[k % len(pool4)]
+            take = sp.batch_size_of(k)
+            sp.add(f[:take], o[:take])
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        res = sp.finish()
+        g1.record()
+        gather_ms[0] = (g0, g1)
+        return res
+
+    ms4x = time_once(run_config4_exact)
+    torch.cuda.synchronize()
+    fin_ms = max_over_ranks(gather_ms[0][0].elapsed_time(gather_ms[0][1]), world, dev)
+    out["config4_calc_centroids_whole_set_exact"] = {
+        "mode": "exact (all-gather of the per-image vectors + ordered device replay; every rank ends with the single-process result)",
+        "images": n_set, "images_per_rank": mine, "ms": ms4x, "images_per_s": n_set / (ms4x * 1e-3),
+        "px_per_s": n_set * h * w / (ms4x * 1e-3), "unit": "feature-px/s (all ranks)",
+        "algo_bytes_per_px": d * 4 + C * 4 + 1,
+        "gbs_per_gpu": mine * h * w * (d * 4 + C * 4 + 1) / (ms4x * 1e-3) / 1e9,
+        "frac_hbm": mine * h * w * (d * 4 + C * 4 + 1) / (ms4x * 1e-3) / 1e9 / peak,
+        "gather_plus_replay_ms": fin_ms, "allgather_bytes_per_rank": sp.per_shard * C * (d * 4 + 5),
+        "note": "finish() = all_gather_into_tensor of vec/vecsum/valid (NCCL over NVLink when world > 1) + diga_centroid_update_sharded"}
+    del pool4, sp, cf_exact
 
     # config 5: full-resolution pseudo-labels with prototype rectification, one 1024x2048 image per call
     pool5 = [(S.features((1, d, 129, 257), g), S.logits((1, C, 129, 257), g), S.logits((1, C, 65, 129), g)) for _ in range(4)]
@@ -586,7 +794,9 @@ def bench_stages(D, S, dev, peak, world, quick):
     host_workers = min(8, os.cpu_count() or 4)
     try:
         run_config5_png(16, "gpu", host_workers)
-        ms_g, size_g, d2h_g = run_config5_png(mine, "gpu", host_workers)
+        runs = [run_config5_png(mine, "gpu", host_workers) for _ in range(3)]          # wall clock incl. file I/O: three runs
+        ms_all = sorted(r[0] for r in runs)
+        ms_g, size_g, d2h_g = ms_all[0], runs[0][1], runs[0][2]
         n_pil = min(mine, 96)
         ms_p, size_p, d2h_p = run_config5_png(n_pil, "pil", host_workers)
     except (RuntimeError, OSError) as e:      # a full or read-only scratch directory must not cost the whole bench line
@@ -598,6 +808,8 @@ def bench_stages(D, S, dev, peak, world, quick):
     out["config5_pseudo_labels_whole_set_to_png_files"] = {
         "images": n_set, "images_per_rank": mine, "ms": ms_g, "images_per_s": n_set / (ms_g * 1e-3),
         "px_per_s": n_set * px5 / (ms_g * 1e-3), "unit": "px/s (all ranks)", "host_threads": host_workers,
+        "host_logical_cores": os.cpu_count(), "ms_runs_sorted": ms_all, "ms_median": ms_all[1],
+        "timing": "wall clock (host-bound stage with file I/O; min of 3 runs is `ms`, median beside it) — not a CUDA-event figure",
         "file_bytes_per_image": size_g, "d2h_bytes_per_image": d2h_g, "files_on": file_root or tempfile.gettempdir(),
         "pillow_encoder": {"images_per_rank": n_pil, "ms_per_image": ms_p / n_pil, "images_per_s": world * n_pil / (ms_p * 1e-3),
                            "file_bytes_per_image": size_p, "d2h_bytes_per_image": d2h_p},
@@ -643,7 +855,11 @@ def main():
     ap.add_argument("--no-stages", action="store_true", help="skip the secondary stage measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-baseline-json", action="store_true", help="(internal) run the CPU arm and print its JSON object")
     args = ap.parse_args()
+    if args.cpu_baseline_json:
+        emit_line(cpu_baseline())
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -683,18 +899,53 @@ def main():
         step(i)
     torch.cuda.synchronize()
 
-    # ---- timed region 1 (eager): per-kernel CUDA events for the roofline ---------------------------------------
+    # ---- timed region 1 (eager): the public-API step, and the two kernels of the step launched back to back through the C
+    # ABI with a CUDA event pair around each launch (kernel time, not wrapper time) -----------------------------------------
     K_eager = min(K, 50)
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K_eager)]
     barrier(world)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K_eager):
-        step(i, events[i])
+        step(i)
     e1.record()
     torch.cuda.synchronize()
     eager_ms_step = max_over_ranks(e0.elapsed_time(e1), world, dev) / K_eager
+
+    kd_ws = L.kd_workspace(dev)
+    loss_buf = torch.empty((), dtype=torch.float32, device=dev)
+    ds_buf = torch.empty(KD_SHAPE, dtype=torch.float32, device=dev)
+    st = L.stream()
+    hw_px = hh * ww
+
+    def kd_fwd_launch(i):
+        t, s = sets[i % len(sets)]
+        L.check(L.lib.diga_kd_fwd(t.data_ptr(), s.data_ptr(), n2, C, hw_px, 0.5, loss_buf.data_ptr(), kd_ws.data_ptr(), st))
+
+    def kd_bwd_launch(i):
+        t, s = sets[i % len(sets)]
+        L.check(L.lib.diga_kd_bwd(t.data_ptr(), s.data_ptr(), n2, C, hw_px, 0.5, up.data_ptr(), ds_buf.data_ptr(), st))
+
+    def kd_fused_launch(i):
+        t, s = sets[i % len(sets)]
+        L.check(L.lib.diga_kd_fwd_bwd(t.data_ptr(), s.data_ptr(), n2, C, hw_px, 0.5, UPSTREAM, loss_buf.data_ptr(),
+                                      ds_buf.data_ptr(), kd_ws.data_ptr(), st))
+
+    def kernel_ms(launch, iters=K_eager, warm=3):
+        """Average launch duration: one CUDA event pair per launch on the launching stream, launches queued back to back."""
+        for i in range(warm):
+            launch(i)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            launch(i)
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+    fwd_ms, bwd_ms, fused_ms = kernel_ms(kd_fwd_launch), kernel_ms(kd_bwd_launch), kernel_ms(kd_fused_launch)
+    del ds_buf
 
     # ---- timed region 2 (headline): the same API calls captured once per input set in CUDA graphs and replayed ----
     # The eager Python call chain (autograd.Function, allocator, ctypes) costs more host time per step than the two
@@ -733,23 +984,20 @@ def main():
     # parity of the replayed result with the eager call on the same inputs
     ref_loss, ref_grad = step(0)
     assert torch.equal(ref_loss, graphs[0][1][0]) and torch.equal(ref_grad, graphs[0][1][1]), "graph replay != eager"
-    fwd_ms = statistics.mean(ev[0].elapsed_time(ev[1]) for ev in events)
-    bwd_ms = statistics.mean(ev[1].elapsed_time(ev[2]) for ev in events)
     bwd_gbs = px_step * KD_BYTES_BWD / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = px_step * KD_BYTES_FWD / (fwd_ms * 1e-3) / 1e9
-    traffic = None
+    traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("kd_bwd_dram_bytes_per_launch")
-
-    # fused single-pass variant (228 B/px), same inputs
-    fused_ms = time_loop(lambda: D.distillation_loss_and_grad(sets[0][0], sets[0][1], 0.5, UPSTREAM), 20, 3, world, dev)
+            traffic_db = json.load(f)
+    traffic = traffic_db.get("kd_bwd_dram_bytes_per_launch")
 
     # ---- end to end: host (pinned) inputs -> H2D -> distillation_loss + backward -> D2H loss -----------------
     e2e = None
     if not args.no_e2e:
         ke = max(3, min(K, 30))
+        numa = bind_to_gpu_numa_node(local_rank)           # pinned buffers are first-touched on the GPU's own NUMA node
         host_t = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
         host_s = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
         host_t.copy_(sets[0][0])
@@ -787,12 +1035,35 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         barrier(world)
+        my_ms = a0.elapsed_time(a1) / ke
         e2e_ms = max_over_ranks(a0.elapsed_time(a1), world, dev) / ke
+        h2d_bytes = 2 * host_t.numel() * 4
+        per_rank = [h2d_bytes / (my_ms * 1e-3) / 1e9]
+        if world > 1:
+            gathered = [None] * world
+            torch.distributed.all_gather_object(gathered, (per_rank[0], numa))
+            per_rank, numas = [x[0] for x in gathered], [x[1] for x in gathered]
+        else:
+            numas = [numa]
+        # the copy alone (no kernels): what the host side can feed this rank while every other rank copies too
+        barrier(world)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            bufs[0][0].copy_(host_t, non_blocking=True)
+            bufs[0][1].copy_(host_s, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        copy_gbs = 5 * h2d_bytes / (max_over_ranks(c0.elapsed_time(c1), world, dev) * 1e-3) / 1e9
         e2e = {"value": world * px_step / (e2e_ms * 1e-3), "unit": "pixel-positions/s",
-               "h2d_bytes_per_step": 2 * host_t.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-               "steps": ke, "note": "pinned host logits -> H2D (double-buffered on a copy stream) -> "
-                                    "distillation_loss + autograd.grad -> D2H loss; gradient stays on the device "
-                                    "for the backbone backward; PCIe-bound"}
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+               "steps": ke, "h2d_gbs_per_rank": [round(x, 2) for x in per_rank], "h2d_copy_only_gbs_slowest_rank": round(copy_gbs, 2),
+               "numa": numas, "host_logical_cores": os.cpu_count(),
+               "note": "pinned host logits -> H2D (double-buffered on a copy stream) -> distillation_loss + autograd.grad -> "
+                       "D2H loss; gradient stays on the device for the backbone backward.  PCIe-bound: 637.5 MB per step and "
+                       "rank; with N ranks the box's host memory / PCIe root complexes feed N copies at once "
+                       "(h2d_copy_only_gbs_slowest_rank is the copy without any kernel)"}
         del host_t, host_s, bufs
 
         # Same loss through the patched call site of INTEGRATION.md (distillation_loss_upsampled on the stride-8 logits the
@@ -834,39 +1105,88 @@ def main():
                     "eager; includes the up-sampling the reference arm does not time"}
         del h_lt, h_ls, h_grad, d_lt, d_ls
 
-    stages = None
+    stages, accum_rows, c1_gpu = None, [], None
     if not args.no_stages:
         del sets
         torch.cuda.empty_cache()
-        stages = bench_stages(D, S, dev, peak, world, quick=(K < 50))
+        accum_rows = accum_kernel_rows(L, S, dev, peak)
+        stages = bench_stages(D, S, dev, peak, world)
+        if rank == 0:
+            c1_gpu = config1_gpu_stages(D, S, dev)
 
+    # CPU arm (rank 0, N=1 only): a process of its own — it makes `.cuda()` a no-op to run the reference's code on the host
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline()
+        import subprocess
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-json"], capture_output=True, text=True,
+                             timeout=900)
+        try:
+            cpu = json.loads(res.stdout.strip().splitlines()[-1])
+        except Exception:                                   # noqa: BLE001
+            cpu = {"value": None, "unit": "pixel-positions/s", "cores": None, "kind": "failed", "sample": (res.stderr or res.stdout)[-300:]}
+        if c1_gpu and cpu.get("stages"):
+            for rec in cpu["stages"]:                       # the matching GPU stage beside each CPU stage (same shapes)
+                gpu = c1_gpu.get(rec["stage"])
+                if gpu:
+                    rec.update(gpu)
+                    rec["gpu_over_cpu_all_threads"] = rec["cpu_ms_all_threads"] / gpu["gpu_ms"]
 
     if rank == 0:
+        def row(stage, kernel, bound, unit, units, bytes_per_unit, ms, how, traffic_key=None, extra=None):
+            gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
+            r = {"row": stage, "kernel": kernel, "bound": bound, "unit": unit, "units_per_launch": units,
+                 "algo_bytes_per_unit": bytes_per_unit, "algo_bytes_per_launch": units * bytes_per_unit, "avg_launch_ms": ms,
+                 "units_per_s_per_gpu": units / (ms * 1e-3), "achieved_gbs": gbs, "frac": gbs / peak,
+                 "frac_of_8000_spec": gbs / 8000.0, "traffic": traffic_db.get(traffic_key) if traffic_key else None, "how": how}
+            if extra:
+                r.update(extra)
+            return r
+
+        ev_how = "CUDA event pair per launch, C-ABI launches queued back to back, rotating inputs >> L2"
+        gr_how = "public-API call replayed from a CUDA graph (CUDA events around 20 replays)"
+        rows = [
+            row("a1", "kd_kernel<LOSS> (forward)", "hbm", "pixel-position", px_step, KD_BYTES_FWD, fwd_ms, ev_how, "kd_fwd_dram_bytes_per_launch"),
+            row("a1", "kd_kernel<GRAD> (backward)", "hbm", "pixel-position", px_step, KD_BYTES_BWD, bwd_ms, ev_how, "kd_bwd_dram_bytes_per_launch"),
+            row("a1", "kd_kernel<LOSS,GRAD> (single pass)", "hbm", "pixel-position", px_step, KD_BYTES_BWD, fused_ms, ev_how),
+        ] + [row(*r) for r in accum_rows]
+        if stages:
+            def from_stage(stage, key, kernel, bound, unit, traffic_key=None, extra=None):
+                st_ = stages.get(key)
+                if st_ and "ms" in st_:
+                    px = st_["px_per_s"] / world * st_["ms"] * 1e-3
+                    rows.append(row(stage, kernel, bound, unit, px, st_["algo_bytes_per_px"], st_["ms"], gr_how, traffic_key, extra))
+            from_stage("a3", "pseudo_label_1scale", "pseudo_label_kernel (one scale)", "hbm", "px", "pl1_dram_bytes_per_launch")
+            from_stage("a3", "pseudo_label_2scale", "pseudo_label_kernel (two scales, max-fused)", "hbm", "px", "pl2_dram_bytes_per_launch")
+            from_stage("a3+f1", "pseudo_label_fused_upsample_labels_only", "pseudo_label_upsampled_kernel (labels from stride-8 logits)", "alu", "px")
+            from_stage("a4", "consensus_select", "consensus_select_kernel", "alu", "px", "select_dram_bytes_per_launch")
+            from_stage("a2", "classmix_dacs_blend_kernel", "classmix_blend_kernel (DACS)", "hbm", "px", "cm_dram_bytes_per_launch")
+            from_stage("a5", "proto_distance_softmax_d2048", "proto_umma_kernel (tcgen05 3xTF32)", "hbm", "feature-px", "proto_dram_bytes_per_launch")
+            from_stage("a6+a7", "centroid_accumulate_update_d2048_iid_classes", "update_from_features call: assign + accum + finish (i.i.d. classes)", "hbm", "feature-px")
+            from_stage("a6+a7", "centroid_accumulate_update_d2048_blocky_classes", "update_from_features call: assign + accum + finish (4x4 blocks)", "hbm", "feature-px")
+            from_stage("f2", "cross_entropy2d_fwd_bwd", "ce_kernel fwd + bwd", "hbm", "px")
+            from_stage("f4", "ema_teacher_update", "ema_update_kernel", "hbm", "parameter")
+            for key, label in (("config3_self_training_step_fused_call_sites", "config 3: self-training step hot path, B=8 @512x1024, D=2048 (patched call sites)"),
+                               ("config4_calc_centroids_whole_set", "config 4: calc_centroids over 2975 images, sum mode (one all-reduce)"),
+                               ("config4_calc_centroids_whole_set_exact", "config 4: calc_centroids over 2975 images, exact mode (all-gather + ordered replay)"),
+                               ("config5_pseudo_labels_whole_set", "config 5: 2975 full-resolution pseudo-label maps with prototype rectification")):
+                st_ = stages.get(key)
+                if st_:
+                    rows.append({"row": key, "kernel": label, "bound": "hbm", "ms": st_["ms"], "px_per_s_all_ranks": st_["px_per_s"],
+                                 "images_per_s_all_ranks": st_.get("images_per_s"), "achieved_gbs": st_["gbs_per_gpu"],
+                                 "frac": st_["frac_hbm"], "how": "CUDA events around the whole stage, max over ranks"})
         line = {
-            "metric": "pixels/sec (symmetric KD loss fwd+bwd)", "value": value, "unit": "pixel-positions/s",
+            "metric": METRIC, "value": value, "unit": "pixel-positions/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 2: symmetric KD fwd+bwd, logits [8,19,512,1024] (B=4 per view) per GPU, "
-                                   "distillation_loss + autograd (fwd 152 B/px + bwd 228 B/px)",
-                       "shape": list(KD_SHAPE), "pixel_positions_per_step_per_gpu": px_step,
-                       "l2": "inputs 638 MB per step exceed the 126 MB L2; 3 rotating input sets",
-                       "launch": "each input set's distillation_loss + autograd.grad call captured in a CUDA graph, "
-                                 "replayed K times (eager_ms_per_step reported beside it)",
-                       "parallelism": f"image-sharded x{world}, no data-path collective"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "notes": {"l2": "inputs 638 MB per step exceed the 126 MB L2; 3 rotating input sets",
+                      "launch": "each input set's distillation_loss + autograd.grad call captured in a CUDA graph, replayed K "
+                                "times (eager_ms_per_step reported beside it)",
+                      "parallelism": f"image-sharded x{world}, no data-path collective on the headline step; the centroid "
+                                     "stages (roofline.rows config4_*) carry the one exchange"},
             "roofline": {"bound": "hbm", "kernel": "kd_kernel<GRAD> (backward)", "achieved": bwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algo_bytes_per_launch": px_step * KD_BYTES_BWD, "avg_launch_ms": bwd_ms,
-                         "frac_of_8000_spec": bwd_gbs / 8000.0},
-            "kernels": {"kd_fwd": {"ms": fwd_ms, "gbs": fwd_gbs, "frac": fwd_gbs / peak, "algo_bytes_per_px": KD_BYTES_FWD,
-                                   "note": "event pair brackets the Python autograd.Function call"},
-                        "kd_bwd": {"ms": bwd_ms, "gbs": bwd_gbs, "frac": bwd_gbs / peak, "algo_bytes_per_px": KD_BYTES_BWD},
-                        "kd_fused_fwd_bwd": {"ms": fused_ms, "gbs": px_step * KD_BYTES_BWD / (fused_ms * 1e-3) / 1e9,
-                                             "frac": px_step * KD_BYTES_BWD / (fused_ms * 1e-3) / 1e9 / peak,
-                                             "px_per_s": world * px_step / (fused_ms * 1e-3),
-                                             "note": "distillation_loss_and_grad: loss + gradient in one 228 B/px pass"}},
+                         "frac_of_8000_spec": bwd_gbs / 8000.0, "rows": rows},
             "eager_ms_per_step": eager_ms_step,
             "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "stages": stages, "cpu_baseline": cpu,
         }

@@ -79,11 +79,8 @@ class Class_Features:
                                "construct Class_Features(device=...) on the device that produces the features")
 
     # -- a6 -------------------------------------------------------------------------------------
-    @L.on_device
-    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out_rows=None):
-        """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
-        ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy.
-        ``out_rows``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
+    def _class_sums(self, feat_cls, outputs, labels_val, labels_full=None):
+        """assign -> accum on the current stream.  Returns (sums [N,C,D], counts [N,C] int32, hw)."""
         L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
         feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
         n, d, h, w = feat.shape
@@ -106,6 +103,24 @@ class Class_Features:
         clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev)
         counts = torch.empty((n, c), dtype=torch.int32, device=dev)
         sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
+        if full is not None:
+            L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
+                                                       cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), st))
+        else:
+            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(),
+                                               clsw.data_ptr(), st))
+        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, c, hw,
+                                          sums.data_ptr(), st))
+        return sums, counts, hw
+
+    @L.on_device
+    def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out_rows=None):
+        """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
+        ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy.
+        ``out_rows``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
+        sums, counts, hw = self._class_sums(feat_cls, outputs, labels_val, labels_full)
+        n, c, d = sums.shape
+        dev, st = sums.device, L.stream()
         if out_rows is not None:
             vec, vecsum, valid = out_rows
             if (tuple(vec.shape), tuple(vecsum.shape), tuple(valid.shape)) != ((n, c, d), (n, c), (n, c)) or \
@@ -115,14 +130,6 @@ class Class_Features:
             vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
             vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
             valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
-        if full is not None:
-            L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
-                                                       cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), st))
-        else:
-            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(),
-                                               clsw.data_ptr(), st))
-        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, c, hw,
-                                          sums.data_ptr(), st))
         L.check(L.lib.diga_centroid_means(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, vec.data_ptr(),
                                           vecsum.data_ptr(), valid.data_ptr(), st))
         return vec, vecsum, valid
@@ -172,14 +179,36 @@ class Class_Features:
         ``update_objective_SingleVector`` on every returned vector in order, with no host sync."""
         mode = self._mode(name)
         self._require_state_device(feat_cls)
-        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val, labels_full)
-        n, c, d = vec.shape
+        L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
+        feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
+        n, d, h, w = feat.shape
+        c = self.class_numbers
         if d != self.feat_dim:
             raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")
+        if out.shape != (n, c, h, w):
+            raise ValueError(f"outputs must be [{n},{c},{h},{w}], got {tuple(out.shape)}")
+        if labels_val is not None and labels_full is not None:
+            raise ValueError("pass either labels_val (down-sampled fp32) or labels_full (int64), not both")
+        lab = full = None
+        hh = ww = 0
+        if labels_val is not None:
+            lab = L.f32c(labels_val.detach())
+            if lab.shape != (n, 1, h, w):
+                raise ValueError(f"labels_val must be [{n},1,{h},{w}], got {tuple(lab.shape)}")
+        if labels_full is not None:
+            full = L.i64c(labels_full)
+            if full.dim() != 3 or full.shape[0] != n:
+                raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
+            hh, ww = full.shape[1], full.shape[2]
         self._proto_key = None
-        L.check(L.lib.diga_centroid_update(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d,
-                                           self._objective_vectors.data_ptr(), self._objective_vectors_num.data_ptr(),
-                                           mode, int(bool(start_mean)), float(self.centroid_momentum), L.stream()))
+        # ONE scratch tensor and ONE library call queue the whole chain (assign -> accum -> finish): the reference drives this
+        # path one image per call (calc_centroids.py:67-78), where per-kernel FFI calls and scratch tensors cost more host
+        # time than the kernels take
+        ws = torch.empty((int(L.lib.diga_centroid_chain_workspace_bytes(n, c, d, h * w)),), dtype=torch.uint8, device=feat.device)
+        L.check(L.lib.diga_centroid_chain(feat.data_ptr(), out.data_ptr(), L.ptr(lab), L.ptr(full), hh, ww, n, c, d, h, w,
+                                          ws.data_ptr(), self._objective_vectors.data_ptr(),
+                                          self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
+                                          float(self.centroid_momentum), L.stream()))
 
     def _update_sharded(self, gvec, gsum, gvalid, n_total, batch, world, per_shard, name='mean', start_mean=True):
         """Ordered replay of an all-gathered row buffer (``diga_b200.parallel``): the reference recurrence over the

@@ -16,7 +16,11 @@
 // piecewise constant, so a shared per-class cell would see 32-way same-address collisions.
 // A CTA owns (image, 4-row group) and covers all pixels of that image, so every sums[n][c][d] has
 // exactly one writer: no global atomics, bitwise deterministic.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace diga {
 
@@ -45,7 +49,10 @@ __device__ __forceinline__ void clsw_pads(uint8_t* m, int64_t wp, int64_t hw, in
   }
 }
 
-template <int BLOCK>
+// kC: compile-time class count (19, 16, or 32 = padded generic, see DIGA_DISPATCH_C): the per-pixel loads are unrolled, so
+// all of a pixel's class planes are requested before the first comparison (the rolled loop exposed one latency per class:
+// 6 us for [8,19,65,129]).
+template <int BLOCK, int kC, bool kPad>
 __global__ void __launch_bounds__(BLOCK)
 centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int nclass, int64_t hw,
                        uint8_t* __restrict__ cls, int32_t* __restrict__ counts, uint32_t* __restrict__ clsw,
@@ -63,12 +70,15 @@ centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict
     const int64_t p = base + threadIdx.x;
     int c = 255;
     if (p < hw) {
-      float m = __ldg(lg + p);
+      float z[kC];
+#pragma unroll
+      for (int k = 0; k < kC; ++k) z[k] = (!kPad || k < nclass) ? __ldg(lg + (int64_t)k * hw + p) : -INFINITY;
+      float m = z[0];
       int am = 0;
-      for (int k = 1; k < nclass; ++k) {
-        const float v = __ldg(lg + (int64_t)k * hw + p);
-        if (v > m) {   // argmax(softmax(out)) == first index of the max logit (calc_centroids.py:121-122)
-          m = v;
+#pragma unroll
+      for (int k = 1; k < kC; ++k) {
+        if (z[k] > m) {   // argmax(softmax(out)) == first index of the max logit (calc_centroids.py:121-122)
+          m = z[k];
           am = k;
         }
       }
@@ -963,6 +973,112 @@ centroid_update_num_kernel(const float* __restrict__ vecsum, const uint8_t* __re
   }
 }
 
+// means + update + count in ONE launch for the online path (a batch of <= kFinishMaxRows image rows per thread): one
+// thread-block CLUSTER per class, CTA y of the cluster owns channels [y*BLOCK, (y+1)*BLOCK) (+ k * Y*BLOCK).  The thread
+// turns the class sums of its channel into the per-image mean vectors (calc_centroids.py:129,141, same expression as
+// centroid_means_kernel), the CTAs exchange their partial channel sums through distributed shared memory to obtain
+// vector.sum() of every image (:148) in a fixed order, and the recurrence of :150-161 runs in registers.  Exactly one
+// cluster touches objnum[c]: every CTA reads it before the first cluster barrier, rank 0 writes it after the last.
+constexpr int kFinishMaxRows = 16;
+
+template <int BLOCK, int K, int NR>
+__global__ void __launch_bounds__(BLOCK)
+centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict__ counts, int n, int64_t C, int64_t D,
+                       int64_t hw, float* __restrict__ vec, float* __restrict__ vecsum, uint8_t* __restrict__ valid,
+                       float* __restrict__ obj, float* __restrict__ objnum, UpdateRule rule, int do_update) {
+  static_assert(NR * K <= kFinishMaxRows, "register budget");   // NR: image rows a thread holds (>= n), K: channels per row
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float warp_part[NR][BLOCK / 32];
+  __shared__ float cta_part[NR];
+  __shared__ float tot[NR];
+  const int64_t c = blockIdx.x;
+  const int Y = gridDim.y;                                   // == cluster size along y
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float num = do_update ? objnum[c] : 0.f;
+  float v[NR][K];                                            // image i, channel dbase + k*Y*BLOCK
+  const int64_t dbase = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
+  // all loads first (counts, then the sums unconditionally), arithmetic afterwards: the divisions below carry a slow-path
+  // branch each, and ptxas does not move loads across them — interleaved, every row paid two exposed L2 latencies
+  // (ncu: 14.8 us for 8 rows; now one latency for the whole batch)
+  int cnt[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) cnt[i] = i < n ? __ldg(counts + i * C + c) : 0;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int64_t d = dbase + (int64_t)k * Y * BLOCK;
+      v[i][k] = (i < n && d < D) ? __ldg(sums + (i * C + c) * D + d) : 0.f;      // (garbage where cnt == 0: masked below)
+    }
+  }
+  const float fhw = (float)hw;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int64_t d = dbase + (int64_t)k * Y * BLOCK;
+      // calc_centroids.py:129,141: avgpool(feat*mask) / avgpool(mask) == (sum/hw) / (count/hw)
+      v[i][k] = (i < n && d < D && cnt[i] > 0) ? (v[i][k] / fhw) / ((float)cnt[i] / fhw) : 0.f;
+      if (i < n && d < D && vec != nullptr) vec[(i * C + c) * D + d] = v[i][k];
+    }
+  }
+  // vector.sum() per image: warp -> CTA -> cluster, every level in a fixed order
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (i < n) {                                             // CTA-uniform
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) p += v[i][k];
+      p = warp_sum(p);
+      if (lane == 0) warp_part[i][warp] = p;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    float p = 0.f;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) p += warp_part[threadIdx.x][w];
+    cta_part[threadIdx.x] = p;
+  }
+  cluster.sync();
+  if ((int)threadIdx.x < n) {
+    float part[8];                                           // cluster size <= 8: all remote loads in flight together
+#pragma unroll
+    for (int r = 0; r < 8; ++r) part[r] = r < Y ? *cluster.map_shared_rank(&cta_part[threadIdx.x], r) : 0.f;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r];                // fixed order
+    tot[threadIdx.x] = t;
+    if (blockIdx.y == 0) {
+      if (vecsum != nullptr) vecsum[threadIdx.x * C + c] = t;
+      if (valid != nullptr) valid[threadIdx.x * C + c] = __ldg(counts + threadIdx.x * C + c) >= 5 ? 1 : 0;   // :134, :136
+    }
+  }
+  cluster.sync();                                            // remote reads done before any CTA may exit; tot[] visible
+  if (!do_update) return;
+  float o[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int64_t d = dbase + (int64_t)k * Y * BLOCK;
+    o[k] = d < D ? obj[c * D + d] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (i < n && cnt[i] >= 5 && tot[i] != 0.f) {                          // :134/:136 skips, :148
+      const bool mean = rule_is_mean(rule, num);
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = rule_apply(rule, mean, o[k], num, v[i][k]);
+      num = fminf(__fadd_rn(num, 1.f), 3000.f);                           // :155-156 / :159,161
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int64_t d = dbase + (int64_t)k * Y * BLOCK;
+    if (d < D) obj[c * D + d] = o[k];
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) objnum[c] = num;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_update_single_kernel(const float* __restrict__ v, int64_t id, int64_t D, float* __restrict__ obj,
@@ -1061,7 +1177,9 @@ int diga_centroid_assign(const float* logits, const float* labels, int64_t n, in
   int64_t gx = (hw + BLOCK - 1) / BLOCK;
   const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
   if (gx > cap) gx = cap;
-  centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(logits, labels, (int)C, hw, cls, counts, clsw);
+  DIGA_DISPATCH_C(C, {
+    centroid_assign_kernel<BLOCK, kC, kPad><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(logits, labels, (int)C, hw, cls, counts, clsw);
+  });
   DIGA_CHECK_LAUNCH("centroid_assign_kernel");
   return DIGA_OK;
 }
@@ -1085,8 +1203,10 @@ int diga_centroid_assign_fullres(const float* logits, const int64_t* labels_full
   int64_t gx = (hw + BLOCK - 1) / BLOCK;
   const int64_t cap = ((int64_t)sm_count() * 8 + n - 1) / n;
   if (gx > cap) gx = cap;
-  centroid_assign_kernel<BLOCK><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(
-      logits, nullptr, (int)C, hw, cls, counts, clsw, labels_full, (int)w, (int)H, (int)W, (float)H / (float)h, (float)W / (float)w);
+  DIGA_DISPATCH_C(C, {
+    centroid_assign_kernel<BLOCK, kC, kPad><<<dim3((unsigned)gx, (unsigned)n), BLOCK, 0, st>>>(
+        logits, nullptr, (int)C, hw, cls, counts, clsw, labels_full, (int)w, (int)H, (int)W, (float)H / (float)h, (float)W / (float)w);
+  });
   DIGA_CHECK_LAUNCH("centroid_assign_kernel");
   return DIGA_OK;
 }
@@ -1209,6 +1329,128 @@ int diga_centroid_update_sharded(const float* vec, const float* vecsum, const ui
                (long long)per_shard, (long long)batches, (long long)group, (long long)world);
   return launch_centroid_update(vec, vecsum, valid, n_total, C, D, objective_vectors, objective_num, mode, start_mean, momentum,
                                 ImageOrder{group, world, per_shard}, (cudaStream_t)stream);
+}
+
+int diga_centroid_finish_supported(int64_t n, int64_t D) {
+  if (n < 1 || D < 1) return 0;
+  const int64_t Y = (D + 255) / 256 < 8 ? (D + 255) / 256 : 8;
+  int64_t K = (D + Y * 256 - 1) / (Y * 256), Kp = 1, Np = 1;
+  while (Kp < K) Kp *= 2;                                  // kernel instantiations: K in {1, 2, 4}, rows in {1, 2, 4, 8, 16}
+  while (Np < n) Np *= 2;
+  return (Kp <= 4 && Np * Kp <= diga::kFinishMaxRows) ? 1 : 0;
+}
+
+int diga_centroid_finish(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw, float* vec,
+                         float* vecsum, uint8_t* valid, float* objective_vectors, float* objective_num, int mode, int start_mean,
+                         double momentum, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(sums && counts, DIGA_ERR_INVALID, "centroid_finish: null pointer");
+  const int do_update = objective_vectors != nullptr;
+  DIGA_REQUIRE(!do_update || objective_num != nullptr, DIGA_ERR_INVALID, "centroid_finish: objective_num missing");
+  DIGA_REQUIRE(!do_update || mode == DIGA_UPDATE_MEAN || mode == DIGA_UPDATE_MOVING_AVERAGE, DIGA_ERR_INVALID,
+               "no such updating way of objective vectors %d", mode);
+  DIGA_REQUIRE(C >= 1 && C <= 65535 && hw > 0, DIGA_ERR_INVALID, "centroid_finish: bad sizes");
+  DIGA_REQUIRE(diga_centroid_finish_supported(n, D), DIGA_ERR_INVALID,
+               "centroid_finish: n=%lld rows of D=%lld exceed the register budget (use centroid_means + centroid_update)",
+               (long long)n, (long long)D);
+  const int64_t Y = (D + 255) / 256 < 8 ? (D + 255) / 256 : 8;
+  const int64_t K = (D + Y * 256 - 1) / (Y * 256);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, (unsigned)Y, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)Y;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const UpdateRule rule = make_rule(do_update ? mode : DIGA_UPDATE_MEAN, start_mean, momentum);
+  cudaError_t e = cudaSuccess;
+  int np = 1;
+  while (np < n) np *= 2;
+#define DIGA_FINISH_KN(KK, NN)                                                                                                \
+  e = cudaLaunchKernelEx(&cfg, centroid_finish_kernel<256, KK, NN>, sums, counts, (int)n, C, D, hw, vec, vecsum, valid,      \
+                         objective_vectors, objective_num, rule, do_update)
+#define DIGA_FINISH_K(KK)                                                                                                     \
+  do {                                                                                                                        \
+    if (np == 1) DIGA_FINISH_KN(KK, 1);                                                                                       \
+    else if (np == 2) DIGA_FINISH_KN(KK, 2);                                                                                  \
+    else if (np == 4) DIGA_FINISH_KN(KK, 4);                                                                                  \
+    else if (np == 8) { if constexpr (KK <= 2) DIGA_FINISH_KN(KK, (KK <= 2 ? 8 : 1)); }                                       \
+    else { if constexpr (KK <= 1) DIGA_FINISH_KN(KK, (KK <= 1 ? 16 : 1)); }                                                   \
+  } while (0)
+  if (K <= 1) DIGA_FINISH_K(1);
+  else if (K <= 2) DIGA_FINISH_K(2);
+  else DIGA_FINISH_K(4);
+#undef DIGA_FINISH_K
+#undef DIGA_FINISH_KN
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("centroid_finish_kernel: launch failed: %s", cudaGetErrorString(e));
+    return DIGA_ERR_CUDA;
+  }
+  DIGA_CHECK_LAUNCH("centroid_finish_kernel");
+  return DIGA_OK;
+}
+
+// ---- a6 -> a7 as ONE call: assign -> accum -> finish (or means + update for batches finish cannot hold) on `stream`.
+// The per-image call sequence of the reference's loops (calc_centroids.py:67-78: one image per call) is host-bound when every
+// kernel is its own FFI call with its own scratch tensors; this entry point takes one workspace and queues the whole chain.
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int64_t diga_centroid_chain_workspace_bytes(int64_t n, int64_t C, int64_t D, int64_t hw) {
+  if (n < 0 || C < 1 || D < 0 || hw < 0) return 0;
+  size_t b = align_up((size_t)n * C * sizeof(int32_t), 256);                       // counts
+  b += align_up((size_t)diga_centroid_clsw_bytes(n, hw), 256);                     // phase-shifted class words
+  b += align_up((size_t)n * hw, 256);                                              // class map
+  b += align_up((size_t)n * C * D * sizeof(float), 256);                           // class sums
+  if (!diga_centroid_finish_supported(n, D)) {
+    b += align_up((size_t)n * C * D * sizeof(float), 256);                         // vec
+    b += align_up((size_t)n * C * sizeof(float), 256) + align_up((size_t)n * C, 256);   // vecsum, valid
+  }
+  return (int64_t)b;
+}
+
+int diga_centroid_chain(const float* feat, const float* logits, const float* labels, const int64_t* labels_full, int64_t H,
+                        int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
+                        float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
+                        diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(feat && logits && workspace && objective_vectors && objective_num, DIGA_ERR_INVALID, "centroid_chain: null pointer");
+  DIGA_REQUIRE(!(labels && labels_full), DIGA_ERR_INVALID, "centroid_chain: pass labels or labels_full, not both");
+  DIGA_REQUIRE(aligned(workspace, 256), DIGA_ERR_MISALIGNED, "centroid_chain: workspace must be 256-byte aligned");
+  DIGA_REQUIRE(n >= 0 && h >= 0 && w >= 0, DIGA_ERR_INVALID, "centroid_chain: bad sizes");
+  if (n == 0) return DIGA_OK;
+  const int64_t hw = h * w;
+  unsigned char* p = static_cast<unsigned char*>(workspace);
+  int32_t* counts = reinterpret_cast<int32_t*>(p);
+  p += align_up((size_t)n * C * sizeof(int32_t), 256);
+  uint32_t* clsw = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)diga_centroid_clsw_bytes(n, hw), 256);
+  uint8_t* cls = p;
+  p += align_up((size_t)n * hw, 256);
+  float* sums = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * D * sizeof(float), 256);
+  int rc = labels_full ? diga_centroid_assign_fullres(logits, labels_full, n, C, h, w, H, W, cls, counts, clsw, stream)
+                       : diga_centroid_assign(logits, labels, n, C, hw, cls, counts, clsw, stream);
+  if (rc != DIGA_OK) return rc;
+  if (hw == 0 || D == 0) return DIGA_OK;
+  rc = diga_centroid_accum(feat, cls, counts, clsw, n, D, C, hw, sums, stream);
+  if (rc != DIGA_OK) return rc;
+  if (diga_centroid_finish_supported(n, D))
+    return diga_centroid_finish(sums, counts, n, C, D, hw, nullptr, nullptr, nullptr, objective_vectors, objective_num, mode,
+                                start_mean, momentum, stream);
+  float* vec = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * D * sizeof(float), 256);
+  float* vecsum = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * sizeof(float), 256);
+  uint8_t* valid = p;
+  rc = diga_centroid_means(sums, counts, n, C, D, hw, vec, vecsum, valid, stream);
+  if (rc != DIGA_OK) return rc;
+  return diga_centroid_update(vec, vecsum, valid, n, C, D, objective_vectors, objective_num, mode, start_mean, momentum, stream);
 }
 
 int diga_centroid_update_single(const float* vector, int64_t id, int64_t C, int64_t D, float* objective_vectors,

@@ -140,6 +140,24 @@ int diga_centroid_means(const float* sums, const int32_t* counts, int64_t n, int
 int diga_centroid_update(const float* vec, const float* vecsum, const uint8_t* valid, int64_t n, int64_t C,
                          int64_t D, float* objective_vectors, float* objective_num, int mode, int start_mean,
                          double momentum, diga_stream_t stream);
+/* means + update in one launch (the online path: a batch of a few images per call): equals diga_centroid_means followed by
+ * diga_centroid_update on the same rows.  One thread-block cluster per class; the per-image vector.sum() of :148 is reduced
+ * over the cluster through distributed shared memory.  vec / vecsum / valid are optional outputs (NULL: not stored);
+ * objective_vectors == NULL: only the means are produced.  Supported while diga_centroid_finish_supported(n, D) != 0
+ * (n * ceil(D / 2048) <= 16 rows per thread), larger batches use the two separate calls. */
+int diga_centroid_finish_supported(int64_t n, int64_t D);
+int diga_centroid_finish(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw,
+                         float* vec, float* vecsum, uint8_t* valid, float* objective_vectors, float* objective_num,
+                         int mode, int start_mean, double momentum, diga_stream_t stream);
+/* a6 -> a7 in ONE call (what Class_Features.update_from_features queues): assign (labels: [n,1,h*w] fp32 or NULL;
+ * labels_full: [n,H,W] int64 or NULL) -> accum -> finish (means + update when the batch is too large for finish), all on
+ * `stream`, scratch in one caller-allocated 256-byte aligned workspace of diga_centroid_chain_workspace_bytes bytes.
+ * Equals calculate_mean_vector followed by update_objective_SingleVector on every vector in (image, class) order. */
+int64_t diga_centroid_chain_workspace_bytes(int64_t n, int64_t C, int64_t D, int64_t hw);
+int diga_centroid_chain(const float* feat, const float* logits, const float* labels, const int64_t* labels_full,
+                        int64_t H, int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
+                        float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
+                        diga_stream_t stream);
 /* Image-sharded exact replay (calc_centroids.py:20-23,67-78,147-164): vec/vecsum/valid are the all-gather
  * of every rank's rows, [world][per_shard] x C (x D); rank r holds loader batches r, r+world, ... of `group` images each.
  * The n_total images are visited in GLOBAL loader order (image g = batch g/group, position g%group), so every rank

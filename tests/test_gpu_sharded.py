@@ -418,3 +418,41 @@ def test_ema_more_than_512_tensors_with_empty_ones(D):
     ema_update_tensors(tg, sg, alpha)
     for a, b in zip(tg, want):
         assert np.array_equal(a.cpu().numpy().view(np.uint32), b.numpy().view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ fused means + update
+@pytest.mark.parametrize("n,d,h,w,name,start_mean", [(8, 2048, 33, 65, "moving_average", True), (4, 4096, 9, 11, "mean", True),
+                                                     (3, 100, 9, 11, "moving_average", False), (16, 256, 17, 19, "mean", True),
+                                                     (1, 8192, 9, 11, "moving_average", True), (2, 30, 5, 5, "mean", True)])
+def test_finish_kernel_equals_means_plus_update_bitwise(D, n, d, h, w, name, start_mean):
+    """diga_centroid_finish (one cluster launch: means, vector.sum() over distributed shared memory, recurrence) against
+    diga_centroid_means + diga_centroid_update on the same class sums: centroids and counts bit-equal, incl. a zero-sum
+    vector, an all-gated image and the start_mean switch at num == 100."""
+    from diga_b200 import _lib as L, synthetic as S
+    g = S.gen(71, "cuda")
+    c = 19
+    feat, out, lab = _inputs(n, d, h, w, c, g, labels=True)
+    if n > 1:
+        lab[1] = 255.0
+    feat[0].masked_fill_((out.argmax(1)[0] == 1).unsqueeze(0), 0.0)
+    assert L.lib.diga_centroid_finish_supported(n, d)
+    a, b = D.Class_Features(c, d), D.Class_Features(c, d)
+    start = (S.centroids(c, d, g), torch.full((c,), 98.0, device=dev()))
+    for cf in (a, b):
+        cf.objective_vectors, cf.objective_vectors_num = start[0].clone(), start[1].clone()
+    for _ in range(3):                                         # crosses num == 100
+        a.update_from_features(feat, out, lab, name, start_mean)                       # fused path
+        vec, vecsum, valid = b._masked_means(feat, out, lab)                           # separate kernels
+        L.check(L.lib.diga_centroid_update(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d, b.objective_vectors.data_ptr(),
+                                           b.objective_vectors_num.data_ptr(), {"mean": 0, "moving_average": 1}[name], int(start_mean),
+                                           1e-4, L.stream()))
+    assert torch.equal(a.objective_vectors_num, b.objective_vectors_num)
+    assert torch.equal(a.objective_vectors, b.objective_vectors)
+    # the optional outputs of the fused kernel equal the means kernel's (vecsum: another summation order, 1e-6)
+    sums, counts, hw = a._class_sums(feat, out, lab)
+    v2, s2, ok2 = torch.empty_like(vec), torch.empty_like(vecsum), torch.empty_like(valid)
+    L.check(L.lib.diga_centroid_finish(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, v2.data_ptr(), s2.data_ptr(), ok2.data_ptr(),
+                                       None, None, 0, 1, 1e-4, L.stream()))
+    assert torch.equal(v2, vec) and torch.equal(ok2, valid)
+    assert torch.allclose(s2, vecsum, rtol=1e-5, atol=1e-5 * float(vec.abs().max()) * 4)
+    assert not L.lib.diga_centroid_finish_supported(17, 2048) and not L.lib.diga_centroid_finish_supported(2, 8 * 2048 + 1)
