@@ -25,6 +25,8 @@ namespace cg = cooperative_groups;
 namespace diga {
 
 int tunable(const char* name, int dflt);
+__device__ __forceinline__ void pdl_wait();
+__device__ __forceinline__ void pdl_launch_dependents();
 
 // ------------------------------------------------------------------------------------------------
 // assign
@@ -59,6 +61,7 @@ centroid_assign_kernel(const float* __restrict__ logits, const float* __restrict
                        const int64_t* __restrict__ labels_full = nullptr,
                        int w = 0, int HH = 0, int WW = 0, float sy = 0.f, float sx = 0.f) {
   __shared__ int hist[DIGA_MAX_CLASSES];
+  pdl_launch_dependents();      // the accumulation kernel may start fetching features (which this kernel does not write)
   if (threadIdx.x < DIGA_MAX_CLASSES) hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t img = blockIdx.y;
@@ -436,6 +439,13 @@ centroid_accum_quad_kernel(const float* __restrict__ feat, const uint8_t* __rest
 // ncu of the round-1 kernel: 374 warp instructions per 4 KB batch, issue slots 41 % busy with every warp waiting on a
 // load; this loop issues ~100.
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (the a6 -> a7 chain, diga_centroid_chain): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible (a no-op for a normally launched kernel), pdl_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as every CTA of this grid has passed it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -476,12 +486,17 @@ struct LeanItem {
   int T;                  // full quads in the row
 };
 
+template <bool FEATURES = true, bool CLASSES = true>
 __device__ __forceinline__ void lean_load(LeanUnit& u, const LeanItem& it, int t, uint32_t dummy4) {
   const unsigned tt = (unsigned)min(t, it.T - 1);  // lanes past the end re-read the last quad against a dummy class word
-  u.cw = __ldg(it.cw + tt);                        // (selected against the dummy word at apply time: no wait here)
-  u.in_row = t < it.T;
+  if constexpr (CLASSES) {
+    u.cw = __ldg(it.cw + tt);                      // (selected against the dummy word at apply time: no wait here)
+    u.in_row = t < it.T;
+  }
+  if constexpr (FEATURES) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) u.x[j] = ldg128_stream(reinterpret_cast<const float*>(it.row[j] + tt));
+    for (int j = 0; j < 4; ++j) u.x[j] = ldg128_stream(reinterpret_cast<const float*>(it.row[j] + tt));
+  }
 }
 
 __device__ __forceinline__ void f4_add_if(float4& a, const float4& b, bool p) {
@@ -611,8 +626,14 @@ centroid_accum_lean_kernel(const float* __restrict__ feat, const uint32_t* __res
   setup(item, it, img, d0, s);
   LeanUnit ring[P];
   const int first = warp * 32 + lane;
+  // first batch: the features are requested BEFORE the grid dependency is awaited (in the chain the predecessor is the
+  // assign kernel, which writes the class words and counts but not the features), the class words after it
 #pragma unroll
-  for (int k = 0; k < P; ++k) lean_load(ring[k], it, first + k * STRIDE, dummy4);   // (rounds past the row: dummy words)
+  for (int k = 0; k < P; ++k) lean_load<true, false>(ring[k], it, first + k * STRIDE, dummy4);   // (rounds past the row: clamped)
+  pdl_wait();
+  pdl_launch_dependents();
+#pragma unroll
+  for (int k = 0; k < P; ++k) lean_load<false, true>(ring[k], it, first + k * STRIDE, dummy4);
 
   while (true) {
     // classes present in this image (per-image counts): absent ones are neither cleared nor reduced nor written
@@ -709,6 +730,8 @@ __global__ void centroid_clsw_build_kernel(const uint8_t* __restrict__ cls, int 
   clsw[(img * 4 + phi) * wp + wi] = word;
 }
 
+static thread_local bool g_chain_pdl = false;     // set by diga_centroid_chain around its launches (same thread): launch as programmatic dependents
+
 template <int WARPS, int P, int MINB, int MODE, bool RING = false>
 static int launch_accum_lean(const float* feat, const uint32_t* clsw, const uint8_t* cls, const int32_t* counts, int nclass,
                              int64_t n, int64_t D, int64_t hw, float* sums, cudaStream_t st) {
@@ -733,7 +756,26 @@ static int launch_accum_lean(const float* feat, const uint32_t* clsw, const uint
   const int64_t items = n * (D / 4);
   const int64_t full = (int64_t)sm_count() * blocks_dev[slot];
   const int64_t grid = tunable("accum_balance", 1) ? balanced_grid(items, blocks_dev[slot]) : (items < full ? items : full);
-  kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, clsw, cls, counts, nclass, n, D, hw, RS, unit - 1, sums);
+  if (g_chain_pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, feat, clsw, cls, counts, nclass, n, D, hw, RS, unit - 1, sums);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("centroid_accum_lean_kernel: launch failed: %s", cudaGetErrorString(e));
+      return DIGA_ERR_CUDA;
+    }
+  } else {
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(feat, clsw, cls, counts, nclass, n, D, hw, RS, unit - 1, sums);
+  }
   DIGA_CHECK_LAUNCH("centroid_accum_lean_kernel");
   return DIGA_OK;
 }
@@ -994,6 +1036,7 @@ centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict
   const int64_t c = blockIdx.x;
   const int Y = gridDim.y;                                   // == cluster size along y
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();                                                // (chain: the accumulation kernel's sums must have landed)
   float num = do_update ? objnum[c] : 0.f;
   float v[NR][K];                                            // image i, channel dbase + k*Y*BLOCK
   const int64_t dbase = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
@@ -1360,13 +1403,15 @@ int diga_centroid_finish(const float* sums, const int32_t* counts, int64_t n, in
   cfg.blockDim = dim3(256, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = (unsigned)Y;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_chain_pdl ? 2 : 1;
   const UpdateRule rule = make_rule(do_update ? mode : DIGA_UPDATE_MEAN, start_mean, momentum);
   cudaError_t e = cudaSuccess;
   int np = 1;
@@ -1438,11 +1483,23 @@ int diga_centroid_chain(const float* feat, const float* logits, const float* lab
                        : diga_centroid_assign(logits, labels, n, C, hw, cls, counts, clsw, stream);
   if (rc != DIGA_OK) return rc;
   if (hw == 0 || D == 0) return DIGA_OK;
+  // Short chains (the per-image calls of the reference's loops) launch accum and finish as programmatic dependents of their
+  // predecessor: accum fetches its first feature batch while assign still runs, finish is resident when the last
+  // accumulation CTA leaves — 24.5 -> 22.6 us per [1,2048,65,129] call.  Long accumulations gain nothing (0.103 -> 0.105 ms
+  // at [8,2048,65,129]: the early feature requests only compete with the assign kernel's own loads) and launch plainly.
+  // Tunable chain_pdl: 0 = never, 1 = short chains (default), 2 = always.
+  struct PdlScope {
+    explicit PdlScope(bool on) { g_chain_pdl = on; }
+    ~PdlScope() { g_chain_pdl = false; }
+  };
+  const int pdl_mode = tunable("chain_pdl", 1);
+  PdlScope pdl_scope(pdl_mode == 2 || (pdl_mode == 1 && n * ((D + 3) / 4) <= (int64_t)sm_count() * 8));
   rc = diga_centroid_accum(feat, cls, counts, clsw, n, D, C, hw, sums, stream);
   if (rc != DIGA_OK) return rc;
   if (diga_centroid_finish_supported(n, D))
     return diga_centroid_finish(sums, counts, n, C, D, hw, nullptr, nullptr, nullptr, objective_vectors, objective_num, mode,
                                 start_mean, momentum, stream);
+  g_chain_pdl = false;
   float* vec = reinterpret_cast<float*>(p);
   p += align_up((size_t)n * C * D * sizeof(float), 256);
   float* vecsum = reinterpret_cast<float*>(p);
