@@ -306,7 +306,7 @@ def _labels_on_feature_grid(labels_i64, size):
     return F.interpolate(labels_i64.reshape([b, 1, h, w]).float(), size=tuple(size), mode='nearest')
 
 
-def _sharded_target_pass(class_features, model, target_loader, rank, world, first):
+def _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess=None):
     """One pass of the target loop (calc_centroids.py:67-78) under ``torchrun``: every rank runs the backbone only on the
     loader batches ``rank, rank + world, ...`` (all ranks iterate the SAME un-sharded loader, like the reference's), the
     per-image class vectors are all-gathered once and replayed in loader order (exact mode of ``diga_b200.parallel``): all
@@ -320,6 +320,8 @@ def _sharded_target_pass(class_features, model, target_loader, rank, world, firs
         if index % world != rank:
             continue
         tdatav = batch[0].cuda()
+        if preprocess is not None:
+            tdatav = preprocess(tdatav)
         with torch.no_grad():
             _, _, out, feature_t = model(tdatav)
             if first:
@@ -345,13 +347,17 @@ def _sharded_target_pass(class_features, model, target_loader, rank, world, firs
     sp.finish()
 
 
-def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full, target_loader):
+def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full, target_loader, preprocess=None):
     """Reference driver ``calc_centroids.py:17-81``: five passes over the loader, running 'mean' update of the
     class centroids, ``feat_centroids`` written next to ``opt.centroid_dir`` after every pass.
 
     ``model(x)`` must return ``(_, _, logits, feat)`` like the reference ``SegModel``.  As in the reference the
     target branch is always taken (``opt.source`` is overwritten with ``False``, :27); the source branch is kept
     for completeness (:29-65).  Returns the ``Class_Features`` object (the reference returns ``None``).
+
+    ``preprocess`` (not in the reference signature, default ``None``): applied to the image batch before ``model`` — the
+    semi-supervised tree flips BGR -> RGB at the call site (``model(sdatav[:, [2, 1, 0], :, :])``,
+    semi-supervised_segmentation/calc_centroids.py:39); the GTA5 tree mirrored here feeds the image as is.
 
     Under ``torchrun`` (an initialised ``torch.distributed`` group of more than one rank) the target loop is image-sharded
     in the exact mode of ``diga_b200.parallel``: identical ``feat_centroids`` on every rank, bit-equal to the single-process run.
@@ -378,7 +384,7 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
                     newlabels = _labels_on_feature_grid(slabelv, out.size()[2:])
                     class_features.update_from_features(feature_s, out, newlabels, 'mean')
         elif world > 1:
-            _sharded_target_pass(class_features, model, target_loader, rank, world, first)
+            _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess)
             first = False
         else:
             for index, batch in enumerate(target_loader):
@@ -386,6 +392,8 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
                     print('epoch', epoch)
                     print('%d processd' % index)
                 tdatav = batch[0].cuda()
+                if preprocess is not None:
+                    tdatav = preprocess(tdatav)
                 with torch.no_grad():
                     _, _, out, feature_t = model(tdatav)
                     if first:

@@ -249,17 +249,24 @@ class PseudoLabelWriter:
         self.close()
 
 
-def generate_pseudo_labels(student, loader, output_dir, size=(1024, 2048), workers=4, encoder="gpu", coalesce=8):
+def generate_pseudo_labels(student, loader, output_dir, size=(1024, 2048), workers=4, encoder="gpu", coalesce=8, preprocess=None):
     """The loop of ``pseudolabel_generator.py:69-105`` with the per-pixel math and the output path replaced:
     two forward passes (full and half resolution, :73-76), fused up-sampling + max + argmax on the GPU, PNGs streamed
     out by :class:`PseudoLabelWriter`.  ``student(x)`` returns ``(_, _, logits, _)`` like the reference ``SegModel``;
-    ``loader`` yields ``(image, _, name)`` batches (batch size 1 in the reference; ``coalesce`` maps are encoded per call)."""
+    ``loader`` yields ``(image, _, name)`` batches (batch size 1 in the reference; ``coalesce`` maps are encoded per call).
+
+    Channel order: this mirrors the GTA5 / Synthia trees, which feed the loader's image to the model as is.  The
+    semi-supervised tree flips BGR -> RGB at the call site (``student(image[:, [2, 1, 0], :, :])``,
+    semi-supervised_segmentation/pseudolabel_generator.py:74-75): pass ``preprocess=lambda x: x[:, [2, 1, 0]]`` there
+    (applied to both resolutions before the model)."""
     import torch.nn.functional as F
     with PseudoLabelWriter(output_dir, workers=workers, encoder=encoder, coalesce=coalesce) as writer, torch.no_grad():
         for index, batch in enumerate(loader):
             image, _, name = batch
             image = image.cuda(non_blocking=True)
             image_ds = F.interpolate(image, (size[0] // 2, size[1] // 2), mode='bilinear', align_corners=True)   # :73
+            if preprocess is not None:
+                image, image_ds = preprocess(image), preprocess(image_ds)
             _, _, output_ds, _ = student(image_ds)                                                                 # :75
             _, _, output, _ = student(image)                                                                       # :76
             label, _ = pseudo_label_two_scale(output, output_ds, size, want_conf=False)                            # :77-85

@@ -28,6 +28,17 @@ def logits(shape, g: torch.Generator, sigma: float = 3.0) -> torch.Tensor:
     return sigma * torch.randn(shape, generator=g, device=g.device, dtype=torch.float32)
 
 
+def logits_peaked(shape, g: torch.Generator, block: int = 6, margin: float = 8.0, sigma: float = 1.0) -> torch.Tensor:
+    """Network-like logits ``[N,C,h,w]``: a piecewise-constant arg-max map (``block`` x ``block`` regions at the logit
+    resolution) leads by ``margin`` over Gaussian noise of scale ``sigma`` — confident inside regions, contested along their
+    borders, which is what a trained segmentation head emits.  The i.i.d. ``logits`` above are the worst case of
+    the arg-max kernels' candidate pruning (nearly every class can win in every source cell); this is the realistic case."""
+    n, c, h, w = shape
+    lab = block_labels(n, h, w, g, block, c, 0.0)
+    onehot = torch.nn.functional.one_hot(lab, c).permute(0, 3, 1, 2).to(torch.float32)
+    return sigma * torch.randn(shape, generator=g, device=g.device, dtype=torch.float32) + margin * onehot
+
+
 def features(shape, g: torch.Generator) -> torch.Tensor:
     return torch.randn(shape, generator=g, device=g.device, dtype=torch.float32)
 

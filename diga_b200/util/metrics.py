@@ -75,12 +75,14 @@ class runningScore(object):
         self._flags.zero_()
 
 
-def evaluate_val(student, val_loader, n_classes=19, size=(1024, 2048), running_metrics=None):
+def evaluate_val(student, val_loader, n_classes=19, size=(1024, 2048), running_metrics=None, preprocess=None):
     """The evaluation loop of ``evaluate_val.py:72-90`` (and ``train_DiGA_gta2city_self_training.py:428-449``) with the
     per-pixel math kept on the GPU: two forward passes (full and half resolution, :78-81), fused up-sampling + max + arg-max
     (:82-86, never materialising the two ``[1,19,1024,2048]`` tensors), confusion matrix on the device (:87-89).
     ``student(x)`` returns ``(_, _, logits, _)`` like the reference ``SegModel``; ``val_loader`` yields ``(images, labels)``.
-    Returns ``running_metrics.get_scores()``."""
+    Returns ``running_metrics.get_scores()``.  ``preprocess``: applied to both image batches before the model — the
+    semi-supervised tree needs ``lambda x: x[:, [2, 1, 0]]`` (its evaluate_val.py:76-77 flips BGR -> RGB at the call site);
+    the GTA5 / Synthia trees, which this mirrors, feed the loader's image as is."""
     import torch.nn.functional as F
 
     from ..pseudolabel import pseudo_label_two_scale
@@ -89,6 +91,8 @@ def evaluate_val(student, val_loader, n_classes=19, size=(1024, 2048), running_m
         for images_val, labels_val in val_loader:
             images_val = images_val.cuda(non_blocking=True)
             images_ds = F.interpolate(images_val, (size[0] // 2, size[1] // 2), mode='bilinear', align_corners=True)   # :78
+            if preprocess is not None:
+                images_val, images_ds = preprocess(images_val), preprocess(images_ds)
             _, _, pred, _ = student(images_val)                                                                       # :80
             _, _, pred_ds, _ = student(images_ds)                                                                     # :81
             label, _ = pseudo_label_two_scale(pred, pred_ds, size, want_conf=False)                                    # :82-86
