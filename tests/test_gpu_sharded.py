@@ -300,6 +300,40 @@ one = D.Class_Features(c, d)
 one.objective_vectors, one.objective_vectors_num = ref.objective_vectors.clone(), torch.full((c,), 150.0)
 one.update_from_features(torch.cat(fs), torch.cat(os_), None, "moving_average", False)
 assert torch.equal(one.objective_vectors, cf3.objective_vectors) and torch.equal(one.objective_vectors_num, cf3.objective_vectors_num)
+# the calc_centroids driver itself under torchrun (calc_centroids.py:17-81): every rank iterates the same loader, runs the
+# model on its own batches only, and all ranks end every pass with the single-process centroids; rank 0 writes the file
+import types, torch.nn as nn
+class TinySeg(nn.Module):
+    def __init__(self, d=64, c=19):
+        super().__init__()
+        torch.manual_seed(0)
+        self.f = nn.Conv2d(3, d, 8, stride=8)
+        self.g = nn.Conv2d(d, c, 1)
+    def forward(self, x):
+        feat = self.f(x)
+        return None, None, 4.0 * self.g(feat), feat
+model = TinySeg().to(dev)
+gen = torch.Generator().manual_seed(1)
+imgs = torch.randn((7, 3, 64, 96), generator=gen)
+for loader in (torch.utils.data.DataLoader(torch.utils.data.TensorDataset(imgs, torch.zeros(7)), batch_size=2, shuffle=False),
+               [(imgs[i:i + 2], torch.zeros(1)) for i in range(0, 7, 2)]):          # DataLoader (len / batch_size known) and a bare list
+    opt = types.SimpleNamespace(source=True, centroid_dir=os.path.join(sys.argv[2], "centroids", "x"))
+    os.makedirs(os.path.dirname(opt.centroid_dir), exist_ok=True)
+    cfd = D.calc_centroids(opt, model, nn.Identity(), nn.Identity(), [], [], loader)
+    seq2 = D.Class_Features(19, 64)
+    with torch.no_grad():
+        for _ in range(5):
+            for batch in loader:
+                _, _, out_b, feat_b = model(batch[0].to(dev))
+                seq2.update_from_features(feat_b, out_b, None, "mean")
+    assert torch.equal(cfd.objective_vectors_num, seq2.objective_vectors_num), (cfd.objective_vectors_num, seq2.objective_vectors_num)
+    err = (cfd.objective_vectors - seq2.objective_vectors).abs().max().item()
+    assert err <= 1e-6 * seq2.objective_vectors.abs().max().item(), ("driver", err)
+    dist.barrier()
+    if rank == 0:
+        saved = torch.load(os.path.join(os.path.dirname(opt.centroid_dir), "feat_centroids"))
+        assert torch.equal(saved, cfd.objective_vectors.cpu())
+    dist.barrier()
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -315,7 +349,7 @@ def test_two_rank_nccl_exact_and_sum_modes(tmp_path, world):
     script.write_text(NCCL_WORKER)
     port = 29700 + (os.getpid() % 200)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(script), ROOT]
+           "--master-port", str(port), str(script), ROOT, str(tmp_path)]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-4000:]
     assert res.stdout.count("ok") >= world
