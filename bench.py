@@ -607,7 +607,9 @@ def bench_stages(D, S, dev, peak, world):
     rng3 = random.Random(99)
     lam = torch.tensor(0.25, device=dev)
 
-    def st_step(fused):
+    lazy_up = D.nn.Upsample(size=(hh, ww), mode="bilinear", align_corners=True)
+
+    def st_step(fused, lazy=False):
         if fused:      # one presence pass over slabelv serves both ClassMix blocks; its host round trip hides behind a5 + a4
             pres = D.present_classes_async(sl)
             wts = cf.get_centroid_weight(feat)                                                     # :301
@@ -630,8 +632,8 @@ def bench_stages(D, S, dev, peak, world):
         if fused:      # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each
             part, l_src, l_kd = D.seg_distillation_total_upsampled(tea_cat, stu, sl, 1.0, 0.25, 0.5)   # :289,:348-352,:382
             total = part + D.cross_entropy2d_upsampled(cpm, mixlabel)                              # :344,:355-356
-        else:
-            up = lambda x: F.interpolate(x, size=(hh, ww), mode="bilinear", align_corners=True)
+        else:          # the reference's call sites as they are; `lazy`: its three nn.Upsample modules built from diga_b200.nn.Upsample
+            up = lazy_up if lazy else (lambda x: F.interpolate(x, size=(hh, ww), mode="bilinear", align_corners=True))
             l_src = D.cross_entropy2d(up(stu[:b]), sl)                                             # :348-349
             l_kd = D.distillation_loss(up(tea_cat), up(stu), 0.5)                                  # :289,:351-352
             l_mix = D.cross_entropy2d(up(cpm), mixlabel)                                           # :344,:355
@@ -640,8 +642,10 @@ def bench_stages(D, S, dev, peak, world):
         return total, g_stu, g_mix, mix1, mix2
 
     step_bytes = 48 + 68 + 24 + 3 * (d * 4 + C * 4) * (h * w) / (hh * ww) + 16
-    for name, fused in (("config3_self_training_step_dropin_functions", False), ("config3_self_training_step_fused_call_sites", True)):
-        add(name, b * hh * ww, step_bytes, lambda fused=fused: st_step(fused), sync_free=False,
+    for name, fused, lazy in (("config3_self_training_step_dropin_functions", False, False),
+                              ("config3_self_training_step_dropin_functions_lazy_upsample", False, True),
+                              ("config3_self_training_step_fused_call_sites", True, False)):
+        add(name, b * hh * ww, step_bytes, lambda fused=fused, lazy=lazy: st_step(fused, lazy), sync_free=False,
             extra={"note": "ClassMix x2 (one 32 B/image host round trip each, as the reference's random.sample needs), prototype "
                            "weights, consensus selection, 2 centroid EMA updates, CE x2 + KD with backward; eager (host syncs); "
                            "algorithmic bytes = the three [8,2048,65,129] feature reads + image/label traffic"})
@@ -1165,7 +1169,9 @@ def main():
             from_stage("a6+a7", "centroid_accumulate_update_d2048_blocky_classes", "update_from_features call: assign + accum + finish (4x4 blocks)", "hbm", "feature-px")
             from_stage("f2", "cross_entropy2d_fwd_bwd", "ce_kernel fwd + bwd", "hbm", "px")
             from_stage("f4", "ema_teacher_update", "ema_update_kernel", "hbm", "parameter")
-            for key, label in (("config3_self_training_step_fused_call_sites", "config 3: self-training step hot path, B=8 @512x1024, D=2048 (patched call sites)"),
+            for key, label in (("config3_self_training_step_dropin_functions", "config 3: self-training step hot path with ONLY the function names swapped (losses behind torch's nn.Upsample)"),
+                               ("config3_self_training_step_dropin_functions_lazy_upsample", "config 3: same unchanged call sites, the scripts' three nn.Upsample modules built from diga_b200.nn.Upsample"),
+                               ("config3_self_training_step_fused_call_sites", "config 3: self-training step hot path, B=8 @512x1024, D=2048 (patched call sites)"),
                                ("config4_calc_centroids_whole_set", "config 4: calc_centroids over 2975 images, sum mode (one all-reduce)"),
                                ("config4_calc_centroids_whole_set_exact", "config 4: calc_centroids over 2975 images, exact mode (all-gather + ordered replay)"),
                                ("config5_pseudo_labels_whole_set", "config 5: 2975 full-resolution pseudo-label maps with prototype rectification")):

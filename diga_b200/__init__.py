@@ -11,11 +11,15 @@ Host side mirrors the reference's interface for this path:
 * ``diga_b200.classmix.classmix``                    <- inline block ``train_DiGA_gta2city_self_training.py:259-275, 306-325``
 * ``diga_b200.selection.consensus_select``           <- inline block ``:298-304``
 * ``diga_b200.pseudolabel.pseudo_label``             <- inline block ``pseudolabel_generator.py:77-85``
+* ``diga_b200.nn.Upsample``                          <- the ``nn.Upsample(bilinear, align_corners=True)`` modules of
+  ``train_DiGA_gta2city_self_training.py:190-192`` / ``pseudolabel_generator.py:55``: returns a lazy tensor that the
+  functions above consume at stride-8 resolution (fused up-sampling), and that materialises for anything else
 
 Everything runs through ``libdiga_b200.so`` (C ABI in ``include/diga_b200.h``); importing this package fails
 loudly when the library has not been built.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
+from . import nn  # noqa: F401  (diga_b200.nn.Upsample: lazy stand-in for the scripts' nn.Upsample modules)
 from .calc_centroids import Class_Features, calc_centroids
 from .classmix import classmix, present_classes_async
 from .pseudolabel import pseudo_label, pseudo_label_two_scale

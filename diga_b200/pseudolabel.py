@@ -29,7 +29,16 @@ CITYSCAPES_PALETTE = CITYSCAPES_PALETTE + [0] * (256 * 3 - len(CITYSCAPES_PALETT
 def pseudo_label(logits, logits_ds=None, want_conf=True, want_int64=False):
     """``logits`` (and optional ``logits_ds``): ``[N,C,H,W]`` fp32.  Returns ``(label uint8 [N,H,W], conf fp32
     [N,H,W] or None)`` (plus an int64 copy of the labels when ``want_int64``).  ``label`` is what the reference
-    stores after ``np.asarray(label, dtype=np.uint8)`` (:92); ``conf`` is the value it computes and discards."""
+    stores after ``np.asarray(label, dtype=np.uint8)`` (:92); ``conf`` is the value it computes and discards.
+    Outputs of ``diga_b200.nn.Upsample`` (``upsample_1024(output)``, :77-78) are consumed at their stride-8 resolution."""
+    from .nn import LazyUpsampled
+    if isinstance(logits, LazyUpsampled) and (logits_ds is None or isinstance(logits_ds, LazyUpsampled)) and not want_int64 and \
+            (logits_ds is None or logits_ds.out_size == logits.out_size):
+        return pseudo_label_two_scale(logits.low, None if logits_ds is None else logits_ds.low, logits.out_size, want_conf)
+    if isinstance(logits, LazyUpsampled):
+        logits = logits.materialize()
+    if isinstance(logits_ds, LazyUpsampled):
+        logits_ds = logits_ds.materialize()
     L.require_cuda(logits, logits_ds, what="pseudo_label input")
     z = L.f32c(logits.detach())
     z2 = None

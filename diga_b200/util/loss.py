@@ -9,6 +9,11 @@ from __future__ import annotations
 import torch
 
 from .. import _lib as L
+from ..nn import LazyUpsampled
+
+
+def _materialized(x):
+    return x.materialize() if isinstance(x, LazyUpsampled) else x
 
 
 def _check(teacher_out: torch.Tensor, student_out: torch.Tensor):
@@ -50,7 +55,13 @@ def distillation_loss(teacher_out, student_out, scale=0.5):
 
     ``teacher_out``, ``student_out``: ``[2B,C,H,W]`` fp32 logits of two stacked views.  Returns
     ``mean CE(softmax(t_view0), s_view1) + scale * mean CE(softmax(t_view1), s_view0)``.
+    Outputs of ``diga_b200.nn.Upsample`` (:class:`~diga_b200.nn.LazyUpsampled`) are consumed at their stride-8 resolution
+    by the fused up-sampling kernels — same call site as the reference's :289,:351-352.
     """
+    if isinstance(teacher_out, LazyUpsampled) and isinstance(student_out, LazyUpsampled) and \
+            teacher_out.out_size == student_out.out_size:
+        return distillation_loss_upsampled(teacher_out.low, student_out.low, student_out.out_size, scale)
+    teacher_out, student_out = _materialized(teacher_out), _materialized(student_out)
     _check(teacher_out, student_out)
     return _DistillationLoss.apply(teacher_out, student_out, scale)
 
@@ -104,7 +115,12 @@ class _CrossEntropy2d(torch.autograd.Function):
 def cross_entropy2d(input, target, weight=None, size_average=True):
     """``util.loss.cross_entropy2d`` (G/util/loss.py:48-62): pixel-wise cross entropy with ``ignore_index=255``;
     pixels with a negative target are dropped; ``size_average`` divides by the number of pixels with target >= 0
-    (ignore-255 pixels included, exactly like the reference).  ``input [N,C,H,W]`` fp32, ``target [N,H,W]`` int64."""
+    (ignore-255 pixels included, exactly like the reference).  ``input [N,C,H,W]`` fp32, ``target [N,H,W]`` int64.
+    An output of ``diga_b200.nn.Upsample`` is consumed at its stride-8 resolution (fused up-sampling, :344,:348-349,:355)."""
+    if isinstance(input, LazyUpsampled):
+        if tuple(target.shape[1:]) == input.out_size:
+            return cross_entropy2d_upsampled(input.low, target, weight, size_average)
+        input = input.materialize()
     L.require_cuda(input, target, weight, what="cross_entropy2d input")
     if input.dim() != 4 or target.dim() != 3 or input.shape[0] != target.shape[0] or input.shape[2:] != target.shape[1:]:
         raise ValueError(f"cross_entropy2d: expected [N,C,H,W] logits and [N,H,W] targets, got {tuple(input.shape)} and "
@@ -353,6 +369,8 @@ class OhemCrossEntropy(torch.nn.Module):
 
     @L.on_device
     def forward(self, score, target):
+        if isinstance(score, LazyUpsampled):       # _ohem_forward up-samples the score itself (:91-95): hand it the stride-8 map
+            score = score.low if tuple(target.shape[1:]) == score.out_size else score.materialize()
         L.require_cuda(score, target, self.weight, what="OhemCrossEntropy input")
         if score.dim() != 4 or target.dim() != 3 or score.shape[0] != target.shape[0]:
             raise ValueError(f"OhemCrossEntropy: expected [N,C,h,w] scores and [N,H,W] targets, got {tuple(score.shape)} and "
