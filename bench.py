@@ -735,8 +735,10 @@ def bench_stages(D, S, dev, peak, world):
         "algo_bytes_per_px": d * 4 + C * 4 + 1,
         "gbs_per_gpu": mine * h * w * (d * 4 + C * 4 + 1) / (ms4x * 1e-3) / 1e9,
         "frac_hbm": mine * h * w * (d * 4 + C * 4 + 1) / (ms4x * 1e-3) / 1e9 / peak,
-        "gather_plus_replay_ms": fin_ms, "allgather_bytes_per_rank": sp.per_shard * C * (d * 4 + 5),
-        "note": "finish() = all_gather_into_tensor of vec/vecsum/valid (NCCL over NVLink when world > 1) + diga_centroid_update_sharded"}
+        "gather_plus_replay_ms": fin_ms, "exchange": sp.exchange, "rows_bytes_per_rank": sp.per_shard * C * (d * 4 + 5),
+        "note": "exchange 'multicast-stores' / 'peer-stores': the per-image vectors are stored into every rank's row buffer by the "
+                "means kernel itself (NVLS multicast / NVLink peer stores on a side stream, symmetric memory), finish() = barrier + "
+                "ordered replay; 'all-gather': finish() = all_gather_into_tensor (NCCL) + replay; 'local': one rank"}
     del pool4, sp, cf_exact
 
     # config 5: full-resolution pseudo-labels with prototype rectification, one 1024x2048 image per call

@@ -200,6 +200,8 @@ class Class_Features:
             if full.dim() != 3 or full.shape[0] != n:
                 raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
             hh, ww = full.shape[1], full.shape[2]
+        if n == 0 or h * w == 0:
+            return                                        # nothing to accumulate (the reference's loops simply do not run)
         self._proto_key = None
         # ONE scratch tensor and ONE library call queue the whole chain (assign -> accum -> finish): the reference drives this
         # path one image per call (calc_centroids.py:67-78), where per-kernel FFI calls and scratch tensors cost more host
@@ -341,7 +343,7 @@ def _sharded_target_pass(class_features, model, target_loader, rank, world, firs
         torch.distributed.all_reduce(sizes[1:], op=torch.distributed.ReduceOp.MAX)
         if first and int(tot[0]) > 0:
             raise RuntimeError("calc_centroids: this rank received no batch, cannot infer the feature dimension")
-        sp = ShardedCentroidPass(class_features, int(tot[0]), max(int(sizes[1]), 1), 'mean')
+        sp = ShardedCentroidPass(class_features, int(tot[0]), max(int(sizes[1]), 1), 'mean', symmetric=False)
         for p in pending:
             sp.add_rows(*p)
     sp.finish()

@@ -858,6 +858,50 @@ centroid_means_kernel(const float* __restrict__ sums, const int32_t* __restrict_
   }
 }
 
+// means fused with the exchange of the image-sharded exact mode: the per-image class vectors are written
+// straight into the row block this rank owns in EVERY rank's gathered buffer — plain stores to peer memory over NVLink
+// (symmetric allocation: the same layout at every `peers[r]`), fire-and-forget while the accumulation of the next batch
+// already runs.  What used to be a separate all-gather of 463 MB at the end of the pass (1.4 ms at 8 ranks) is gone; the pass
+// ends with a barrier and the ordered replay.
+struct PeerBuffers {
+  unsigned char* base[DIGA_MAX_PEERS];
+  unsigned char* multicast;                   // NVLS multicast mapping of the same allocation (one store reaches every rank), or null
+  int world;
+  int64_t off_vec, off_vecsum, off_valid;     // byte offsets of vec [rows,C,D] f32, vecsum [rows,C] f32, valid [rows,C] u8
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+centroid_means_scatter_kernel(const float* __restrict__ sums, const int32_t* __restrict__ counts, int64_t C, int64_t D,
+                              int64_t hw, int64_t row0, PeerBuffers peers) {
+  __shared__ float red[BLOCK / 32];
+  const int64_t nc = (int64_t)blockIdx.y * C + blockIdx.x;                 // local (image, class)
+  const int64_t gnc = (row0 + blockIdx.y) * C + blockIdx.x;                // its place in the gathered buffers
+  const int cnt = counts[nc];
+  const float frac = (float)cnt / (float)hw;
+  float part = 0.f;
+  for (int64_t d = threadIdx.x; d < D; d += BLOCK) {
+    float v = 0.f;
+    if (cnt > 0) v = (sums[nc * D + d] / (float)hw) / frac;                // same expression as centroid_means_kernel
+    if (peers.multicast != nullptr) {
+      // one store, replicated by the NVSwitch into every rank's copy (the 155 KB of a row leave this GPU once, not `world` times)
+      asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(peers.multicast + peers.off_vec) + gnc * D + d),
+                   "f"(v)
+                   : "memory");
+    } else {
+      for (int r = 0; r < peers.world; ++r) reinterpret_cast<float*>(peers.base[r] + peers.off_vec)[gnc * D + d] = v;
+    }
+    part += v;
+  }
+  const float tot = block_sum<BLOCK>(part, red);
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < peers.world; ++r) {                                // (two scalars per row: plain peer stores)
+      reinterpret_cast<float*>(peers.base[r] + peers.off_vecsum)[gnc] = tot;
+      (peers.base[r] + peers.off_valid)[gnc] = (cnt >= 5) ? 1 : 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // update (calc_centroids.py:147-164), arithmetic mirrored op for op (separately rounded mul/add/div)
 // ------------------------------------------------------------------------------------------------
@@ -1340,6 +1384,31 @@ static int launch_centroid_update(const float* vec, const float* vecsum, const u
   const int64_t rows = order.world == 1 ? n : order.world * order.per_shard;
   centroid_update_num_kernel<256><<<(unsigned)C, 256, 0, st>>>(vecsum, valid, rows, C, objective_num);
   DIGA_CHECK_LAUNCH("centroid_update_num_kernel");
+  return DIGA_OK;
+}
+
+int diga_centroid_means_scatter(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw,
+                                void* const* peer_bases, void* multicast_base, int64_t world, int64_t off_vec, int64_t off_vecsum,
+                                int64_t off_valid, int64_t row0, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(sums && counts && peer_bases, DIGA_ERR_INVALID, "centroid_means_scatter: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES && n >= 0 && n <= 65535 && D >= 0 && hw > 0 && row0 >= 0, DIGA_ERR_INVALID,
+               "centroid_means_scatter: bad sizes");
+  DIGA_REQUIRE(world >= 1 && world <= DIGA_MAX_PEERS, DIGA_ERR_INVALID, "centroid_means_scatter: world=%lld outside [1,%d]",
+               (long long)world, DIGA_MAX_PEERS);
+  DIGA_REQUIRE(off_vec % 16 == 0 && off_vecsum % 4 == 0 && off_vec >= 0 && off_vecsum >= 0 && off_valid >= 0, DIGA_ERR_MISALIGNED,
+               "centroid_means_scatter: misaligned offsets");
+  if (n == 0) return DIGA_OK;
+  PeerBuffers pb;
+  pb.multicast = tunable("scatter_multicast", 1) ? static_cast<unsigned char*>(multicast_base) : nullptr;
+  pb.world = (int)world;
+  pb.off_vec = off_vec;
+  pb.off_vecsum = off_vecsum;
+  pb.off_valid = off_valid;
+  for (int r = 0; r < DIGA_MAX_PEERS; ++r) pb.base[r] = r < world ? static_cast<unsigned char*>(peer_bases[r]) : nullptr;
+  for (int r = 0; r < world; ++r) DIGA_REQUIRE(pb.base[r] != nullptr, DIGA_ERR_INVALID, "centroid_means_scatter: null peer buffer %d", r);
+  centroid_means_scatter_kernel<256><<<dim3((unsigned)C, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(sums, counts, C, D, hw, row0, pb);
+  DIGA_CHECK_LAUNCH("centroid_means_scatter_kernel");
   return DIGA_OK;
 }
 

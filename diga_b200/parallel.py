@@ -16,12 +16,22 @@ running mean while ``num + n <= 3000`` (the first pass over 2975 images); beyond
 ``obj = (3000 obj + v) / 3001`` weights later images more, and this mode replaces those weights by their average
 (documented approximation; the exact mode exists for parity).
 
-Collectives run through ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic).
+Collectives run through ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic).  On
+NVLink-connected GPUs the exact mode does not call a collective for its data at all: the row buffers are ONE symmetric
+allocation per rank (``torch.distributed._symmetric_memory``), and the kernel that turns class sums into per-image vectors
+(``diga_centroid_means_scatter``) stores every row directly into the row block its rank owns in EVERY rank's buffer — peer
+stores over NVLink, issued while the accumulation of the next batch runs.  The pass then ends with a barrier and the ordered
+replay; the 463 MB all-gather is gone (``DIGA_SYMM=0`` in the environment, or a failed rendezvous, falls back to it).
 """
 from __future__ import annotations
 
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 CLAMP = 3000.0          # calc_centroids.py:156,161
 
@@ -105,7 +115,7 @@ class ShardedCentroidPass:
     """
 
     def __init__(self, class_features, n_images: int, batch: int = 1, name: str = "mean", start_mean: bool = True, group=None,
-                 device=None, rank=None, world=None):
+                 device=None, rank=None, world=None, symmetric: bool = True):
         self.cf, self.group = class_features, group
         self.rank, self.world = _world(group)
         if rank is not None or world is not None:         # explicit placement (tests build the shards of several ranks in one
@@ -119,11 +129,50 @@ class ShardedCentroidPass:
         c, d = class_features.class_numbers, int(class_features.objective_vectors.shape[1])
         dev = class_features.objective_vectors.device if device is None else torch.device(device)
         rows = max(self.per_shard, 1)
-        self.vec = torch.empty((rows, c, d), dtype=torch.float32, device=dev)
-        self.vecsum = torch.zeros((rows, c), dtype=torch.float32, device=dev)      # rows never filled must read as "skip"
-        self.valid = torch.zeros((rows, c), dtype=torch.uint8, device=dev)
         self._gathered = None
         self._local_batches = 0
+        self._symm = None
+        if symmetric and self.world > 1 and dev.type == "cuda" and rank is None and os.environ.get("DIGA_SYMM", "1") != "0":
+            self._symm = self._try_symmetric(rows, c, d, dev)
+        if self._symm is None:
+            self.vec = torch.empty((rows, c, d), dtype=torch.float32, device=dev)
+            self.vecsum = torch.zeros((rows, c), dtype=torch.float32, device=dev)      # rows never filled must read as "skip"
+            self.valid = torch.zeros((rows, c), dtype=torch.uint8, device=dev)
+
+    def _try_symmetric(self, rows, c, d, dev):
+        """One symmetric allocation [vec | vecsum | valid] for the GATHERED rows of all ranks; returns None when symmetric
+        memory cannot be set up here (then the all-gather path is used).  Collective: every rank of the group calls it."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            total = self.world * rows
+            off_vec, n_vec = 0, total * c * d * 4
+            off_sum = (n_vec + 255) // 256 * 256
+            off_val = (off_sum + total * c * 4 + 255) // 256 * 256
+            nbytes = (off_val + total * c + 255) // 256 * 256
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            if hdl.world_size != self.world or self.world > 16:
+                return None
+            buf.zero_()                                   # rows no rank ever writes (shorter shards) must read as "skip"
+            hdl.barrier(channel=0)
+            ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and os.environ.get("DIGA_MULTICAST", "1") != "0" else 0
+            gvec = buf[off_vec:off_vec + n_vec].view(torch.float32).view(total, c, d)
+            gsum = buf[off_sum:off_sum + total * c * 4].view(torch.float32).view(total, c)
+            gval = buf[off_val:off_val + total * c].view(total, c)
+            return {"buf": buf, "hdl": hdl, "ptrs": ptrs, "mc": mc or None, "off": (off_vec, off_sum, off_val), "views": (gvec, gsum, gval)}
+        except Exception as e:                            # noqa: BLE001  (no NVLink peer access, old torch, ...): documented fallback
+            self._symm_error = f"{type(e).__name__}: {e}"
+            return None
+
+    @property
+    def exchange(self) -> str:
+        """How the rows travel: 'peer-stores' (fused into the means kernel over NVLink), 'all-gather', or 'local' (one rank)."""
+        if self.world == 1:
+            return "local"
+        if self._symm is None:
+            return "all-gather"
+        return "multicast-stores" if self._symm["mc"] else "peer-stores"
 
     def my_batches(self):
         """Global indices of the loader batches this rank processes, in the order ``add`` expects them."""
@@ -145,6 +194,9 @@ class ShardedCentroidPass:
 
     def add_rows(self, vec, vecsum, valid):
         """Append precomputed per-image rows ``vec [n,C,D]``, ``vecsum [n,C]``, ``valid [n,C]`` of this rank's next batch."""
+        if self._symm is not None:
+            raise RuntimeError("ShardedCentroidPass.add_rows needs the all-gather exchange: construct with symmetric=False "
+                               "(add() writes the rows of a batch through the peer-store kernel)")
         rows = self._next_rows(vec.shape[0])
         self.vec[rows].copy_(vec)
         self.vecsum[rows].copy_(vecsum)
@@ -152,12 +204,35 @@ class ShardedCentroidPass:
 
     def add(self, feat_cls, outputs, labels_val=None, labels_full=None):
         """a6 of this rank's next batch (``calculate_mean_vector``, calc_centroids.py:120-145), written straight into the
-        pass buffer; no host sync."""
+        pass buffer — with symmetric memory into the row block of this rank in EVERY rank's buffer; no host sync."""
         rows = self._next_rows(feat_cls.shape[0])
-        self.cf._masked_means(feat_cls, outputs, labels_val, labels_full, out_rows=(self.vec[rows], self.vecsum[rows], self.valid[rows]))
+        if self._symm is None:
+            self.cf._masked_means(feat_cls, outputs, labels_val, labels_full, out_rows=(self.vec[rows], self.vecsum[rows], self.valid[rows]))
+            return
+        with torch.cuda.device(feat_cls.device):
+            sums, counts, hw = self.cf._class_sums(feat_cls, outputs, labels_val, labels_full)
+            n, c, d = sums.shape
+            off = self._symm["off"]
+            # the scatter kernel runs on a side stream: its NVLink stores (and their acknowledgement latency) overlap the
+            # assign / accumulation kernels of the next batch instead of sitting between them
+            main = torch.cuda.current_stream()
+            side = self._symm.setdefault("side", torch.cuda.Stream())
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                L.check(L.lib.diga_centroid_means_scatter(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, self._symm["ptrs"],
+                                                          self._symm["mc"], self.world, off[0], off[1], off[2],
+                                                          self.rank * max(self.per_shard, 1) + rows.start, side.cuda_stream))
+            sums.record_stream(side)
+            counts.record_stream(side)
 
     def gather(self):
-        """The exchange: all-gather of the three row buffers -> ``[world * per_shard, ...]`` on every rank."""
+        """The exchange: all-gather of the three row buffers -> ``[world * per_shard, ...]`` on every rank.  With symmetric
+        memory the rows are already everywhere (peer stores of the means kernel): a barrier makes them visible."""
+        if self._symm is not None:
+            if "side" in self._symm:
+                torch.cuda.current_stream().wait_stream(self._symm["side"])
+            self._symm["hdl"].barrier(channel=0)
+            return self._symm["views"]
         if self.world == 1:
             return self.vec, self.vecsum, self.valid
         if self._gathered is None:
@@ -176,6 +251,11 @@ class ShardedCentroidPass:
         return self.cf.objective_vectors, self.cf.objective_vectors_num
 
     def reset(self):
-        self.vecsum.zero_()
-        self.valid.zero_()
+        if self._symm is not None:
+            # nobody may start writing the next pass into a buffer another rank is still replaying from; the rows written per
+            # pass are the same every pass, so there is nothing to clear
+            self._symm["hdl"].barrier(channel=1)
+        else:
+            self.vecsum.zero_()
+            self.valid.zero_()
         self._local_batches = 0

@@ -38,6 +38,7 @@ enum diga_status {
 enum diga_update_mode { DIGA_UPDATE_MEAN = 0, DIGA_UPDATE_MOVING_AVERAGE = 1 };
 
 #define DIGA_MAX_CLASSES 32
+#define DIGA_MAX_PEERS 16          /* ranks of one NVLink domain a peer-memory kernel can address */
 #define DIGA_IGNORE_LABEL 255
 
 int diga_version(void);
@@ -158,6 +159,16 @@ int diga_centroid_chain(const float* feat, const float* logits, const float* lab
                         int64_t H, int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
                         float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
                         diga_stream_t stream);
+/* means fused with the exchange of the image-sharded exact mode: like diga_centroid_means, but the rows (vec, vecsum, valid of
+ * the n local images) are stored at row row0.. of the gathered buffers of ALL `world` ranks through peer pointers
+ * (peer_bases[r]: base of rank r's symmetric allocation, host array; the three arrays live at the given byte offsets in each).
+ * multicast_base (optional): the NVLS multicast mapping of the same allocation — the vectors are then written with ONE
+ * multimem.st per element that the NVSwitch replicates into every rank's copy.
+ * NVLink stores from the kernel — the all-gather of the pass disappears.  Visibility at the peers is the caller's
+ * barrier (the stores are complete when this kernel has finished on its stream). */
+int diga_centroid_means_scatter(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw,
+                                void* const* peer_bases, void* multicast_base, int64_t world, int64_t off_vec,
+                                int64_t off_vecsum, int64_t off_valid, int64_t row0, diga_stream_t stream);
 /* Image-sharded exact replay (calc_centroids.py:20-23,67-78,147-164): vec/vecsum/valid are the all-gather
  * of every rank's rows, [world][per_shard] x C (x D); rank r holds loader batches r, r+world, ... of `group` images each.
  * The n_total images are visited in GLOBAL loader order (image g = batch g/group, position g%group), so every rank

@@ -648,6 +648,14 @@ def test_edge_shapes(D):
     assert vec == [] and ids == []
     cf19.update_from_features(f, out, labels)
     assert torch.equal(cf19.objective_vectors, before) and float(cf19.objective_vectors_num.sum()) == 0.0
+    # empty batch through the fused chain and the exact-mode pass: a no-op
+    cf19.update_from_features(f[:0], out[:0], None, "mean")
+    assert torch.equal(cf19.objective_vectors, before)
+    from diga_b200.parallel import ShardedCentroidPass
+    sp = ShardedCentroidPass(cf19, 0, batch=4)
+    assert list(sp.my_batches()) == []
+    sp.finish()
+    assert torch.equal(cf19.objective_vectors, before)
 
 
 def test_streams_and_noncontiguous(D):

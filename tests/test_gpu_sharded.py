@@ -257,13 +257,24 @@ for o in outs: o[:, :6] += 3
 ref = O.ClassFeaturesOracle(c, d)
 for _ in range(2):
     ref = O.centroid_pass(feats, outs, c, d, cf=ref)
-# exact mode, two passes
+# exact mode, two passes: rows exchanged by peer stores fused into the means kernel (symmetric memory) ...
 cf = D.Class_Features(c, d)
 sp = P.ShardedCentroidPass(cf, n_img, batch)
+print("rank", rank, "exchange:", sp.exchange, getattr(sp, "_symm_error", ""))
+assert sp.exchange == os.environ.get("DIGA_EXPECT_EXCHANGE", sp.exchange)
 for _ in range(2):
     for k in sp.my_batches():
         sp.add(feats[k], outs[k])
     sp.finish()
+# ... and by the all-gather: the same bits
+cf_ag = D.Class_Features(c, d)
+sp_ag = P.ShardedCentroidPass(cf_ag, n_img, batch, symmetric=False)
+assert sp_ag.exchange == "all-gather"
+for _ in range(2):
+    for k in sp_ag.my_batches():
+        sp_ag.add(feats[k], outs[k])
+    sp_ag.finish()
+assert torch.equal(cf_ag.objective_vectors, cf.objective_vectors) and torch.equal(cf_ag.objective_vectors_num, cf.objective_vectors_num)
 num = cf.objective_vectors_num.cpu()
 assert torch.equal(num, ref.objective_vectors_num), (num, ref.objective_vectors_num)
 err = (cf.objective_vectors.cpu() - ref.objective_vectors).abs().max().item()
