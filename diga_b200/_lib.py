@@ -51,6 +51,8 @@ SIGNATURES = {
     "diga_centroid_finish": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i, _i, _d, _p]),
     "diga_centroid_chain_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "diga_centroid_chain": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i, _i, _d, _p]),
+    "diga_centroid_chain_sums": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "diga_centroid_chain_reduce": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "diga_centroid_means_scatter": (_i, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _p]),
     "diga_centroid_update_sharded": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),
     "diga_centroid_update_single": (_i, [_p, _i64, _i64, _i64, _p, _p, _i, _i, _d, _p]),

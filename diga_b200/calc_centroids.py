@@ -11,6 +11,7 @@ whole a6 -> a7 chain without any host sync and are what the ``calc_centroids`` d
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import random
 
@@ -79,8 +80,8 @@ class Class_Features:
                                "construct Class_Features(device=...) on the device that produces the features")
 
     # -- a6 -------------------------------------------------------------------------------------
-    def _class_sums(self, feat_cls, outputs, labels_val, labels_full=None):
-        """assign -> accum on the current stream.  Returns (sums [N,C,D], counts [N,C] int32, hw)."""
+    def _prep(self, feat_cls, outputs, labels_val, labels_full):
+        """Validated, contiguous fp32 / int64 views of the inputs of the a6 chain + its one scratch tensor."""
         L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
         feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
         n, d, h, w = feat.shape
@@ -90,6 +91,7 @@ class Class_Features:
         if labels_val is not None and labels_full is not None:
             raise ValueError("pass either labels_val (down-sampled fp32) or labels_full (int64), not both")
         lab = full = None
+        hh = ww = 0
         if labels_val is not None:
             lab = L.f32c(labels_val.detach())
             if lab.shape != (n, 1, h, w):
@@ -98,29 +100,27 @@ class Class_Features:
             full = L.i64c(labels_full)
             if full.dim() != 3 or full.shape[0] != n:
                 raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
-        dev, hw, st = feat.device, h * w, L.stream()
-        cls = torch.empty((n, hw), dtype=torch.uint8, device=dev)
-        clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev)
-        counts = torch.empty((n, c), dtype=torch.int32, device=dev)
-        sums = torch.empty((n, c, d), dtype=torch.float32, device=dev)
-        if full is not None:
-            L.check(L.lib.diga_centroid_assign_fullres(out.data_ptr(), full.data_ptr(), n, c, h, w, full.shape[1], full.shape[2],
-                                                       cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), st))
-        else:
-            L.check(L.lib.diga_centroid_assign(out.data_ptr(), L.ptr(lab), n, c, hw, cls.data_ptr(), counts.data_ptr(),
-                                               clsw.data_ptr(), st))
-        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, c, hw,
-                                          sums.data_ptr(), st))
-        return sums, counts, hw
+            hh, ww = full.shape[1], full.shape[2]
+        # ONE scratch tensor per call: class map, phase-shifted class words, counts, sums (and means where a path needs them)
+        ws = torch.empty((max(int(L.lib.diga_centroid_chain_workspace_bytes(n, c, d, h * w)), 256),), dtype=torch.uint8, device=feat.device)
+        return feat, out, lab, full, hh, ww, (n, c, d, h, w), ws
+
+    def _class_sums(self, feat_cls, outputs, labels_val, labels_full=None):
+        """assign -> accum on the current stream in one library call.  Returns ``(sums_ptr, counts_ptr, (n, c, d, hw), ws)``:
+        raw device pointers of ``sums [N,C,D]`` fp32 and ``counts [N,C]`` int32 inside the scratch tensor ``ws`` (keep it alive)."""
+        feat, out, lab, full, hh, ww, (n, c, d, h, w), ws = self._prep(feat_cls, outputs, labels_val, labels_full)
+        sums_p, counts_p = C.c_void_p(), C.c_void_p()
+        L.check(L.lib.diga_centroid_chain_sums(feat.data_ptr(), out.data_ptr(), L.ptr(lab), L.ptr(full), hh, ww, n, c, d, h, w,
+                                               ws.data_ptr(), C.byref(sums_p), C.byref(counts_p), L.stream()))
+        return sums_p.value, counts_p.value, (n, c, d, h * w), ws
 
     @L.on_device
     def _masked_means(self, feat_cls, outputs, labels_val, labels_full=None, out_rows=None):
         """assign -> accum -> means on the current stream.  Returns (vec [N,C,D], vecsum [N,C], valid [N,C]).
         ``labels_full``: the full-resolution int64 map ``[N,H,W]`` instead of its nearest-down-sampled fp32 copy.
         ``out_rows``: (vec, vecsum, valid) tensors to write into (rows of a pass buffer) instead of fresh ones."""
-        sums, counts, hw = self._class_sums(feat_cls, outputs, labels_val, labels_full)
-        n, c, d = sums.shape
-        dev, st = sums.device, L.stream()
+        sums_p, counts_p, (n, c, d, hw), ws = self._class_sums(feat_cls, outputs, labels_val, labels_full)
+        dev, st = ws.device, L.stream()
         if out_rows is not None:
             vec, vecsum, valid = out_rows
             if (tuple(vec.shape), tuple(vecsum.shape), tuple(valid.shape)) != ((n, c, d), (n, c), (n, c)) or \
@@ -130,8 +130,10 @@ class Class_Features:
             vec = torch.empty((n, c, d), dtype=torch.float32, device=dev)
             vecsum = torch.empty((n, c), dtype=torch.float32, device=dev)
             valid = torch.empty((n, c), dtype=torch.uint8, device=dev)
-        L.check(L.lib.diga_centroid_means(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, vec.data_ptr(),
-                                          vecsum.data_ptr(), valid.data_ptr(), st))
+        if n and hw and d:
+            L.check(L.lib.diga_centroid_means(sums_p, counts_p, n, c, d, hw, vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), st))
+        else:
+            vec.zero_(), vecsum.zero_(), valid.zero_()
         return vec, vecsum, valid
 
     def calculate_mean_vector(self, feat_cls, outputs, labels_val=None, model=None):
@@ -179,34 +181,15 @@ class Class_Features:
         ``update_objective_SingleVector`` on every returned vector in order, with no host sync."""
         mode = self._mode(name)
         self._require_state_device(feat_cls)
-        L.require_cuda(feat_cls, outputs, labels_val, labels_full, what="Class_Features input")
-        feat, out = L.f32c(feat_cls.detach()), L.f32c(outputs.detach())
-        n, d, h, w = feat.shape
-        c = self.class_numbers
+        feat, out, lab, full, hh, ww, (n, c, d, h, w), ws = self._prep(feat_cls, outputs, labels_val, labels_full)
         if d != self.feat_dim:
             raise ValueError(f"features have {d} channels, centroids have {self.feat_dim}")
-        if out.shape != (n, c, h, w):
-            raise ValueError(f"outputs must be [{n},{c},{h},{w}], got {tuple(out.shape)}")
-        if labels_val is not None and labels_full is not None:
-            raise ValueError("pass either labels_val (down-sampled fp32) or labels_full (int64), not both")
-        lab = full = None
-        hh = ww = 0
-        if labels_val is not None:
-            lab = L.f32c(labels_val.detach())
-            if lab.shape != (n, 1, h, w):
-                raise ValueError(f"labels_val must be [{n},1,{h},{w}], got {tuple(lab.shape)}")
-        if labels_full is not None:
-            full = L.i64c(labels_full)
-            if full.dim() != 3 or full.shape[0] != n:
-                raise ValueError(f"labels_full must be [{n},H,W] int64, got {tuple(full.shape)}")
-            hh, ww = full.shape[1], full.shape[2]
         if n == 0 or h * w == 0:
             return                                        # nothing to accumulate (the reference's loops simply do not run)
         self._proto_key = None
         # ONE scratch tensor and ONE library call queue the whole chain (assign -> accum -> finish): the reference drives this
         # path one image per call (calc_centroids.py:67-78), where per-kernel FFI calls and scratch tensors cost more host
         # time than the kernels take
-        ws = torch.empty((int(L.lib.diga_centroid_chain_workspace_bytes(n, c, d, h * w)),), dtype=torch.uint8, device=feat.device)
         L.check(L.lib.diga_centroid_chain(feat.data_ptr(), out.data_ptr(), L.ptr(lab), L.ptr(full), hh, ww, n, c, d, h, w,
                                           ws.data_ptr(), self._objective_vectors.data_ptr(),
                                           self._objective_vectors_num.data_ptr(), mode, int(bool(start_mean)),
@@ -252,14 +235,13 @@ class Class_Features:
 
     @L.on_device
     def accumulate_mean_pass(self, acc, feat_cls, outputs, labels_val=None):
-        """Multi-GPU 'mean' pass: ``acc [C, D+1]`` += (sum of per-image class means, image count).
-        ``diga_b200.parallel.finish_mean_pass`` all-reduces ``acc`` and writes the centroids."""
-        vec, vecsum, valid = self._masked_means(feat_cls, outputs, labels_val)
-        n, c, d = vec.shape
-        if tuple(acc.shape) != (c, d + 1) or acc.dtype != torch.float32 or not acc.is_cuda:
-            raise ValueError(f"acc must be a CUDA fp32 [{c},{d + 1}] tensor")
-        L.check(L.lib.diga_centroid_reduce_images(vec.data_ptr(), vecsum.data_ptr(), valid.data_ptr(), n, c, d,
-                                                  acc.data_ptr(), L.stream()))
+        """Multi-GPU 'mean' pass, sum mode: ``acc [C, D+1]`` += (sum of per-image class means, image count).
+        ``diga_b200.parallel.finish_mean_pass`` all-reduces ``acc`` and writes the centroids.  One library call per batch."""
+        feat, out, lab, full, hh, ww, (n, c, d, h, w), ws = self._prep(feat_cls, outputs, labels_val, None)
+        if tuple(acc.shape) != (c, d + 1) or acc.dtype != torch.float32 or not acc.is_cuda or acc.device != feat.device:
+            raise ValueError(f"acc must be a CUDA fp32 [{c},{d + 1}] tensor on {feat.device}")
+        L.check(L.lib.diga_centroid_chain_reduce(feat.data_ptr(), out.data_ptr(), L.ptr(lab), None, 0, 0, n, c, d, h, w, ws.data_ptr(),
+                                                 acc.data_ptr(), L.stream()))
 
     # -- a5 -------------------------------------------------------------------------------------
     @L.on_device

@@ -900,6 +900,7 @@ centroid_means_scatter_kernel(const float* __restrict__ sums, const int32_t* __r
       (peers.base[r] + peers.off_valid)[gnc] = (cnt >= 5) ? 1 : 0;
     }
   }
+  __threadfence_system();      // the peer / multicast stores are ordered before this kernel's completion at system scope
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1521,62 +1522,130 @@ int64_t diga_centroid_chain_workspace_bytes(int64_t n, int64_t C, int64_t D, int
   b += align_up((size_t)diga_centroid_clsw_bytes(n, hw), 256);                     // phase-shifted class words
   b += align_up((size_t)n * hw, 256);                                              // class map
   b += align_up((size_t)n * C * D * sizeof(float), 256);                           // class sums
-  if (!diga_centroid_finish_supported(n, D)) {
-    b += align_up((size_t)n * C * D * sizeof(float), 256);                         // vec
-    b += align_up((size_t)n * C * sizeof(float), 256) + align_up((size_t)n * C, 256);   // vecsum, valid
-  }
+  b += align_up((size_t)n * C * D * sizeof(float), 256);                           // vec     (paths that do not end in `finish`)
+  b += align_up((size_t)n * C * sizeof(float), 256) + align_up((size_t)n * C, 256);   // vecsum, valid
   return (int64_t)b;
 }
+
+namespace {
+struct ChainBufs {
+  int32_t* counts;
+  uint32_t* clsw;
+  uint8_t* cls;
+  float* sums;
+  float* vec;
+  float* vecsum;
+  uint8_t* valid;
+};
+
+ChainBufs chain_layout(void* workspace, int64_t n, int64_t C, int64_t D, int64_t hw) {
+  ChainBufs b;
+  unsigned char* p = static_cast<unsigned char*>(workspace);
+  b.counts = reinterpret_cast<int32_t*>(p);
+  p += align_up((size_t)n * C * sizeof(int32_t), 256);
+  b.clsw = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)diga_centroid_clsw_bytes(n, hw), 256);
+  b.cls = p;
+  p += align_up((size_t)n * hw, 256);
+  b.sums = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * D * sizeof(float), 256);
+  b.vec = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * D * sizeof(float), 256);
+  b.vecsum = reinterpret_cast<float*>(p);
+  p += align_up((size_t)n * C * sizeof(float), 256);
+  b.valid = p;
+  return b;
+}
+
+struct PdlScope {
+  explicit PdlScope(bool on) { diga::g_chain_pdl = on; }
+  ~PdlScope() { diga::g_chain_pdl = false; }
+};
+
+// assign -> accum into the workspace.  Short chains (the per-image calls of the reference's loops) launch accum (and the
+// finish kernel of diga_centroid_chain) as programmatic dependents of their predecessor: accum fetches its first feature
+// batch while assign still runs, finish is resident when the last accumulation CTA leaves — 24.5 -> 22.6 us per
+// [1,2048,65,129] call.  Long accumulations gain nothing (0.103 -> 0.105 ms at [8,2048,65,129]: the early feature requests only
+// compete with the assign kernel's own loads) and launch plainly.  Tunable chain_pdl: 0 = never, 1 = short chains, 2 = always.
+int chain_sums(const float* feat, const float* logits, const float* labels, const int64_t* labels_full, int64_t H, int64_t W,
+               int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, const ChainBufs& b, diga_stream_t stream) {
+  using namespace diga;
+  const int64_t hw = h * w;
+  int rc = labels_full ? diga_centroid_assign_fullres(logits, labels_full, n, C, h, w, H, W, b.cls, b.counts, b.clsw, stream)
+                       : diga_centroid_assign(logits, labels, n, C, hw, b.cls, b.counts, b.clsw, stream);
+  if (rc != DIGA_OK || hw == 0 || D == 0) return rc;
+  const int pdl_mode = tunable("chain_pdl", 1);
+  g_chain_pdl = pdl_mode == 2 || (pdl_mode == 1 && n * ((D + 3) / 4) <= (int64_t)sm_count() * 8);
+  return diga_centroid_accum(feat, b.cls, b.counts, b.clsw, n, D, C, hw, b.sums, stream);
+}
+
+int chain_check(const void* feat, const void* logits, const void* labels, const void* labels_full, void* workspace, int64_t n,
+                int64_t h, int64_t w, const char* what) {
+  using namespace diga;
+  DIGA_REQUIRE(feat && logits && workspace, DIGA_ERR_INVALID, "%s: null pointer", what);
+  DIGA_REQUIRE(!(labels && labels_full), DIGA_ERR_INVALID, "%s: pass labels or labels_full, not both", what);
+  DIGA_REQUIRE(aligned(workspace, 256), DIGA_ERR_MISALIGNED, "%s: workspace must be 256-byte aligned", what);
+  DIGA_REQUIRE(n >= 0 && h >= 0 && w >= 0, DIGA_ERR_INVALID, "%s: bad sizes", what);
+  return DIGA_OK;
+}
+}  // namespace
 
 int diga_centroid_chain(const float* feat, const float* logits, const float* labels, const int64_t* labels_full, int64_t H,
                         int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
                         float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
                         diga_stream_t stream) {
   using namespace diga;
-  DIGA_REQUIRE(feat && logits && workspace && objective_vectors && objective_num, DIGA_ERR_INVALID, "centroid_chain: null pointer");
-  DIGA_REQUIRE(!(labels && labels_full), DIGA_ERR_INVALID, "centroid_chain: pass labels or labels_full, not both");
-  DIGA_REQUIRE(aligned(workspace, 256), DIGA_ERR_MISALIGNED, "centroid_chain: workspace must be 256-byte aligned");
-  DIGA_REQUIRE(n >= 0 && h >= 0 && w >= 0, DIGA_ERR_INVALID, "centroid_chain: bad sizes");
+  int rc = chain_check(feat, logits, labels, labels_full, workspace, n, h, w, "centroid_chain");
+  if (rc != DIGA_OK) return rc;
+  DIGA_REQUIRE(objective_vectors && objective_num, DIGA_ERR_INVALID, "centroid_chain: null pointer");
   if (n == 0) return DIGA_OK;
   const int64_t hw = h * w;
-  unsigned char* p = static_cast<unsigned char*>(workspace);
-  int32_t* counts = reinterpret_cast<int32_t*>(p);
-  p += align_up((size_t)n * C * sizeof(int32_t), 256);
-  uint32_t* clsw = reinterpret_cast<uint32_t*>(p);
-  p += align_up((size_t)diga_centroid_clsw_bytes(n, hw), 256);
-  uint8_t* cls = p;
-  p += align_up((size_t)n * hw, 256);
-  float* sums = reinterpret_cast<float*>(p);
-  p += align_up((size_t)n * C * D * sizeof(float), 256);
-  int rc = labels_full ? diga_centroid_assign_fullres(logits, labels_full, n, C, h, w, H, W, cls, counts, clsw, stream)
-                       : diga_centroid_assign(logits, labels, n, C, hw, cls, counts, clsw, stream);
-  if (rc != DIGA_OK) return rc;
-  if (hw == 0 || D == 0) return DIGA_OK;
-  // Short chains (the per-image calls of the reference's loops) launch accum and finish as programmatic dependents of their
-  // predecessor: accum fetches its first feature batch while assign still runs, finish is resident when the last
-  // accumulation CTA leaves — 24.5 -> 22.6 us per [1,2048,65,129] call.  Long accumulations gain nothing (0.103 -> 0.105 ms
-  // at [8,2048,65,129]: the early feature requests only compete with the assign kernel's own loads) and launch plainly.
-  // Tunable chain_pdl: 0 = never, 1 = short chains (default), 2 = always.
-  struct PdlScope {
-    explicit PdlScope(bool on) { g_chain_pdl = on; }
-    ~PdlScope() { g_chain_pdl = false; }
-  };
-  const int pdl_mode = tunable("chain_pdl", 1);
-  PdlScope pdl_scope(pdl_mode == 2 || (pdl_mode == 1 && n * ((D + 3) / 4) <= (int64_t)sm_count() * 8));
-  rc = diga_centroid_accum(feat, cls, counts, clsw, n, D, C, hw, sums, stream);
-  if (rc != DIGA_OK) return rc;
+  const ChainBufs b = chain_layout(workspace, n, C, D, hw);
+  PdlScope pdl_scope(false);
+  rc = chain_sums(feat, logits, labels, labels_full, H, W, n, C, D, h, w, b, stream);
+  if (rc != DIGA_OK || hw == 0 || D == 0) return rc;
   if (diga_centroid_finish_supported(n, D))
-    return diga_centroid_finish(sums, counts, n, C, D, hw, nullptr, nullptr, nullptr, objective_vectors, objective_num, mode,
+    return diga_centroid_finish(b.sums, b.counts, n, C, D, hw, nullptr, nullptr, nullptr, objective_vectors, objective_num, mode,
                                 start_mean, momentum, stream);
   g_chain_pdl = false;
-  float* vec = reinterpret_cast<float*>(p);
-  p += align_up((size_t)n * C * D * sizeof(float), 256);
-  float* vecsum = reinterpret_cast<float*>(p);
-  p += align_up((size_t)n * C * sizeof(float), 256);
-  uint8_t* valid = p;
-  rc = diga_centroid_means(sums, counts, n, C, D, hw, vec, vecsum, valid, stream);
+  rc = diga_centroid_means(b.sums, b.counts, n, C, D, hw, b.vec, b.vecsum, b.valid, stream);
   if (rc != DIGA_OK) return rc;
-  return diga_centroid_update(vec, vecsum, valid, n, C, D, objective_vectors, objective_num, mode, start_mean, momentum, stream);
+  return diga_centroid_update(b.vec, b.vecsum, b.valid, n, C, D, objective_vectors, objective_num, mode, start_mean, momentum, stream);
+}
+
+int diga_centroid_chain_sums(const float* feat, const float* logits, const float* labels, const int64_t* labels_full, int64_t H,
+                             int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
+                             float** sums_out, int32_t** counts_out, diga_stream_t stream) {
+  using namespace diga;
+  int rc = chain_check(feat, logits, labels, labels_full, workspace, n, h, w, "centroid_chain_sums");
+  if (rc != DIGA_OK) return rc;
+  DIGA_REQUIRE(sums_out && counts_out, DIGA_ERR_INVALID, "centroid_chain_sums: null pointer");
+  const ChainBufs b = chain_layout(workspace, n, C, D, h * w);
+  *sums_out = b.sums;
+  *counts_out = b.counts;
+  if (n == 0) return DIGA_OK;
+  PdlScope pdl_scope(false);
+  return chain_sums(feat, logits, labels, labels_full, H, W, n, C, D, h, w, b, stream);
+}
+
+int diga_centroid_chain_reduce(const float* feat, const float* logits, const float* labels, const int64_t* labels_full, int64_t H,
+                               int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace, float* acc,
+                               diga_stream_t stream) {
+  using namespace diga;
+  int rc = chain_check(feat, logits, labels, labels_full, workspace, n, h, w, "centroid_chain_reduce");
+  if (rc != DIGA_OK) return rc;
+  DIGA_REQUIRE(acc, DIGA_ERR_INVALID, "centroid_chain_reduce: null pointer");
+  if (n == 0) return DIGA_OK;
+  const int64_t hw = h * w;
+  const ChainBufs b = chain_layout(workspace, n, C, D, hw);
+  {
+    PdlScope pdl_scope(false);
+    rc = chain_sums(feat, logits, labels, labels_full, H, W, n, C, D, h, w, b, stream);
+  }
+  if (rc != DIGA_OK || hw == 0 || D == 0) return rc;
+  rc = diga_centroid_means(b.sums, b.counts, n, C, D, hw, b.vec, b.vecsum, b.valid, stream);
+  if (rc != DIGA_OK) return rc;
+  return diga_centroid_reduce_images(b.vec, b.vecsum, b.valid, n, C, D, acc, stream);
 }
 
 int diga_centroid_update_single(const float* vector, int64_t id, int64_t C, int64_t D, float* objective_vectors,

@@ -210,8 +210,7 @@ class ShardedCentroidPass:
             self.cf._masked_means(feat_cls, outputs, labels_val, labels_full, out_rows=(self.vec[rows], self.vecsum[rows], self.valid[rows]))
             return
         with torch.cuda.device(feat_cls.device):
-            sums, counts, hw = self.cf._class_sums(feat_cls, outputs, labels_val, labels_full)
-            n, c, d = sums.shape
+            sums_p, counts_p, (n, c, d, hw), ws = self.cf._class_sums(feat_cls, outputs, labels_val, labels_full)
             off = self._symm["off"]
             # the scatter kernel runs on a side stream: its NVLink stores (and their acknowledgement latency) overlap the
             # assign / accumulation kernels of the next batch instead of sitting between them
@@ -219,11 +218,10 @@ class ShardedCentroidPass:
             side = self._symm.setdefault("side", torch.cuda.Stream())
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                L.check(L.lib.diga_centroid_means_scatter(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, self._symm["ptrs"],
+                L.check(L.lib.diga_centroid_means_scatter(sums_p, counts_p, n, c, d, hw, self._symm["ptrs"],
                                                           self._symm["mc"], self.world, off[0], off[1], off[2],
                                                           self.rank * max(self.per_shard, 1) + rows.start, side.cuda_stream))
-            sums.record_stream(side)
-            counts.record_stream(side)
+            ws.record_stream(side)
 
     def gather(self):
         """The exchange: all-gather of the three row buffers -> ``[world * per_shard, ...]`` on every rank.  With symmetric

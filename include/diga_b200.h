@@ -159,6 +159,14 @@ int diga_centroid_chain(const float* feat, const float* logits, const float* lab
                         int64_t H, int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
                         float* objective_vectors, float* objective_num, int mode, int start_mean, double momentum,
                         diga_stream_t stream);
+/* The same chain up to the class sums (assign -> accum): *sums_out [n,C,D] and *counts_out [n,C] point into the workspace. */
+int diga_centroid_chain_sums(const float* feat, const float* logits, const float* labels, const int64_t* labels_full,
+                             int64_t H, int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w, void* workspace,
+                             float** sums_out, int32_t** counts_out, diga_stream_t stream);
+/* ... and ending in the multi-GPU sum-mode accumulator: assign -> accum -> means -> acc[C, D+1] += (vectors, their number). */
+int diga_centroid_chain_reduce(const float* feat, const float* logits, const float* labels, const int64_t* labels_full,
+                               int64_t H, int64_t W, int64_t n, int64_t C, int64_t D, int64_t h, int64_t w,
+                               void* workspace, float* acc, diga_stream_t stream);
 /* means fused with the exchange of the image-sharded exact mode: like diga_centroid_means, but the rows (vec, vecsum, valid of
  * the n local images) are stored at row row0.. of the gathered buffers of ALL `world` ranks through peer pointers
  * (peer_bases[r]: base of rank r's symmetric allocation, host array; the three arrays live at the given byte offsets in each).

@@ -494,9 +494,9 @@ def test_finish_kernel_equals_means_plus_update_bitwise(D, n, d, h, w, name, sta
     assert torch.equal(a.objective_vectors_num, b.objective_vectors_num)
     assert torch.equal(a.objective_vectors, b.objective_vectors)
     # the optional outputs of the fused kernel equal the means kernel's (vecsum: another summation order, 1e-6)
-    sums, counts, hw = a._class_sums(feat, out, lab)
+    sums_p, counts_p, (_, _, _, hw), ws = a._class_sums(feat, out, lab)        # pointers into the scratch tensor `ws`
     v2, s2, ok2 = torch.empty_like(vec), torch.empty_like(vecsum), torch.empty_like(valid)
-    L.check(L.lib.diga_centroid_finish(sums.data_ptr(), counts.data_ptr(), n, c, d, hw, v2.data_ptr(), s2.data_ptr(), ok2.data_ptr(),
+    L.check(L.lib.diga_centroid_finish(sums_p, counts_p, n, c, d, hw, v2.data_ptr(), s2.data_ptr(), ok2.data_ptr(),
                                        None, None, 0, 1, 1e-4, L.stream()))
     assert torch.equal(v2, vec) and torch.equal(ok2, valid)
     assert torch.allclose(s2, vecsum, rtol=1e-5, atol=1e-5 * float(vec.abs().max()) * 4)
