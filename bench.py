@@ -1003,6 +1003,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         ke = max(3, min(K, 30))
+        affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
         numa = bind_to_gpu_numa_node(local_rank)           # pinned buffers are first-touched on the GPU's own NUMA node
         host_t = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
         host_s = torch.empty(KD_SHAPE, dtype=torch.float32).pin_memory()
@@ -1110,6 +1111,8 @@ def main():
                     "nn.Upsample, self_training.py:344,351): H2D of both maps, D2H of the loss and of the gradient, one stream, "
                     "eager; includes the up-sampling the reference arm does not time"}
         del h_lt, h_ls, h_grad, d_lt, d_ls
+        if affinity0 is not None:
+            os.sched_setaffinity(0, affinity0)             # the CPU arm (a child process) is meant to see every core again
 
     stages, accum_rows, c1_gpu = None, [], None
     if not args.no_stages:

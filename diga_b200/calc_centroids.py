@@ -290,15 +290,16 @@ def _labels_on_feature_grid(labels_i64, size):
     return F.interpolate(labels_i64.reshape([b, 1, h, w]).float(), size=tuple(size), mode='nearest')
 
 
-def _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess=None):
+def _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess=None, state=None):
     """One pass of the target loop (calc_centroids.py:67-78) under ``torchrun``: every rank runs the backbone only on the
     loader batches ``rank, rank + world, ...`` (all ranks iterate the SAME un-sharded loader, like the reference's), the
     per-image class vectors are all-gathered once and replayed in loader order (exact mode of ``diga_b200.parallel``): all
     ranks end the pass with the centroids the single-process loop produces."""
     from .parallel import ShardedCentroidPass
-    sp = None
-    n_images = len(target_loader.dataset) if hasattr(target_loader, "dataset") else None
-    bsz = getattr(target_loader, "batch_size", None)
+    state = {} if state is None else state
+    sp = state.get("pass")                       # the row buffers (a symmetric allocation) are set up once and re-used by every pass
+    n_images = len(target_loader.dataset) if hasattr(target_loader, "dataset") else state.get("n_images")
+    bsz = getattr(target_loader, "batch_size", None) or state.get("bsz")
     pending = []
     for index, batch in enumerate(target_loader):
         if index % world != rank:
@@ -312,7 +313,7 @@ def _sharded_target_pass(class_features, model, target_loader, rank, world, firs
                 class_features.objective_vectors = torch.zeros([19, feature_t.shape[1]])
                 first = False
             if sp is None and n_images is not None and bsz:
-                sp = ShardedCentroidPass(class_features, n_images, bsz, 'mean')
+                sp = state["pass"] = ShardedCentroidPass(class_features, n_images, bsz, 'mean')
             if sp is not None:
                 sp.add(feature_t, out)
             else:
@@ -325,7 +326,8 @@ def _sharded_target_pass(class_features, model, target_loader, rank, world, firs
         torch.distributed.all_reduce(sizes[1:], op=torch.distributed.ReduceOp.MAX)
         if first and int(tot[0]) > 0:
             raise RuntimeError("calc_centroids: this rank received no batch, cannot infer the feature dimension")
-        sp = ShardedCentroidPass(class_features, int(tot[0]), max(int(sizes[1]), 1), 'mean', symmetric=False)
+        state["n_images"], state["bsz"] = int(tot[0]), max(int(sizes[1]), 1)      # known from now on: later passes use add()
+        sp = ShardedCentroidPass(class_features, state["n_images"], state["bsz"], 'mean', symmetric=False)
         for p in pending:
             sp.add_rows(*p)
     sp.finish()
@@ -351,6 +353,7 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
     rank, world = 0, 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    sharded_state = {}
     for epoch in range(5):
         model.eval(), enc_s.eval(), dec_s2t.eval()
         opt.source = False
@@ -368,7 +371,7 @@ def calc_centroids(opt, model, enc_s, dec_s2t, source_loader, source_loader_full
                     newlabels = _labels_on_feature_grid(slabelv, out.size()[2:])
                     class_features.update_from_features(feature_s, out, newlabels, 'mean')
         elif world > 1:
-            _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess)
+            _sharded_target_pass(class_features, model, target_loader, rank, world, first, preprocess, sharded_state)
             first = False
         else:
             for index, batch in enumerate(target_loader):
