@@ -906,8 +906,10 @@ centroid_means_scatter_kernel(const float* __restrict__ sums, const int32_t* __r
 // ------------------------------------------------------------------------------------------------
 // update (calc_centroids.py:147-164), arithmetic mirrored op for op (separately rounded mul/add/div)
 // ------------------------------------------------------------------------------------------------
+constexpr int kUpdateSum = 2;   // internal: the sum-mode accumulator of the multi-GPU pass (not a reference update rule)
+
 struct UpdateRule {
-  int mode;          // DIGA_UPDATE_*
+  int mode;          // DIGA_UPDATE_* or kUpdateSum
   int start_mean;
   float m, one_minus_m;
 };
@@ -1072,7 +1074,10 @@ template <int BLOCK, int K, int NR>
 __global__ void __launch_bounds__(BLOCK)
 centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict__ counts, int n, int64_t C, int64_t D,
                        int64_t hw, float* __restrict__ vec, float* __restrict__ vecsum, uint8_t* __restrict__ valid,
-                       float* __restrict__ obj, float* __restrict__ objnum, UpdateRule rule, int do_update) {
+                       float* __restrict__ obj, float* __restrict__ objnum, UpdateRule rule, int do_update, int64_t obj_stride,
+                       int64_t num_stride) {
+  // obj_stride / num_stride: row pitch of the centroid matrix and element pitch of the counts — D and 1 for the state of
+  // Class_Features, D+1 and D+1 when the target is the sum-mode accumulator acc[C, D+1] (count in column D, rule.mode = SUM)
   static_assert(NR * K <= kFinishMaxRows, "register budget");   // NR: image rows a thread holds (>= n), K: channels per row
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float warp_part[NR][BLOCK / 32];
@@ -1082,7 +1087,7 @@ centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict
   const int Y = gridDim.y;                                   // == cluster size along y
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_wait();                                                // (chain: the accumulation kernel's sums must have landed)
-  float num = do_update ? objnum[c] : 0.f;
+  float num = do_update ? objnum[c * num_stride] : 0.f;
   float v[NR][K];                                            // image i, channel dbase + k*Y*BLOCK
   const int64_t dbase = (int64_t)blockIdx.y * BLOCK + threadIdx.x;
   // all loads first (counts, then the sums unconditionally), arithmetic afterwards: the divisions below carry a slow-path
@@ -1148,23 +1153,29 @@ centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int64_t d = dbase + (int64_t)k * Y * BLOCK;
-    o[k] = d < D ? obj[c * D + d] : 0.f;
+    o[k] = d < D ? obj[c * obj_stride + d] : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     if (i < n && cnt[i] >= 5 && tot[i] != 0.f) {                          // :134/:136 skips, :148
-      const bool mean = rule_is_mean(rule, num);
+      if (rule.mode == kUpdateSum) {                                      // multi-GPU sum mode: acc += (vector, 1)
 #pragma unroll
-      for (int k = 0; k < K; ++k) o[k] = rule_apply(rule, mean, o[k], num, v[i][k]);
-      num = fminf(__fadd_rn(num, 1.f), 3000.f);                           // :155-156 / :159,161
+        for (int k = 0; k < K; ++k) o[k] += v[i][k];
+        num += 1.f;
+      } else {
+        const bool mean = rule_is_mean(rule, num);
+#pragma unroll
+        for (int k = 0; k < K; ++k) o[k] = rule_apply(rule, mean, o[k], num, v[i][k]);
+        num = fminf(__fadd_rn(num, 1.f), 3000.f);                         // :155-156 / :159,161
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int64_t d = dbase + (int64_t)k * Y * BLOCK;
-    if (d < D) obj[c * D + d] = o[k];
+    if (d < D) obj[c * obj_stride + d] = o[k];
   }
-  if (blockIdx.y == 0 && threadIdx.x == 0) objnum[c] = num;
+  if (blockIdx.y == 0 && threadIdx.x == 0) objnum[c * num_stride] = num;
 }
 
 template <int BLOCK>
@@ -1453,15 +1464,27 @@ int diga_centroid_finish_supported(int64_t n, int64_t D) {
   return (Kp <= 4 && Np * Kp <= diga::kFinishMaxRows) ? 1 : 0;
 }
 
+static int centroid_finish_impl(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw, float* vec,
+                                float* vecsum, uint8_t* valid, float* objective_vectors, float* objective_num, int mode,
+                                int start_mean, double momentum, int64_t obj_stride, int64_t num_stride, diga_stream_t stream);
+
 int diga_centroid_finish(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw, float* vec,
                          float* vecsum, uint8_t* valid, float* objective_vectors, float* objective_num, int mode, int start_mean,
                          double momentum, diga_stream_t stream) {
   using namespace diga;
+  DIGA_REQUIRE(objective_vectors == nullptr || mode == DIGA_UPDATE_MEAN || mode == DIGA_UPDATE_MOVING_AVERAGE, DIGA_ERR_INVALID,
+               "no such updating way of objective vectors %d", mode);
+  return centroid_finish_impl(sums, counts, n, C, D, hw, vec, vecsum, valid, objective_vectors, objective_num, mode, start_mean,
+                              momentum, D, 1, stream);
+}
+
+static int centroid_finish_impl(const float* sums, const int32_t* counts, int64_t n, int64_t C, int64_t D, int64_t hw, float* vec,
+                                float* vecsum, uint8_t* valid, float* objective_vectors, float* objective_num, int mode,
+                                int start_mean, double momentum, int64_t obj_stride, int64_t num_stride, diga_stream_t stream) {
+  using namespace diga;
   DIGA_REQUIRE(sums && counts, DIGA_ERR_INVALID, "centroid_finish: null pointer");
   const int do_update = objective_vectors != nullptr;
   DIGA_REQUIRE(!do_update || objective_num != nullptr, DIGA_ERR_INVALID, "centroid_finish: objective_num missing");
-  DIGA_REQUIRE(!do_update || mode == DIGA_UPDATE_MEAN || mode == DIGA_UPDATE_MOVING_AVERAGE, DIGA_ERR_INVALID,
-               "no such updating way of objective vectors %d", mode);
   DIGA_REQUIRE(C >= 1 && C <= 65535 && hw > 0, DIGA_ERR_INVALID, "centroid_finish: bad sizes");
   DIGA_REQUIRE(diga_centroid_finish_supported(n, D), DIGA_ERR_INVALID,
                "centroid_finish: n=%lld rows of D=%lld exceed the register budget (use centroid_means + centroid_update)",
@@ -1488,7 +1511,7 @@ int diga_centroid_finish(const float* sums, const int32_t* counts, int64_t n, in
   while (np < n) np *= 2;
 #define DIGA_FINISH_KN(KK, NN)                                                                                                \
   e = cudaLaunchKernelEx(&cfg, centroid_finish_kernel<256, KK, NN>, sums, counts, (int)n, C, D, hw, vec, vecsum, valid,      \
-                         objective_vectors, objective_num, rule, do_update)
+                         objective_vectors, objective_num, rule, do_update, obj_stride, num_stride)
 #define DIGA_FINISH_K(KK)                                                                                                     \
   do {                                                                                                                        \
     if (np == 1) DIGA_FINISH_KN(KK, 1);                                                                                       \
@@ -1643,6 +1666,11 @@ int diga_centroid_chain_reduce(const float* feat, const float* logits, const flo
     rc = chain_sums(feat, logits, labels, labels_full, H, W, n, C, D, h, w, b, stream);
   }
   if (rc != DIGA_OK || hw == 0 || D == 0) return rc;
+  // means + reduce in ONE cluster launch (the finish kernel with the accumulator as its target: acc[c][:D] += vector,
+  // acc[c][D] += 1 for every valid image) — 10.5 us of two small kernels -> one, per batch
+  if (diga_centroid_finish_supported(n, D) && tunable("chain_reduce_fused", 1))
+    return centroid_finish_impl(b.sums, b.counts, n, C, D, hw, nullptr, nullptr, nullptr, acc, acc + D, kUpdateSum, 0, 0.0, D + 1, D + 1,
+                                stream);
   rc = diga_centroid_means(b.sums, b.counts, n, C, D, hw, b.vec, b.vecsum, b.valid, stream);
   if (rc != DIGA_OK) return rc;
   return diga_centroid_reduce_images(b.vec, b.vecsum, b.valid, n, C, D, acc, stream);
