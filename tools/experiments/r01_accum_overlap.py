@@ -1,4 +1,6 @@
-"""Two experiments, one GPU call (results -> gpurun_out/exp_accum_overlap.jsonl):
+"""[round-1 ABI: diga_centroid_accum has since gained the counts / class-word arguments; kept as the record of the round-1
+experiment, not runnable against the current library]
+Two experiments, one GPU call (results -> gpurun_out/exp_accum_overlap.jsonl):
  (1) centroid_accum_quad_kernel against the label pattern (constant / large regions / 4x4 blocks / iid) for the default
      launch shape and the cross-item prefetch variants (13-15);
  (2) config 5 per image: the ALU-bound two-scale label kernel on a side stream beside the HBM-bound distance kernel."""

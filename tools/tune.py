@@ -86,21 +86,22 @@ def sweep_pl():
 
 
 def sweep_accum():
+    """Superseded by tools/sweep_accum.py (round 2: every shape x label pattern x kernel variant, checked against the round-1
+    kernel); kept as the short form.  Class maps are plain byte maps here, so the class words come from diga_centroid_clsw_build."""
     g = S.gen(3, dev)
     for (n, d, h, w) in ((8, 2048, 65, 129), (8, 2048, 64, 128), (1, 2048, 65, 129)):
+        hw = h * w
         feat = S.features((n, d, h, w), g)
-        cls = torch.randint(0, 19, (n, h * w), device=dev, dtype=torch.uint8)
         sums = torch.empty((n, 19, d), device=dev)
-        for variant in (0, 2, 6, 9):
-            L.set_tunable("accum_variant", variant)
-            ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
-            report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "random"}, ms, feat.numel() * 4)
-        blk = S.block_labels(n, h, w, S.gen(9, dev), 4, 19, 0.1)           # 32x32 image blocks at stride 8
-        cls2 = blk.reshape(n, h * w).to(torch.uint8).contiguous()
-        for variant in (0, 2, 6, 9):
-            L.set_tunable("accum_variant", variant)
-            ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls2.data_ptr(), n, d, 19, h * w, sums.data_ptr(), L.stream())))
-            report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": "4x4 blocks"}, ms, feat.numel() * 4)
+        clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev)
+        for label, cls in (("random", torch.randint(0, 19, (n, hw), device=dev, dtype=torch.uint8)),
+                           ("4x4 blocks", S.block_labels(n, h, w, S.gen(9, dev), 4, 19, 0.1).reshape(n, hw).to(torch.uint8).contiguous())):
+            L.check(L.lib.diga_centroid_clsw_build(cls.data_ptr(), n, 19, hw, clsw.data_ptr(), L.stream()))
+            for variant in (0, 14, 17, 9, 2):
+                L.set_tunable("accum_variant", variant)
+                ms = timeit(lambda: L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), None, clsw.data_ptr(), n, d, 19, hw,
+                                                                      sums.data_ptr(), L.stream())))
+                report("centroid_accum", {"variant": variant, "shape": [n, d, h, w], "labels": label}, ms, feat.numel() * 4)
     L.set_tunable("accum_variant", 0)
 
 
