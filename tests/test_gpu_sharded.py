@@ -501,3 +501,26 @@ def test_finish_kernel_equals_means_plus_update_bitwise(D, n, d, h, w, name, sta
     assert torch.equal(v2, vec) and torch.equal(ok2, valid)
     assert torch.allclose(s2, vecsum, rtol=1e-5, atol=1e-5 * float(vec.abs().max()) * 4)
     assert not L.lib.diga_centroid_finish_supported(17, 2048) and not L.lib.diga_centroid_finish_supported(2, 8 * 2048 + 1)
+
+
+def test_accum_from_plain_class_map_and_built_class_words(D):
+    """The C-ABI pieces a caller with its own class map uses: diga_centroid_clsw_build + diga_centroid_accum without the
+    per-image counts (every class is then cleared, reduced and written) against the einsum of the one-hot map."""
+    from diga_b200 import _lib as L, synthetic as S
+    g = S.gen(12, "cuda")
+    for n, d, h, w, c in ((2, 256, 65, 129, 19), (1, 128, 9, 12, 16), (2, 64, 5, 7, 19)):
+        hw = h * w
+        feat = S.features((n, d, h, w), g)
+        cls = torch.randint(0, c, (n, hw), device=dev(), dtype=torch.uint8, generator=g)
+        cls[:, ::7] = 255                                                   # gated-out pixels
+        clsw = torch.empty((int(L.lib.diga_centroid_clsw_bytes(n, hw)) // 4,), dtype=torch.int32, device=dev())
+        sums = torch.full((n, c, d), float("nan"), device=dev())
+        L.check(L.lib.diga_centroid_clsw_build(cls.data_ptr(), n, c, hw, clsw.data_ptr(), L.stream()))
+        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), None, clsw.data_ptr(), n, d, c, hw, sums.data_ptr(), L.stream()))
+        onehot = torch.nn.functional.one_hot(cls.long(), 256)[:, :, :c].double()               # [n, hw, c]; 255 -> no class
+        want = torch.einsum("ndp,npc->ncd", feat.reshape(n, d, hw).double(), onehot)
+        assert_normwise(sums, want, what=f"class sums {(n, d, h, w)}")
+        # without class words the round-1 byte-map kernel answers; same sums
+        sums2 = torch.empty_like(sums)
+        L.check(L.lib.diga_centroid_accum(feat.data_ptr(), cls.data_ptr(), None, None, n, d, c, hw, sums2.data_ptr(), L.stream()))
+        assert_normwise(sums2, want, what="byte-map kernel")
