@@ -835,6 +835,14 @@ static int launch_accum(const float* feat, const uint8_t* cls, int nclass, int64
 // ------------------------------------------------------------------------------------------------
 // means
 // ------------------------------------------------------------------------------------------------
+// Per-image class mean of one channel: the reference forms avgpool(feat * mask) / avgpool(mask) = (sum / hw) / (count / hw)
+// (calc_centroids.py:129,141) — three fp32 roundings around the exact value sum / count, on top of torch's own summation
+// order.  One correctly rounded division is at least as close to it (parity bar for the vectors: 1e-5) and is the ONE
+// expression every kernel below uses, so that all paths (means, finish, means + scatter) produce the same bits.  Round 1 used
+// the two-division form; the finish kernel is a chain of dependent arithmetic on two warps per scheduler, and the divisions
+// were a third of its instructions.
+__device__ __forceinline__ float class_mean(float sum, int cnt) { return __fdiv_rn(sum, (float)cnt); }
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 centroid_means_kernel(const float* __restrict__ sums, const int32_t* __restrict__ counts, int64_t C, int64_t D,
@@ -843,11 +851,10 @@ centroid_means_kernel(const float* __restrict__ sums, const int32_t* __restrict_
   const int64_t nc = (int64_t)blockIdx.y * C + blockIdx.x;
   const int cnt = counts[nc];
   // calc_centroids.py:129,141: avgpool(feat*mask) / avgpool(mask) == (sum/hw) / (count/hw)
-  const float frac = (float)cnt / (float)hw;
   float part = 0.f;
   for (int64_t d = threadIdx.x; d < D; d += BLOCK) {
     float v = 0.f;
-    if (cnt > 0) v = (sums[nc * D + d] / (float)hw) / frac;
+    if (cnt > 0) v = class_mean(sums[nc * D + d], cnt);
     vec[nc * D + d] = v;
     part += v;
   }
@@ -878,11 +885,10 @@ centroid_means_scatter_kernel(const float* __restrict__ sums, const int32_t* __r
   const int64_t nc = (int64_t)blockIdx.y * C + blockIdx.x;                 // local (image, class)
   const int64_t gnc = (row0 + blockIdx.y) * C + blockIdx.x;                // its place in the gathered buffers
   const int cnt = counts[nc];
-  const float frac = (float)cnt / (float)hw;
   float part = 0.f;
   for (int64_t d = threadIdx.x; d < D; d += BLOCK) {
     float v = 0.f;
-    if (cnt > 0) v = (sums[nc * D + d] / (float)hw) / frac;                // same expression as centroid_means_kernel
+    if (cnt > 0) v = class_mean(sums[nc * D + d], cnt);                    // same expression as centroid_means_kernel
     if (peers.multicast != nullptr) {
       // one store, replicated by the NVSwitch into every rank's copy (the 155 KB of a row leave this GPU once, not `world` times)
       asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(peers.multicast + peers.off_vec) + gnc * D + d),
@@ -1104,14 +1110,12 @@ centroid_finish_kernel(const float* __restrict__ sums, const int32_t* __restrict
       v[i][k] = (i < n && d < D) ? __ldg(sums + (i * C + c) * D + d) : 0.f;      // (garbage where cnt == 0: masked below)
     }
   }
-  const float fhw = (float)hw;
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int64_t d = dbase + (int64_t)k * Y * BLOCK;
-      // calc_centroids.py:129,141: avgpool(feat*mask) / avgpool(mask) == (sum/hw) / (count/hw)
-      v[i][k] = (i < n && d < D && cnt[i] > 0) ? (v[i][k] / fhw) / ((float)cnt[i] / fhw) : 0.f;
+      v[i][k] = (i < n && d < D && cnt[i] > 0) ? class_mean(v[i][k], cnt[i]) : 0.f;
       if (i < n && d < D && vec != nullptr) vec[(i * C + c) * D + d] = v[i][k];
     }
   }

@@ -104,7 +104,8 @@ int diga_classmix_blend(const int64_t* slabel, const uint8_t* lut_host, const fl
  *           labels: [n,1,hw] fp32 as produced by F.interpolate(mode='nearest') of the int64 map.
  *   accum : sums[n][c][d] = sum over pixels of class c of feat[n,d,p]  (fully overwritten,
  *           deterministic: every output element has exactly one writer, no atomics).
- *   means : vec[n][c][d] = (sums/hw) / (counts/hw); valid[n][c] = counts >= 5;
+ *   means : vec[n][c][d] = sums / counts (one correctly rounded division; the reference's (sum/hw) / (count/hw) rounds
+ *           three times around the same value); valid[n][c] = counts >= 5;
  *           vecsum[n][c] = sum_d vec (for the reference's `vector.sum() == 0` skip).
  * ------------------------------------------------------------------------------------------ */
 /* clsw (optional, may be NULL): phase-shifted class words for the 128-bit accumulation kernel, diga_centroid_clsw_bytes(n, hw)
