@@ -1174,6 +1174,11 @@ def main():
             from_stage("a6+a7", "centroid_accumulate_update_d2048_blocky_classes", "update_from_features call: assign + accum + finish (4x4 blocks)", "hbm", "feature-px")
             from_stage("f2", "cross_entropy2d_fwd_bwd", "ce_kernel fwd + bwd", "hbm", "px")
             from_stage("f4", "ema_teacher_update", "ema_update_kernel", "hbm", "parameter")
+            from_stage("f1", "kd_fused_upsample_fwd_bwd", "loss_up_kernel<KD> loss+gradient from the stride-8 logits (distillation_loss_upsampled + autograd)", "alu", "pixel-position")
+            from_stage("f1+f2", "cross_entropy2d_fused_upsample_fwd_bwd", "loss_up_kernel<CE> loss+gradient from the stride-8 logits", "alu", "px")
+            from_stage("f1", "seg_plus_kd_fused_upsample_fwd_bwd", "loss_up_kernel<KD+CE> loss pass + gradient pass (self_training.py:348-352)", "alu", "pixel-position")
+            from_stage("f5", "confusion_matrix_eval", "confusion_matrix_kernel (runningScore.update)", "hbm", "px")
+            from_stage("f3", "label_reader_resize_remap", "label_resize_remap_kernel (CityLoader NEAREST resize + id look-up)", "hbm", "px")
             for key, label in (("config3_self_training_step_dropin_functions", "config 3: self-training step hot path with ONLY the function names swapped (losses behind torch's nn.Upsample)"),
                                ("config3_self_training_step_dropin_functions_lazy_upsample", "config 3: same unchanged call sites, the scripts' three nn.Upsample modules built from diga_b200.nn.Upsample"),
                                ("config3_self_training_step_fused_call_sites", "config 3: self-training step hot path, B=8 @512x1024, D=2048 (patched call sites)"),
