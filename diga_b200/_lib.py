@@ -85,6 +85,8 @@ SIGNATURES = {
     "diga_png_deflate_scratch_bytes": (_i64, [_i64, _i64]),
     "diga_png_deflate": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p, _p]),
     "diga_png_write_file": (_i, [C.c_char_p, _p, _i64, _i64, _i64, _p, _i64]),
+    "diga_png_crc": (_i, [_p, _i64, _i64, _p, _p, _p]),
+    "diga_png_write_file_crc": (_i, [C.c_char_p, _p, _i64, _i64, _i64, _p, _i64, C.c_uint32]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

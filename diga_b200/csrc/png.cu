@@ -354,20 +354,131 @@ void put_be32(uint8_t* p, uint32_t v) {
   p[3] = (uint8_t)v;
 }
 
-bool write_chunk(FILE* f, const char tag[4], const uint8_t* data, size_t n) {
+// `known_crc`: the chunk's CRC-32 when it was already computed (the IDAT chunk: on the GPU, diga_png_crc)
+bool write_chunk(FILE* f, const char tag[4], const uint8_t* data, size_t n, const uint32_t* known_crc = nullptr) {
   uint8_t head[8], tail[4];
   put_be32(head, (uint32_t)n);
   memcpy(head + 4, tag, 4);
-  uint32_t crc = crc32_update(0, head + 4, 4);
-  if (n) crc = crc32_update(crc, data, n);
+  uint32_t crc;
+  if (known_crc) {
+    crc = *known_crc;
+  } else {
+    crc = crc32_update(0, head + 4, 4);
+    if (n) crc = crc32_update(crc, data, n);
+  }
   put_be32(tail, crc);
   return fwrite(head, 1, 8, f) == 8 && (n == 0 || fwrite(data, 1, n, f) == n) && fwrite(tail, 1, 4, f) == 4;
 }
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// CRC-32 of the IDAT chunk ("IDAT" + zlib stream) on the GPU, so that the host only writes bytes.  CRC is linear over GF(2):
+// with raw(M) = M(x) * x^32 mod P (register starts at 0, no final inversion) the register after a message is
+//     crc32(M) = raw(M) ^ (0xffffffff * x^(8|M|) mod P) ^ 0xffffffff        and       raw(A || B) = raw(A) * x^(8|B|) ^ raw(B),
+// and leading zero bytes do not change raw().  One CTA per image: the message is cut, FROM ITS END, into 256 ranges of R bytes
+// (the first ranges may start before the message: virtual zeros), every thread runs the byte-wise table recurrence over its
+// range, and a shared-memory tree combines the 256 remainders — every right operand of level k has length R * 2^k, so one
+// multiplier x^(8 R 2^k) per level serves all pairs (multiplication mod P: zlib's multmodp, reflected bit order).
+// ------------------------------------------------------------------------------------------------
+namespace diga {
+
+constexpr uint32_t kCrcPoly = 0xedb88320u;
+__constant__ uint32_t kCrcX2n[32] = {   // x^(2^n) mod P, n = 0..31
+    0x40000000u, 0x20000000u, 0x08000000u, 0x00800000u, 0x00008000u, 0xedb88320u, 0xb1e6b092u, 0xa06a2517u,
+    0xed627daeu, 0x88d14467u, 0xd7bbfe6au, 0xec447f11u, 0x8e7ea170u, 0x6427800eu, 0x4d47bae0u, 0x09fe548fu,
+    0x83852d0fu, 0x30362f1au, 0x7b5a9cc3u, 0x31fec169u, 0x9fec022au, 0x6c8dedc4u, 0x15d6874du, 0x5fde7a4eu,
+    0xbad90e37u, 0x2e4e5eefu, 0x4eaba214u, 0xa8a472c0u, 0x429a969eu, 0x148d302au, 0xc40ba6d0u, 0xc4e22c3cu};
+
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (uint32_t m = 0x80000000u;; m >>= 1) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    if (m == 1) break;
+    b = (b & 1u) ? (b >> 1) ^ kCrcPoly : b >> 1;
+  }
+  return p;
+}
+// x^(8 * nbytes) mod P
+__device__ __forceinline__ uint32_t crc_x8n(uint64_t nbytes) {
+  uint32_t p = 0x80000000u;
+  for (unsigned k = 3; nbytes; nbytes >>= 1, ++k)
+    if (nbytes & 1) p = crc_multmodp(kCrcX2n[k & 31], p);
+  return p;
+}
+
+constexpr int kCrcBlock = 256;
+
+__global__ void __launch_bounds__(kCrcBlock)
+png_crc_kernel(const uint8_t* __restrict__ payload, int64_t capacity, const int64_t* __restrict__ lengths, uint32_t* __restrict__ crc_out) {
+  __shared__ uint32_t table[256];
+  __shared__ uint32_t part[kCrcBlock];
+  const int t = threadIdx.x;
+  {
+    uint32_t c = (uint32_t)t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ kCrcPoly : c >> 1;
+    table[t] = c;
+  }
+  __syncthreads();
+  const int64_t img = blockIdx.x;
+  const uint8_t* p = payload + img * capacity;
+  const int64_t len = lengths[img];
+  const int64_t total = (len < 0 ? 0 : len > capacity ? capacity : len) + 4;       // "IDAT" + stream (never past the image's slot)
+  int64_t R = (total + kCrcBlock - 1) / kCrcBlock;
+  R = (R + 3) & ~(int64_t)3;
+  if (R < 4) R = 4;
+  const int64_t lo = total - (int64_t)(kCrcBlock - t) * R, hi = lo + R;
+  uint32_t c = 0;
+  for (int64_t j = lo < 0 ? 0 : lo; j < hi; ++j) {
+    const uint32_t byte = j < 4 ? (uint32_t)("IDAT"[j]) : (uint32_t)__ldg(p + (j - 4));
+    c = table[(c ^ byte) & 0xffu] ^ (c >> 8);
+  }
+  part[t] = c;
+  uint32_t op = crc_x8n((uint64_t)R);
+  for (int n = kCrcBlock / 2; n >= 1; n >>= 1) {
+    __syncthreads();
+    uint32_t v = 0;
+    if (t < n) v = crc_multmodp(op, part[2 * t]) ^ part[2 * t + 1];
+    __syncthreads();
+    if (t < n) part[t] = v;
+    op = crc_multmodp(op, op);
+  }
+  if (t == 0) crc_out[img] = part[0] ^ crc_multmodp(crc_x8n((uint64_t)total), 0xffffffffu) ^ 0xffffffffu;
+}
+
+}  // namespace diga
+
+extern "C" int diga_png_crc(const uint8_t* payload, int64_t n, int64_t capacity, const int64_t* lengths, uint32_t* crc_out,
+                            diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(payload && lengths && crc_out, DIGA_ERR_INVALID, "png_crc: null pointer");
+  DIGA_REQUIRE(n >= 0 && n <= 65535 && capacity >= 1, DIGA_ERR_INVALID, "png_crc: bad sizes");
+  DIGA_REQUIRE(aligned(lengths, 8) && aligned(crc_out, 4), DIGA_ERR_MISALIGNED, "png_crc: misaligned pointer");
+  if (n == 0) return DIGA_OK;
+  png_crc_kernel<<<(unsigned)n, kCrcBlock, 0, (cudaStream_t)stream>>>(payload, capacity, lengths, crc_out);
+  DIGA_CHECK_LAUNCH("png_crc_kernel");
+  return DIGA_OK;
+}
+
+static int png_write_file_impl(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                               const uint8_t* palette_host, int64_t palette_bytes, const uint32_t* idat_crc);
+
 extern "C" int diga_png_write_file(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
                                    const uint8_t* palette_host, int64_t palette_bytes) {
+  return png_write_file_impl(path, payload_host, length, H, W, palette_host, palette_bytes, nullptr);
+}
+
+extern "C" int diga_png_write_file_crc(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                                       const uint8_t* palette_host, int64_t palette_bytes, uint32_t idat_crc) {
+  return png_write_file_impl(path, payload_host, length, H, W, palette_host, palette_bytes, &idat_crc);
+}
+
+static int png_write_file_impl(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                               const uint8_t* palette_host, int64_t palette_bytes, const uint32_t* idat_crc) {
   using namespace diga;
   DIGA_REQUIRE(path && payload_host && palette_host, DIGA_ERR_INVALID, "png_write_file: null pointer");
   DIGA_REQUIRE(length > 6 && length < (int64_t(1) << 31) && H >= 1 && W >= 1 && H < (int64_t(1) << 31) && W < (int64_t(1) << 31),
@@ -387,8 +498,8 @@ extern "C" int diga_png_write_file(const char* path, const uint8_t* payload_host
   ihdr[9] = 3;   // colour type: palette
   ihdr[10] = ihdr[11] = ihdr[12] = 0;
   bool ok = fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr, 13) &&
-            write_chunk(f, "PLTE", palette_host, (size_t)palette_bytes) && write_chunk(f, "IDAT", payload_host, (size_t)length) &&
-            write_chunk(f, "IEND", nullptr, 0);
+            write_chunk(f, "PLTE", palette_host, (size_t)palette_bytes) &&
+            write_chunk(f, "IDAT", payload_host, (size_t)length, idat_crc) && write_chunk(f, "IEND", nullptr, 0);
   ok = (fclose(f) == 0) && ok;
   if (!ok) {
     set_error("png_write_file: short write to %s: %s", path, strerror(errno));

@@ -124,6 +124,19 @@ def png_deflate(label_u8):
     return payload, lengths
 
 
+@L.on_device
+def png_crc(payload, lengths):
+    """CRC-32 of every image's IDAT chunk (``b"IDAT" + payload[i, :lengths[i]]``) computed on the GPU: ``uint32 [N]`` (stored in
+    an int64 tensor so that it copies out with the lengths).  ``payload`` / ``lengths`` as :func:`png_deflate` returns them."""
+    L.require_cuda(payload, lengths, what="png_crc input")
+    if payload.dtype != torch.uint8 or payload.dim() != 2 or lengths.dtype != torch.int64 or lengths.shape != (payload.shape[0],):
+        raise ValueError("png_crc: expected the (payload uint8 [N,capacity], lengths int64 [N]) pair of png_deflate")
+    n, cap = payload.shape
+    tmp = torch.empty((n,), dtype=torch.int32, device=payload.device)
+    L.check(L.lib.diga_png_crc(payload.data_ptr(), n, cap, lengths.data_ptr(), tmp.data_ptr(), L.stream()))
+    return tmp.to(torch.int64) & 0xFFFFFFFF
+
+
 class PseudoLabelWriter:
     """Streams label maps from the GPU to palette PNGs (next row f3; replaces pseudolabel_generator.py:66,89-105).
 
@@ -213,31 +226,33 @@ class PseudoLabelWriter:
         else:
             n, h, w = label_u8.shape
             payload, lengths = png_deflate(label_u8)
+            meta = torch.stack((lengths, png_crc(payload, lengths)))        # [2, n]: stream lengths and IDAT CRC-32s (both made on the GPU)
             pre = min(self.prefix, payload.shape[1])
             if slot is not None and slot[0][0].shape == (n, pre):
                 buf, lens = slot[0]
             else:
-                buf, lens = torch.empty((n, pre), dtype=torch.uint8).pin_memory(), torch.empty((n,), dtype=torch.int64).pin_memory()
+                buf, lens = torch.empty((n, pre), dtype=torch.uint8).pin_memory(), torch.empty((2, n), dtype=torch.int64).pin_memory()
             self._copy_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._copy_stream):
-                lens.copy_(lengths, non_blocking=True)
+                lens.copy_(meta, non_blocking=True)
                 buf.copy_(payload[:, :pre], non_blocking=True)
                 ev.record(self._copy_stream)
-            self.bytes_d2h += n * (pre + 8)
+            self.bytes_d2h += n * (pre + 16)
 
             base = buf.data_ptr()
 
             def job(k, name):
                 ev.synchronize()
-                m = int(lens[k])
+                m, crc = int(lens[0, k]), int(lens[1, k])
                 if m <= pre:
                     ptr, host = base + k * pre, None
                 else:                                        # a noise-like map: fetch the whole stream
                     with torch.cuda.stream(self._copy_stream):
                         host = payload[k, :m].cpu()
                     ptr = host.data_ptr()
-                # framing (CRC-32) and the file write happen inside the library, i.e. without the interpreter lock
-                L.check(L.lib.diga_png_write_file(os.fsencode(self._path(name)), ptr, m, h, w, _PALETTE_BYTES, len(_PALETTE_BYTES)))
+                # framing and the file write happen inside the library, i.e. without the interpreter lock; the IDAT CRC-32 came with
+                # the stream, so the host thread touches the payload only to hand it to write()
+                L.check(L.lib.diga_png_write_file_crc(os.fsencode(self._path(name)), ptr, m, h, w, _PALETTE_BYTES, len(_PALETTE_BYTES), crc))
 
             keep, pinned = (payload, lengths, label_u8), (buf, lens)
         futures = [self._pool.submit(job, k, nm) for k, nm in enumerate(names)]

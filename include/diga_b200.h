@@ -358,6 +358,12 @@ int diga_png_deflate(const uint8_t* labels, int64_t n, int64_t H, int64_t W, uin
  * and write it to `path`.  No CUDA call; safe to call from several host threads at once. */
 int diga_png_write_file(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
                         const uint8_t* palette_host, int64_t palette_bytes);
+/* CRC-32 of every image's IDAT chunk ("IDAT" + payload[i, :lengths[i]]) on the GPU (tree combination of 256 partial remainders
+ * per image), and the host writer that takes it: the host threads then only frame and write bytes. */
+int diga_png_crc(const uint8_t* payload, int64_t n, int64_t capacity, const int64_t* lengths, uint32_t* crc_out,
+                 diga_stream_t stream);
+int diga_png_write_file_crc(const char* path, const uint8_t* payload_host, int64_t length, int64_t H, int64_t W,
+                            const uint8_t* palette_host, int64_t palette_bytes, uint32_t idat_crc);
 
 #ifdef __cplusplus
 }

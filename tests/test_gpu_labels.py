@@ -157,3 +157,36 @@ def test_png_deflate_random_shapes_vs_oracle():
         payload, lengths = payload.cpu().numpy(), lengths.cpu().numpy()
         for i in range(n):
             assert payload[i, :lengths[i]].tobytes() == P.deflate_stream(lab[i]), (n, h, w, i)
+
+
+@pytest.mark.parametrize("name", ["blocks_odd", "constant", "noise", "one_pixel", "run_258_edges", "many_rows"])
+def test_png_idat_crc_on_gpu_equals_zlib(name):
+    """png_crc (csrc/png.cu png_crc_kernel: 256 ranges per image combined with the zlib x^n mod P operator) against
+    zlib.crc32 over the chunk type and the stream, for streams from a few bytes to tens of kilobytes."""
+    import zlib
+    from diga_b200.pseudolabel import png_crc, png_deflate
+    lab = _png_patterns()[name]
+    payload, lengths = png_deflate(torch.from_numpy(lab).to(DEV))
+    crc = png_crc(payload, lengths).cpu().numpy()
+    payload, lengths = payload.cpu().numpy(), lengths.cpu().numpy()
+    for i in range(lab.shape[0]):
+        assert int(crc[i]) == zlib.crc32(b"IDAT" + payload[i, :lengths[i]].tobytes()), f"{name}[{i}]"
+
+
+def test_png_idat_crc_arbitrary_bytes_and_lengths():
+    """The CRC kernel on random bytes for every length class (0, shorter than the 256 ranges, not a multiple of them, MiB-sized)."""
+    import zlib
+    from diga_b200.pseudolabel import png_crc
+    g = torch.Generator(device=DEV).manual_seed(3)
+    cap = (1 << 20) + 77
+    lens = [0, 1, 3, 4, 5, 255, 256, 257, 1023, 4096, 65537, 300001, cap]
+    payload = torch.randint(0, 256, (len(lens), cap), generator=g, device=DEV, dtype=torch.uint8)
+    lengths = torch.tensor(lens, device=DEV, dtype=torch.int64)
+    crc = png_crc(payload, lengths).cpu().numpy()
+    host = payload.cpu().numpy()
+    for i, m in enumerate(lens):
+        assert int(crc[i]) == zlib.crc32(b"IDAT" + host[i, :m].tobytes()), m
+    with pytest.raises(ValueError):
+        png_crc(payload, lengths[:3])
+    with pytest.raises(RuntimeError):
+        png_crc(payload.cpu(), lengths.cpu())
