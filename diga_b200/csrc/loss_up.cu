@@ -36,6 +36,7 @@ struct LossUpPlan {
   int64_t ctas;
   size_t off_partial, off_scratch, bytes;
 };
+constexpr size_t kLuTileMax = 64 * 1024;   // largest source tile a CTA stages in shared memory (else it reads global memory)
 
 // The tap arithmetic of bilinear_tap() on the host (IEEE single multiply + truncation: identical results).
 static inline void host_tap(float scale, int dst, int in, int* i0, int* i1) {
@@ -92,6 +93,7 @@ struct LossUpArgs {
   const float* sel_thr;    // OHEM: device scalar, a pixel is kept iff 0 <= sel_pred < sel_thr[0]
   int ignore_label;        // OHEM: target value that is masked out (CE: 255 is >= nclass anyway)
   int ry, R, K;
+  int tile;                // 1: the CTA stages its source rows [views][R][nclass][K + 1] in shared memory (cp.async) first
   float* scratch;
   double* partial;
   unsigned int* ticket;
@@ -108,16 +110,36 @@ __device__ __forceinline__ int lu_swz(int x) { return x + (x >> 3); }
 #ifndef LU_MINB_GRAD
 #define LU_MINB_GRAD 2      // ... and the gradient kernels (up to 255 registers: Gt/Gb and the two exp arrays stay in registers)
 #endif
+// Dynamic shared memory of the kernel: the strip's vertical taps, then (CE only) the per-column class tables
+//   tabT / tabD [C][128]: the student's (top, dif) of the current cell, so that the target-class logit of a pixel is two
+//                         shared loads + one FFMA instead of C compares and selects;
+//   oh [2][C][128]      : (gradient only) the one-hot term of the CE gradient, accumulated per source-row parity; it is
+//                         subtracted from the class gradients when the row is flushed.
+// Every thread touches its own column only: no barriers.
+__host__ __device__ static inline size_t lu_tab_offset(int ry) { return ((size_t)ry * sizeof(int2) + 15) & ~(size_t)15; }
+__host__ __device__ static inline size_t lu_tile_bytes(int views, int R, int nclass, int K) {
+  return ((size_t)views * R * nclass * (K + 1) * sizeof(float) + 15) & ~(size_t)15;
+}
+static inline size_t lu_dyn_bytes(int ry, int ctemplate, bool ce, bool grad, size_t tile_bytes) {
+  return lu_tab_offset(ry) + tile_bytes + (ce ? (size_t)(grad ? 4 : 2) * ctemplate * kLuBlock * sizeof(float) : 0);
+}
+__device__ __forceinline__ void lu_cp_async4(float* dst_shared, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+}
+
 template <int C, bool PAD, bool KD, bool CE, bool LOSS, bool GRAD>
 __global__ void __launch_bounds__(kLuBlock, GRAD ? LU_MINB_GRAD : LU_MINB_LOSS)
 loss_up_kernel(const LossUpArgs a) {
-  extern __shared__ __align__(16) int2 ytab[];             // per-row vertical taps of the strip
+  extern __shared__ __align__(16) unsigned char lu_dyn[];
+  int2* ytab = reinterpret_cast<int2*>(lu_dyn);            // per-row vertical taps of the strip
   const int n = blockIdx.z, ky = blockIdx.y, kx = blockIdx.x, tid = threadIdx.x;
   const int X0 = kx * kLuBlock, X = X0 + tid;
   const bool in_range = X < a.W;
   const int Y0 = ky * a.ry, Yend = min(Y0 + a.ry, a.H);
   const int64_t plane = (int64_t)a.h * a.w;
   const int nclass = a.nclass;
+  using Col = LerpColumn2<C, PAD>;
+  constexpr int P = Col::P;
   const Tap tx = bilinear_tap(a.sw, in_range ? X : a.W - 1, a.w);
   // Horizontal tap as the column pair (kc, kc + 1): a lane clamped at the last source column (i1 == i0) reads the pair
   // (i0 - 1, i0) with weights (0, l0 + l1) so that the second load is always "first + 1" (a 1-column source has no pair).
@@ -134,6 +156,11 @@ loss_up_kernel(const LossUpArgs a) {
   }
   const bool ce_img = CE && n < a.n_ce;
   const int64_t* trow = ce_img ? a.target + ((int64_t)n * a.H) * a.W + (in_range ? X : a.W - 1) : nullptr;
+  float* tile = reinterpret_cast<float*>(lu_dyn + lu_tab_offset(a.ry));
+  const size_t tile_bytes = a.tile ? lu_tile_bytes(KD ? 2 : 1, a.R, nclass, a.K) : 0;
+  float* tabT = reinterpret_cast<float*>(lu_dyn + lu_tab_offset(a.ry) + tile_bytes) + tid;   // this thread's column of [C][128]
+  float* tabD = tabT + C * kLuBlock;
+  float* oh = tabD + C * kLuBlock;                                                 // [2][C][128], GRAD only
 
   float ckd = 0.f, cce = 0.f;
   if constexpr (GRAD) {
@@ -152,11 +179,49 @@ loss_up_kernel(const LossUpArgs a) {
   const int ylo = bilinear_tap(a.sh, Y0, a.h).i0;
   const float* scol = a.stu + (int64_t)n * nclass * plane + (int64_t)ylo * a.w + kc;   // (row ylo, class 0, column kc)
   const float* tcol = KD ? tbase + (int64_t)ylo * a.w + kc : nullptr;
+  // The strip's source rows, both views, go to shared memory with ONE round of asynchronous copies (`a.tile`; geometries
+  // whose tile would not fit keep reading global memory): a cell crossing then costs shared-memory latency instead of two
+  // dependent trips to L2 / DRAM — every source row is first touched by the CTAs that interpolate from it.
+  // Layout: segment = (view, row, class) in that order, K + 1 columns each, first column = kc of the CTA's first thread.
+  const Tap t0 = bilinear_tap(a.sw, X0, a.w);
+  const int xbase = (t0.i1 == t0.i0 && pair) ? t0.i0 - 1 : t0.i0;
+  const int Kp = a.K + 1;
+  const int Rn = bilinear_tap(a.sh, Yend - 1, a.h).i1 - ylo + 1;
+  if (a.tile) {
+    const int ncols = min(Kp, a.w - xbase);
+    const int segs = (KD ? 2 : 1) * Rn * nclass;
+    int seg = tid / ncols, col = tid - seg * ncols;
+    const int dseg = kLuBlock / ncols, dcol = kLuBlock - dseg * ncols;
+    int c = seg, r = 0, view = 0;                            // decode of `seg`, advanced incrementally
+    while (seg < segs) {
+      while (c >= nclass) {
+        c -= nclass;
+        if (++r == Rn) r = 0, ++view;
+      }
+      const float* src = (view ? tcol : scol) - kc + xbase + (int64_t)c * plane + (int64_t)r * a.w + col;
+      lu_cp_async4(tile + seg * Kp + col, src);
+      col += dcol;
+      const int wrap = col >= ncols;
+      col -= wrap ? ncols : 0;
+      seg += dseg + wrap;
+      c += dseg + wrap;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float* stile = tile + (kc - xbase);                // (row 0, class 0, column kc) of the student view
+  const float* ttile = stile + Rn * nclass * Kp;
+  const int tile_row = nclass * Kp;
 
   // per-row vertical taps, computed once per CTA: {local row of i0 | (i1 - i0) << 16, l1}
   for (int i = tid; i < Yend - Y0; i += kLuBlock) {
     const Tap t = bilinear_tap(a.sh, Y0 + i, a.h);
     ytab[i] = make_int2((t.i0 - ylo) | ((t.i1 - t.i0) << 16), __float_as_int(t.l1));
+  }
+  if constexpr (CE && GRAD) {
+    if (ce_img) {
+#pragma unroll
+      for (int c = 0; c < 2 * C; ++c) oh[c * kLuBlock] = 0.f;
+    }
   }
 
   // ---- backward staging (shared memory): [column (swizzled)][class], classes padded to a multiple of four ----------
@@ -168,6 +233,7 @@ loss_up_kernel(const LossUpArgs a) {
   if constexpr (GRAD) {
     for (int i = tid; i <= Kt; i += kLuBlock) st[i] = nvalid;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   if constexpr (GRAD) {
     if (in_range) {
@@ -176,33 +242,45 @@ loss_up_kernel(const LossUpArgs a) {
     }
     __syncthreads();
   }
-  float Gt[GRAD ? C : 1], Gb[GRAD ? C : 1];
+  float2 Gt[GRAD ? P : 1], Gb[GRAD ? P : 1];
   if constexpr (GRAD) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) Gt[c] = Gb[c] = 0.f;
+    for (int p = 0; p < P; ++p) Gt[p] = Gb[p] = make_float2(0.f, 0.f);
   }
   // flush: horizontal half of the transposed interpolation for one completed source row.  Every column stages
   // l0*G (-> source column i0) and l1*G (-> i0 + 1) as float4 class quads; a work item (source column, class quad) sums
   // the contiguous run of output columns that map to it and stores one float4 of the CTA's patch [row][column][CP].
-  auto flush = [&](const float (&G)[GRAD ? C : 1], int row) {
+  auto flush = [&](const float2 (&G)[GRAD ? P : 1], int row) {
     if constexpr (GRAD) {
       const int sx = lu_swz(tid);
-      const float wa = in_range ? (clamped ? tx.l0 + tx.l1 : tx.l0) : 0.f;
-      const float wb = (in_range && !clamped) ? tx.l1 : 0.f;
+      const float2 wa = splat2(in_range ? (clamped ? tx.l0 + tx.l1 : tx.l0) : 0.f);
+      const float2 wb = splat2((in_range && !clamped) ? tx.l1 : 0.f);
+      float* ohs = oh + (row & 1) * (C * kLuBlock);        // the row's one-hot accumulator (CE images)
 #pragma unroll
       for (int q = 0; q < CQ; ++q) {
-        float4 va, vb;
-        float* pa = reinterpret_cast<float*>(&va);
-        float* pb = reinterpret_cast<float*>(&vb);
+        float2 g[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 4 * q + k;
-          const float gv = (c < C && (!PAD || c < nclass)) ? G[c < C ? c : 0] : 0.f;
-          pa[k] = wa * gv;
-          pb[k] = wb * gv;
+        for (int k = 0; k < 2; ++k) {
+          const int p = 2 * q + k;
+          g[k] = p < P ? G[p < P ? p : 0] : make_float2(0.f, 0.f);
+          if (!Col::on(2 * p, nclass)) g[k].x = 0.f;
+          if (!Col::on(2 * p + 1, nclass)) g[k].y = 0.f;
+          if constexpr (CE) {
+            if (ce_img) {
+              if (Col::on(2 * p, nclass)) {
+                g[k].x -= ohs[(2 * p) * kLuBlock];
+                ohs[(2 * p) * kLuBlock] = 0.f;
+              }
+              if (Col::on(2 * p + 1, nclass)) {
+                g[k].y -= ohs[(2 * p + 1) * kLuBlock];
+                ohs[(2 * p + 1) * kLuBlock] = 0.f;
+              }
+            }
+          }
         }
-        *reinterpret_cast<float4*>(&sa[sx][4 * q]) = va;
-        *reinterpret_cast<float4*>(&sb[sx][4 * q]) = vb;
+        const float2 a0 = fmul2(wa, g[0]), a1 = fmul2(wa, g[1]), b0 = fmul2(wb, g[0]), b1 = fmul2(wb, g[1]);
+        *reinterpret_cast<float4*>(&sa[sx][4 * q]) = make_float4(a0.x, a0.y, a1.x, a1.y);
+        *reinterpret_cast<float4*>(&sb[sx][4 * q]) = make_float4(b0.x, b0.y, b1.x, b1.y);
       }
       __syncthreads();
       float4* dst = reinterpret_cast<float4*>(a.scratch + ((cta * a.R + row) * a.K) * CP);
@@ -224,83 +302,108 @@ loss_up_kernel(const LossUpArgs a) {
     }
   };
 
-  LerpColumn<C, PAD> cs;
-  LerpColumn<KD ? C : 1, PAD> ct;
+  Col cs;
+  LerpColumn2<KD ? C : 1, PAD> ct;
   float acc_kd = 0.f, acc_ce = 0.f, acc_cnt = 0.f;
   int cur_r0 = -1, cur_r1 = -1;
   int64_t tgt = 0, tgt_next = 0;
   if (ce_img) tgt = ld_stream_i64(trow + (int64_t)Y0 * a.W);
 
+  int2 yt_next = ytab[0];
   for (int Y = Y0; Y < Yend; ++Y) {
     if (ce_img && Y + 1 < Yend) tgt_next = ld_stream_i64(trow + (int64_t)(Y + 1) * a.W);
-    const int t32 = (CE && tgt >= 0 && tgt < nclass) ? (int)tgt : -1;     // class index of a supervised pixel, else -1
-    const int2 yt = ytab[Y - Y0];
+    const int2 yt = yt_next;
+    yt_next = ytab[min(Y + 1, Yend - 1) - Y0];               // one row ahead: the tap is not on the row's critical path
     const int r0 = yt.x & 0xffff, r1 = r0 + (yt.x >> 16);
     const float yl1 = __int_as_float(yt.y), yl0 = 1.0f - yl1;
+    const float2 yl1v = splat2(yl1);
     if (r0 != cur_r0) {                                      // first row, or crossed into the next source cell (CTA-uniform)
       if constexpr (GRAD) {
         if (cur_r0 >= 0) {
           flush(Gt, cur_r0);                                 // source row cur_r0 is complete for this strip
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            Gt[c] = Gb[c];
-            Gb[c] = 0.f;
+          for (int p = 0; p < P; ++p) {
+            Gt[p] = Gb[p];
+            Gb[p] = make_float2(0.f, 0.f);
           }
         }
       }
-      cs.enter(cur_r0 < 0, scol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
-      if constexpr (KD) ct.enter(cur_r0 < 0, tcol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+      if (a.tile) {
+        cs.enter(cur_r0 < 0, stile, tile_row, Kp, r0, r1, pair, l0s, l1s, nclass);
+        if constexpr (KD) ct.enter(cur_r0 < 0, ttile, tile_row, Kp, r0, r1, pair, l0s, l1s, nclass);
+      } else {
+        cs.enter(cur_r0 < 0, scol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+        if constexpr (KD) ct.enter(cur_r0 < 0, tcol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+      }
+      if constexpr (CE) {
+        if (ce_img) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            if (Col::on(2 * p, nclass)) tabT[(2 * p) * kLuBlock] = cs.top[p].x, tabD[(2 * p) * kLuBlock] = cs.dif[p].x;
+            if (Col::on(2 * p + 1, nclass)) tabT[(2 * p + 1) * kLuBlock] = cs.top[p].y, tabD[(2 * p + 1) * kLuBlock] = cs.dif[p].y;
+          }
+        }
+      }
       cur_r0 = r0;
       cur_r1 = r1;
     }
 
     // Per-pixel statistics in the log2 domain, relative to the cell reference (see LerpColumn):
-    //   es_c = 2^v_c, Ss = sum es_c, (KD) e_c = 2^u_c, St = sum e_c, cross2 = sum e_c v_c.
-    // Sums run as four interleaved chains.  EXACT re-bases on the per-pixel max (taken only after an underflow).
-    // In the seg + KD kernels only the first n_ce images carry targets: the per-class target compares / selects (76
-    // instructions per pixel) are compiled out of the body the other images run (`ce_img` is CTA-uniform).
-    auto pixel = [&](auto ce_tag) {
-    constexpr bool CEP = CE && decltype(ce_tag)::value;
-    float es[GRAD ? C : 1], et[(GRAD && KD) ? C : 1];
-    float Ss = 0.f, St = 0.f, cross2 = 0.f, dtgt = 0.f;
+    //   es_c = 2^v_c, Ss = sum es_c, (KD) e_c = 2^u_c, St = sum e_c, cross2 = sum e_c v_c,
+    // on class pairs (FFMA2 / FADD2), two interleaved chains of pairs.  EXACT re-bases on the per-pixel max (taken only
+    // after an underflow).
+    float2 es[GRAD ? P : 1], et[(GRAD && KD) ? P : 1];
+    float Ss = 0.f, St = 0.f, cross2 = 0.f, ms = 0.f;
     auto stats = [&](auto exact_tag) {
       constexpr bool EXACT = decltype(exact_tag)::value;
-      float ms = 0.f, mt = 0.f;
+      float mt = 0.f;
       if constexpr (EXACT) {
         ms = mt = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-          if (!PAD || c < nclass) {
-            ms = fmaxf(ms, cs.value(yl1, c));
-            if constexpr (KD) mt = fmaxf(mt, ct.value(yl1, c));
-          }
-      }
-      float Ss4[4] = {0.f, 0.f, 0.f, 0.f};
-      [[maybe_unused]] float St4[4] = {0.f, 0.f, 0.f, 0.f}, cr4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-        if (!PAD || c < nclass) {
-          float v = cs.value(yl1, c);
-          if constexpr (EXACT) v -= ms;
-          const float e_s = fast_ex2(v);
-          Ss4[c & 3] += e_s;
+        for (int p = 0; p < P; ++p) {
+          const float2 v = cs.value2(yl1v, p);
+          if (Col::on(2 * p, nclass)) ms = fmaxf(ms, v.x);
+          if (Col::on(2 * p + 1, nclass)) ms = fmaxf(ms, v.y);
           if constexpr (KD) {
-            float u = ct.value(yl1, c);
-            if constexpr (EXACT) u -= mt;
-            const float e_t = fast_ex2(u);
-            St4[c & 3] += e_t;
-            cr4[c & 3] = fmaf(e_t, v, cr4[c & 3]);
-            if constexpr (GRAD) et[c] = e_t;
+            const float2 u = ct.value2(yl1v, p);
+            if (Col::on(2 * p, nclass)) mt = fmaxf(mt, u.x);
+            if (Col::on(2 * p + 1, nclass)) mt = fmaxf(mt, u.y);
           }
-          if constexpr (CEP) {
-            if (t32 == c) dtgt = v;
-          }
-          if constexpr (GRAD) es[c] = e_s;
         }
-      Ss = (Ss4[0] + Ss4[1]) + (Ss4[2] + Ss4[3]);
+      }
+      const float2 nms = splat2(-ms), nmt = splat2(-mt);
+      float2 S2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      [[maybe_unused]] float2 T2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      [[maybe_unused]] float2 X2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float2 e_s = make_float2(0.f, 0.f), e_t = make_float2(0.f, 0.f);
+        if (Col::on(2 * p, nclass)) {
+          float2 v = cs.value2(yl1v, p);
+          if constexpr (EXACT) v = fadd2(v, nms);
+          e_s.x = fast_ex2(v.x);
+          if (Col::on(2 * p + 1, nclass)) e_s.y = fast_ex2(v.y);
+          S2[p & 1] = fadd2(S2[p & 1], e_s);
+          if constexpr (KD) {
+            float2 u = ct.value2(yl1v, p);
+            if constexpr (EXACT) u = fadd2(u, nmt);
+            e_t.x = fast_ex2(u.x);
+            if (Col::on(2 * p + 1, nclass)) e_t.y = fast_ex2(u.y);
+            T2[p & 1] = fadd2(T2[p & 1], e_t);
+            X2[p & 1] = ffma2(e_t, v, X2[p & 1]);
+          }
+        }
+        if constexpr (GRAD) {
+          es[p] = e_s;
+          if constexpr (KD) et[p] = e_t;
+        }
+      }
+      const float2 s = fadd2(S2[0], S2[1]);
+      Ss = s.x + s.y;
       if constexpr (KD) {
-        St = (St4[0] + St4[1]) + (St4[2] + St4[3]);
-        cross2 = (cr4[0] + cr4[1]) + (cr4[2] + cr4[3]);
+        const float2 t = fadd2(T2[0], T2[1]), x = fadd2(X2[0], X2[1]);
+        St = t.x + t.y;
+        cross2 = x.x + x.y;
       }
     };
     stats(std::false_type{});
@@ -308,47 +411,53 @@ loss_up_kernel(const LossUpArgs a) {
 
     float inv_t = 0.f;
     if constexpr (KD) inv_t = fast_rcp(St);
-    float wt = 1.f;
+    float wt = 1.f, dtgt = 0.f;
     bool counted = false, valid = false;
-    if constexpr (CEP) {
-      counted = ce_img && in_range && tgt >= 0;                     // loss.py:56  mask = target >= 0
-      valid = counted && tgt < nclass && tgt != a.ignore_label;     // 255 (any id >= C) is ignored by nll_loss
-      if (ohem && valid) {                                          // OhemCrossEntropy keeps the hard pixels only
-        const float pv = __ldg(prow + (int64_t)Y * a.W);
-        valid = pv >= 0.f && pv < sel_thr;
+    if constexpr (CE) {
+      if (ce_img) {
+        counted = in_range && tgt >= 0;                               // loss.py:56  mask = target >= 0
+        valid = counted && tgt < nclass && tgt != a.ignore_label;     // 255 (any id >= C) is ignored by nll_loss
+        if (ohem && valid) {                                          // OhemCrossEntropy keeps the hard pixels only
+          const float pv = __ldg(prow + (int64_t)Y * a.W);
+          valid = pv >= 0.f && pv < sel_thr;
+        }
+        if (valid) {
+          if (a.weight != nullptr) wt = __ldg(a.weight + tgt);
+          const int o = (int)tgt * kLuBlock;
+          dtgt = fmaf(yl1, tabD[o], tabT[o]) - ms;                    // the target class's logit, same frame as the sums
+        }
       }
-      if (valid && a.weight != nullptr) wt = __ldg(a.weight + tgt);
     }
     if constexpr (LOSS) {                                            // accumulated in log2 units (x ln 2 at the end)
       const float lse2 = fast_lg2(Ss);
       if constexpr (KD) {
         if (in_range) acc_kd += wkd * (lse2 - cross2 * inv_t);
       }
-      if constexpr (CEP) {
+      if constexpr (CE) {
         if (valid) acc_ce += wt * (lse2 - dtgt);
         if (counted) acc_cnt += 1.f;
       }
     }
     if constexpr (GRAD) {
-      const float cpx = (CEP && valid) ? wt * cce : 0.f;
-      const float ga = (ckd + cpx) * fast_rcp(Ss);
-      const float gb = ckd * inv_t;
+      const float cpx = (CE && valid) ? wt * cce : 0.f;
+      const float2 ga = splat2((ckd + cpx) * fast_rcp(Ss)), ngb = splat2(-(ckd * inv_t));
+      const float2 yl0v = splat2(yl0);
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        if (!PAD || c < nclass) {
-          float g = ga * es[c];
-          if constexpr (KD) g = fmaf(-gb, et[c], g);
-          if constexpr (CEP) g -= (t32 == c) ? cpx : 0.f;
-          Gt[c] = fmaf(yl0, g, Gt[c]);
-          Gb[c] = fmaf(yl1, g, Gb[c]);
+      for (int p = 0; p < P; ++p)
+        if (Col::on(2 * p, nclass)) {
+          float2 g = fmul2(ga, es[p]);
+          if constexpr (KD) g = ffma2(ngb, et[p], g);
+          Gt[p] = ffma2(yl0v, g, Gt[p]);
+          Gb[p] = ffma2(yl1v, g, Gb[p]);
         }
-    }
-    };
-    if constexpr (CE && KD) {
-      if (ce_img) pixel(std::true_type{});
-      else pixel(std::false_type{});
-    } else {
-      pixel(std::integral_constant<bool, CE>{});
+      if constexpr (CE) {
+        if (valid) {                                                 // one-hot term, per source-row parity (see flush)
+          float* o0 = oh + ((r0 & 1) * C + (int)tgt) * kLuBlock;
+          *o0 += yl0 * cpx;
+          float* o1 = oh + ((r1 & 1) * C + (int)tgt) * kLuBlock;
+          *o1 += yl1 * cpx;
+        }
+      }
     }
     tgt = tgt_next;
   }
@@ -356,7 +465,7 @@ loss_up_kernel(const LossUpArgs a) {
   if constexpr (GRAD) {
     if (cur_r1 == cur_r0) {                                  // clamped at the last source row: both taps hit it
 #pragma unroll
-      for (int c = 0; c < C; ++c) Gt[c] += Gb[c];
+      for (int p = 0; p < P; ++p) Gt[p] = fadd2(Gt[p], Gb[p]);
       flush(Gt, cur_r0);
     } else {
       flush(Gt, cur_r0);
@@ -534,10 +643,23 @@ static int check_common(const char* who, const float* stu, int64_t n, int64_t C,
 template <bool KD, bool CE, bool LOSS, bool GRAD>
 static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* dlow, cudaStream_t st) {
   dim3 grid((unsigned)p.SX, (unsigned)p.SY, (unsigned)a.n);
-  const size_t tab_bytes = (size_t)p.ry * sizeof(int2);
-  DIGA_REQUIRE(tab_bytes <= 32 * 1024, DIGA_ERR_INVALID, "loss_up: strip height %d too large", p.ry);
+  DIGA_REQUIRE((size_t)p.ry * sizeof(int2) <= 32 * 1024, DIGA_ERR_INVALID, "loss_up: strip height %d too large", p.ry);
+  const size_t tile_bytes = lu_tile_bytes(KD ? 2 : 1, p.R, (int)C, p.K);
+  a.tile = tile_bytes <= kLuTileMax && tunable("lossup_tile", 1) != 0;
   DIGA_DISPATCH_C(C, {
-    loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD><<<grid, kLuBlock, tab_bytes, st>>>(a);
+    const size_t dyn = lu_dyn_bytes(p.ry, kC, CE, GRAD, a.tile ? tile_bytes : 0);
+    auto kernel = loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD>;
+    static size_t configured_dev[64] = {0};            // per instantiation and device
+    size_t& configured = configured_dev[device_slot()];
+    if (dyn > 16 * 1024 && configured < dyn) {           // static staging + dynamic tables can pass the 48 KB default
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("loss_up: cannot reserve %zu bytes of shared memory", dyn);
+        return DIGA_ERR_CUDA;
+      }
+      configured = dyn;
+    }
+    kernel<<<grid, kLuBlock, dyn, st>>>(a);
     DIGA_CHECK_LAUNCH("loss_up_kernel");
     if (GRAD) {
       const float inv_sh_ry = a.sh > 0.f ? 1.0f / (a.sh * (float)p.ry) : 0.f;

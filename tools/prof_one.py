@@ -68,6 +68,25 @@ elif which == "presence":
     sl = S.block_labels(8, 512, 1024, g)
     for _ in range(3):
         present_classes(sl)
+elif which == "lossup3":                     # config 3's two loss launches: seg + KD on [16,...] (8 supervised), CE on [8,...]
+    tea, stu, cpm = S.logits((16, 19, 65, 129), g), S.logits((16, 19, 65, 129), g), S.logits((8, 19, 65, 129), g)
+    sl, ml = S.block_labels(8, 512, 1024, g), S.block_labels(8, 512, 1024, g)
+    for _ in range(3):
+        s, c2 = stu.detach().requires_grad_(True), cpm.detach().requires_grad_(True)
+        part, l_src, l_kd = D.seg_distillation_total_upsampled(tea, s, sl, 1.0, 0.25, 0.5)
+        total = part + D.cross_entropy2d_upsampled(c2, ml)
+        torch.autograd.grad(total, [s, c2])
+    torch.cuda.synchronize()
+    if len(sys.argv) > 2:                    # event timing of the pair (outside ncu)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            s, c2 = stu.detach().requires_grad_(True), cpm.detach().requires_grad_(True)
+            part, l_src, l_kd = D.seg_distillation_total_upsampled(tea, s, sl, 1.0, 0.25, 0.5)
+            total = part + D.cross_entropy2d_upsampled(c2, ml)
+            torch.autograd.grad(total, [s, c2])
+        e1.record(); torch.cuda.synchronize()
+        print("lossup3 pair ms", e0.elapsed_time(e1) / 20, float(total))
 elif which == "lossup":
     tea, stu = S.logits((8, 19, 65, 129), g), S.logits((8, 19, 65, 129), g)
     tgt = S.block_labels(4, 512, 1024, g)
