@@ -113,71 +113,76 @@ DIGA_F32X2_2(fmul2, "mul.rn.f32x2")
 #undef DIGA_F32X2_2
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-// LerpColumn on class pairs: pair p holds classes (2p, 2p + 1).  A lane without a class (odd C, or c >= nclass in the
-// padded variant) carries finite don't-care values; the callers force its exponential to zero and skip it in maxima.
-template <int C, bool PAD>
-struct LerpColumn2 {
-  static constexpr int P = (C + 1) / 2;
-  float2 top[P], dif[P];
+// LerpColumn on class pairs (NP pairs = 2 NP class slots per thread).  A slot without a class (odd C, or c >= nclass in
+// the padded variant) is fed kLerpPad from both source rows: its value stays hugely negative (dif == 0 exactly, top
+// absorbs every re-basing), so its exponential is an exact zero and it never wins a maximum — no special case in the
+// per-pixel loops.
+constexpr float kLerpPad = -1e30f;
+
+template <int NP>
+struct LerpColumnP {
+  float2 top[NP], dif[NP];
   float ref2 = 0.f;
 
-  static __device__ __forceinline__ bool on(int c, int nclass) { return c < C && (!PAD || c < nclass); }
-
-  template <bool PAIR>
-  __device__ __forceinline__ void hrow(float2 (&dst)[P], const float* q, int64_t class_stride, float l0s, float l1s,
-                                       float sub, int nclass) {
+  // dst[p] = l0s * v[c][k] + l1s * v[c][k + 1] - sub.
+  // TILE: `q` points at the class vector of source column k in the CTA's shared-memory tile [row][column][2 NP] (absent
+  // classes pre-filled with kLerpPad); the next column is `col_stride` floats on: two 64-bit loads per class pair.
+  __device__ __forceinline__ void hrow_tile(float2 (&dst)[NP], const float* q, int col_stride, float l0s, float l1s, float sub) {
+    const float2 w0 = splat2(l0s), w1 = splat2(l1s), ns = splat2(-sub);
+    const float2* qa = reinterpret_cast<const float2*>(q);
+    const float2* qb = reinterpret_cast<const float2*>(q + col_stride);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) dst[p] = ffma2(w0, qa[p], ffma2(w1, qb[p], ns));
+  }
+  // global memory: `q` points at v[0][k] of the source row, classes `class_stride` apart (an absent class re-reads the last one)
+  __device__ __forceinline__ void hrow_global(float2 (&dst)[NP], const float* __restrict__ q, int64_t class_stride, int second, float l0s,
+                                              float l1s, float sub, int nlimit) {
     const float2 w0 = splat2(l0s), w1 = splat2(l1s), ns = splat2(-sub);
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      float2 va = make_float2(0.f, 0.f), vb = make_float2(0.f, 0.f);
-      if (on(2 * p, nclass)) {                      // plain loads: `q` is the CTA's shared-memory tile or global memory
-        va.x = q[0];
-        vb.x = q[PAIR ? 1 : 0];
-        q += class_stride;
-      }
-      if (on(2 * p + 1, nclass)) {
-        va.y = q[0];
-        vb.y = q[PAIR ? 1 : 0];
-        q += class_stride;
-      }
+    for (int p = 0; p < NP; ++p) {
+      const int c0 = 2 * p, c1 = c0 + 1;
+      const float* q0 = q + (int64_t)min(c0, nlimit - 1) * class_stride;
+      const float* q1 = q + (int64_t)min(c1, nlimit - 1) * class_stride;
+      float2 va = make_float2(__ldg(q0), __ldg(q1)), vb = make_float2(__ldg(q0 + second), __ldg(q1 + second));
+      if (c0 >= nlimit) va.x = vb.x = kLerpPad;
+      if (c1 >= nlimit) va.y = vb.y = kLerpPad;
       dst[p] = ffma2(w0, va, ffma2(w1, vb, ns));
     }
   }
-  __device__ __forceinline__ float rowmax(const float2 (&v)[P], int nclass) {
-    float m0 = v[0].x, m1 = v[0].x, m2 = v[0].x;
+  __device__ __forceinline__ float rowmax(const float2 (&v)[NP]) {
+    float m0 = v[0].x, m1 = v[0].y, m2 = v[0].x;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
+    for (int p = 1; p < NP; ++p) {
       float& m = (p % 3 == 0) ? m0 : (p % 3 == 1) ? m1 : m2;
-      if (on(2 * p + 1, nclass)) m = fmax3(m, v[p].x, v[p].y);
-      else if (on(2 * p, nclass)) m = fmaxf(m, v[p].x);
+      m = fmax3(m, v[p].x, v[p].y);
     }
     return fmax3(m0, m1, m2);
   }
-  __device__ __forceinline__ void enter(bool fresh, const float* base, int64_t row_stride, int64_t class_stride, int r0,
-                                        int r1, bool pair, float l0s, float l1s, int nclass) {
+  // rows r0 (-> top) and r1 (-> bottom) of the cell; `fresh` = first cell of the strip, otherwise the old bottom row
+  // (top + dif) becomes the new top row.  `load(dst, row, sub)` fetches one horizontally interpolated source row.
+  template <typename Load>
+  __device__ __forceinline__ void enter(bool fresh, int r0, int r1, Load&& load) {
     if (fresh) {
-      if (pair) hrow<true>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
-      else hrow<false>(top, base + r0 * row_stride, class_stride, l0s, l1s, 0.f, nclass);
+      load(top, r0, 0.f);
       ref2 = 0.f;
     } else {
 #pragma unroll
-      for (int p = 0; p < P; ++p) top[p] = fadd2(top[p], dif[p]);
+      for (int p = 0; p < NP; ++p) top[p] = fadd2(top[p], dif[p]);
     }
-    float m = rowmax(top, nclass);
+    float m = rowmax(top);
     if (r1 != r0) {
-      if (pair) hrow<true>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
-      else hrow<false>(dif, base + r1 * row_stride, class_stride, l0s, l1s, ref2, nclass);
-      m = fmaxf(m, rowmax(dif, nclass));
+      load(dif, r1, ref2);
+      m = fmaxf(m, rowmax(dif));
       const float2 neg1 = splat2(-1.f), nm = splat2(-m);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
+      for (int p = 0; p < NP; ++p) {
         dif[p] = ffma2(top[p], neg1, dif[p]);          // dif - top, one rounding
         top[p] = fadd2(top[p], nm);
       }
     } else {
       const float2 nm = splat2(-m);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
+      for (int p = 0; p < NP; ++p) {
         dif[p] = make_float2(0.f, 0.f);
         top[p] = fadd2(top[p], nm);
       }

@@ -28,8 +28,9 @@ namespace diga {
 
 int tunable(const char* name, int dflt);
 
-constexpr int kLuBlock = 128;
-constexpr int kLuLd = kLuBlock + kLuBlock / 8 + 2;  // row pitch of the swizzled staging arrays
+constexpr int kLuBlock = 128;                       // threads per CTA = output columns per CTA
+constexpr int kLuCols = kLuBlock;
+constexpr int kLuLd = kLuCols + kLuCols / 8 + 2;    // rows of the swizzled staging arrays
 
 struct LossUpPlan {
   int ry, SX, SY, R, K;
@@ -49,7 +50,7 @@ static LossUpPlan make_plan(int64_t n, int64_t C, int64_t h, int64_t w, int64_t 
   LossUpPlan p;
   p.ry = tunable("lossup_ry", 32);
   if (p.ry < 1) p.ry = 1;
-  p.SX = (int)((W + kLuBlock - 1) / kLuBlock);
+  p.SX = (int)((W + kLuCols - 1) / kLuCols);
   p.SY = (int)((H + p.ry - 1) / p.ry);
   const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
   p.R = 1;
@@ -63,8 +64,8 @@ static LossUpPlan make_plan(int64_t n, int64_t C, int64_t h, int64_t w, int64_t 
   p.K = 1;
   for (int kx = 0; kx < p.SX; ++kx) {
     int lo, hi, t;
-    const int xe = (int)((int64_t)(kx + 1) * kLuBlock < W ? (int64_t)(kx + 1) * kLuBlock : W) - 1;
-    host_tap(sw, kx * kLuBlock, (int)w, &lo, &t);
+    const int xe = (int)((int64_t)(kx + 1) * kLuCols < W ? (int64_t)(kx + 1) * kLuCols : W) - 1;
+    host_tap(sw, kx * kLuCols, (int)w, &lo, &t);
     host_tap(sw, xe, (int)w, &t, &hi);
     if (hi - lo + 1 > p.K) p.K = hi - lo + 1;
   }
@@ -105,41 +106,68 @@ struct LossUpArgs {
 __device__ __forceinline__ int lu_swz(int x) { return x + (x >> 3); }
 
 #ifndef LU_MINB_LOSS
-#define LU_MINB_LOSS 3      // resident CTAs per SM the loss-only kernels are compiled for (168 registers, no spills; 4 spills and is slower)
+#define LU_MINB_LOSS 2      // resident CTAs per SM the loss-only kernels are compiled for
 #endif
 #ifndef LU_MINB_GRAD
-#define LU_MINB_GRAD 2      // ... and the gradient kernels (up to 255 registers: Gt/Gb and the two exp arrays stay in registers)
+#define LU_MINB_GRAD 2      // ... and the gradient kernels (up to 255 registers)
 #endif
-// Dynamic shared memory of the kernel: the strip's vertical taps, then (CE only) the per-column class tables
-//   tabT / tabD [C][128]: the student's (top, dif) of the current cell, so that the target-class logit of a pixel is two
-//                         shared loads + one FFMA instead of C compares and selects;
-//   oh [2][C][128]      : (gradient only) the one-hot term of the CE gradient, accumulated per source-row parity; it is
-//                         subtracted from the class gradients when the row is flushed.
-// Every thread touches its own column only: no barriers.
-__host__ __device__ static inline size_t lu_tab_offset(int ry) { return ((size_t)ry * sizeof(int2) + 15) & ~(size_t)15; }
-__host__ __device__ static inline size_t lu_tile_bytes(int views, int R, int nclass, int K) {
-  return ((size_t)views * R * nclass * (K + 1) * sizeof(float) + 15) & ~(size_t)15;
+constexpr float kLuRecurrenceMax = 24.f;   // largest |dif| (log2 units per source row) a warp advances by multiplication
+
+// Dynamic shared memory of the loss kernel, in this order:
+//   ytab  [ry] int2          vertical taps of the strip's rows
+//   tile                     the strip's source rows [view][row][column][CP] (see the kernel); 0 bytes when the CTA reads
+//                            global memory
+//   tabT / tabD [CP][128]    (CE) the student's (top, dif) of the current cell: the target-class logit of a pixel is two
+//                            shared loads + one FFMA instead of C compares and selects
+//   oh [2][CP][128]          (CE, gradient) the one-hot term of the CE gradient per source-row parity; subtracted from the
+//                            class gradients when the row is flushed
+//   tea [2][CP/2][128] float2 (KD) the teacher's (top, dif): only needed at cell crossings and on the exact path
+//   wtab [CP]                (CE) class weights (1 when the caller passes none)
+//   tcode [ry][128] uint8    (CE) the strip's targets: class id, 254 = counted but ignored, 255 = not counted
+// A per-column table entry is written and read by the thread that owns the column (tcode / wtab: before the first barrier).
+struct LuSmem {
+  size_t tile, tab, oh, tea, wtab, tcode, total;
+};
+__host__ __device__ static inline LuSmem lu_smem(int ry, int cp, bool kd, bool ce, bool grad, size_t tile_bytes) {
+  LuSmem m;
+  m.tile = ((size_t)ry * sizeof(int2) + 15) & ~(size_t)15;
+  m.tab = m.tile + tile_bytes;
+  m.oh = m.tab + (ce ? (size_t)2 * cp * kLuBlock * sizeof(float) : 0);
+  m.tea = m.oh + ((ce && grad) ? (size_t)2 * cp * kLuBlock * sizeof(float) : 0);
+  m.wtab = m.tea + (kd ? (size_t)2 * (cp / 2) * kLuBlock * sizeof(float2) : 0);
+  m.tcode = m.wtab + (ce ? (size_t)cp * sizeof(float) : 0);
+  m.total = m.tcode + (ce ? (((size_t)ry * kLuBlock + 15) & ~(size_t)15) : 0);
+  return m;
 }
-static inline size_t lu_dyn_bytes(int ry, int ctemplate, bool ce, bool grad, size_t tile_bytes) {
-  return lu_tab_offset(ry) + tile_bytes + (ce ? (size_t)(grad ? 4 : 2) * ctemplate * kLuBlock * sizeof(float) : 0);
+__host__ __device__ static inline size_t lu_tile_bytes(int views, int R, int cp, int K) {
+  return ((size_t)views * R * (K + 1) * cp * sizeof(float) + 15) & ~(size_t)15;
 }
 __device__ __forceinline__ void lu_cp_async4(float* dst_shared, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
 }
 
+// One CTA = 128 output columns x `ry` output rows of one image, one thread per column.
+//
+// Exponentials: inside a source cell the interpolated logit of a class is linear in the output row, v(Y+1) = v(Y) +
+// dif * sh, hence 2^v(Y+1) = 2^v(Y) * 2^(dif * sh): the kernel seeds 2^v and the per-row factor with MUFU.EX2 when the
+// walk enters a cell and advances with one FMUL2 per class pair and row (<= 8 rows at stride 8: a few ulp of drift, re-
+// seeded at every crossing; the vertical tap fl(sh * Y) - i0 deviates from an exact progression by <= ulp(h), i.e. a
+// relative 1e-6 in the exponentials at |dif| = 1).  A warp whose cell holds |dif| > 24 (adjacent source rows > 16 logits
+// apart in some class) evaluates every row with MUFU.EX2 and, if a sum still underflows, re-bases on the per-pixel max.
 template <int C, bool PAD, bool KD, bool CE, bool LOSS, bool GRAD>
 __global__ void __launch_bounds__(kLuBlock, GRAD ? LU_MINB_GRAD : LU_MINB_LOSS)
 loss_up_kernel(const LossUpArgs a) {
   extern __shared__ __align__(16) unsigned char lu_dyn[];
   int2* ytab = reinterpret_cast<int2*>(lu_dyn);            // per-row vertical taps of the strip
+  constexpr int CP = (C + 3) & ~3, CQ = CP / 4;            // classes padded to a multiple of four
+  constexpr int P = CP / 2;                                // class pairs per thread
+  using Col = LerpColumnP<P>;
   const int n = blockIdx.z, ky = blockIdx.y, kx = blockIdx.x, tid = threadIdx.x;
   const int X0 = kx * kLuBlock, X = X0 + tid;
   const bool in_range = X < a.W;
   const int Y0 = ky * a.ry, Yend = min(Y0 + a.ry, a.H);
   const int64_t plane = (int64_t)a.h * a.w;
   const int nclass = a.nclass;
-  using Col = LerpColumn2<C, PAD>;
-  constexpr int P = Col::P;
   const Tap tx = bilinear_tap(a.sw, in_range ? X : a.W - 1, a.w);
   // Horizontal tap as the column pair (kc, kc + 1): a lane clamped at the last source column (i1 == i0) reads the pair
   // (i0 - 1, i0) with weights (0, l0 + l1) so that the second load is always "first + 1" (a 1-column source has no pair).
@@ -155,12 +183,15 @@ loss_up_kernel(const LossUpArgs a) {
     wkd = n < a.B ? a.scale : 1.f;
   }
   const bool ce_img = CE && n < a.n_ce;
-  const int64_t* trow = ce_img ? a.target + ((int64_t)n * a.H) * a.W + (in_range ? X : a.W - 1) : nullptr;
-  float* tile = reinterpret_cast<float*>(lu_dyn + lu_tab_offset(a.ry));
-  const size_t tile_bytes = a.tile ? lu_tile_bytes(KD ? 2 : 1, a.R, nclass, a.K) : 0;
-  float* tabT = reinterpret_cast<float*>(lu_dyn + lu_tab_offset(a.ry) + tile_bytes) + tid;   // this thread's column of [C][128]
-  float* tabD = tabT + C * kLuBlock;
-  float* oh = tabD + C * kLuBlock;                                                 // [2][C][128], GRAD only
+  const LuSmem lay = lu_smem(a.ry, CP, KD, CE, GRAD, a.tile ? lu_tile_bytes(KD ? 2 : 1, a.R, CP, a.K) : 0);
+  float* tile = reinterpret_cast<float*>(lu_dyn + lay.tile);
+  float* tabT = reinterpret_cast<float*>(lu_dyn + lay.tab) + tid;                  // this column of [CP][128]
+  float* tabD = tabT + CP * kLuBlock;
+  float* oh = reinterpret_cast<float*>(lu_dyn + lay.oh) + tid;                     // [2][CP][128]
+  float2* teaT = reinterpret_cast<float2*>(lu_dyn + lay.tea) + tid;                // [CP/2][128] class pairs
+  float2* teaD = teaT + P * kLuBlock;
+  float* wtab = reinterpret_cast<float*>(lu_dyn + lay.wtab);
+  unsigned char* tcode = lu_dyn + lay.tcode;
 
   float ckd = 0.f, cce = 0.f;
   if constexpr (GRAD) {
@@ -182,14 +213,14 @@ loss_up_kernel(const LossUpArgs a) {
   // The strip's source rows, both views, go to shared memory with ONE round of asynchronous copies (`a.tile`; geometries
   // whose tile would not fit keep reading global memory): a cell crossing then costs shared-memory latency instead of two
   // dependent trips to L2 / DRAM — every source row is first touched by the CTAs that interpolate from it.
-  // Layout: segment = (view, row, class) in that order, K + 1 columns each, first column = kc of the CTA's first thread.
+  // Layout [view][row][column][CP], first column = kc of the CTA's first thread; the class slots >= nclass hold kLerpPad.
   const Tap t0 = bilinear_tap(a.sw, X0, a.w);
   const int xbase = (t0.i1 == t0.i0 && pair) ? t0.i0 - 1 : t0.i0;
   const int Kp = a.K + 1;
   const int Rn = bilinear_tap(a.sh, Yend - 1, a.h).i1 - ylo + 1;
   if (a.tile) {
     const int ncols = min(Kp, a.w - xbase);
-    const int segs = (KD ? 2 : 1) * Rn * nclass;
+    const int segs = (KD ? 2 : 1) * Rn * nclass;             // segment = (view, row, class), `ncols` floats each
     int seg = tid / ncols, col = tid - seg * ncols;
     const int dseg = kLuBlock / ncols, dcol = kLuBlock - dseg * ncols;
     int c = seg, r = 0, view = 0;                            // decode of `seg`, advanced incrementally
@@ -199,7 +230,7 @@ loss_up_kernel(const LossUpArgs a) {
         if (++r == Rn) r = 0, ++view;
       }
       const float* src = (view ? tcol : scol) - kc + xbase + (int64_t)c * plane + (int64_t)r * a.w + col;
-      lu_cp_async4(tile + seg * Kp + col, src);
+      lu_cp_async4(tile + (((view * Rn + r) * Kp) + col) * CP + c, src);
       col += dcol;
       const int wrap = col >= ncols;
       col -= wrap ? ncols : 0;
@@ -207,25 +238,44 @@ loss_up_kernel(const LossUpArgs a) {
       c += dseg + wrap;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (nclass < CP) {
+      const int npad = CP - nclass, total = (KD ? 2 : 1) * Rn * Kp * npad;
+      for (int i = tid; i < total; i += kLuBlock) tile[(i / npad) * CP + nclass + i % npad] = kLerpPad;
+    }
   }
-  const float* stile = tile + (kc - xbase);                // (row 0, class 0, column kc) of the student view
-  const float* ttile = stile + Rn * nclass * Kp;
-  const int tile_row = nclass * Kp;
+  const float* stile = tile + (kc - xbase) * CP;           // (row 0, column kc) of the student view
+  const float* ttile = stile + Rn * Kp * CP;
+  const int tile_row = Kp * CP, tile_col = pair ? CP : 0;
 
   // per-row vertical taps, computed once per CTA: {local row of i0 | (i1 - i0) << 16, l1}
   for (int i = tid; i < Yend - Y0; i += kLuBlock) {
     const Tap t = bilinear_tap(a.sh, Y0 + i, a.h);
     ytab[i] = make_int2((t.i0 - ylo) | ((t.i1 - t.i0) << 16), __float_as_int(t.l1));
   }
-  if constexpr (CE && GRAD) {
+  if constexpr (CE) {
     if (ce_img) {
+      // the strip's targets as one byte per pixel: the int64 loads of the whole strip are in flight together, off the
+      // row loop (loss.py:56 counts target >= 0; nll_loss ignores 255 — any id >= C — and the OHEM ignore label)
+      const int64_t* tg = a.target + ((int64_t)n * a.H + Y0) * a.W + (in_range ? X : a.W - 1);
+      const int rows = Yend - Y0;
+      for (int row0 = 0; row0 < rows; row0 += 16) {          // 16 loads in flight per thread, then the conversions
+        int64_t t[16];
 #pragma unroll
-      for (int c = 0; c < 2 * C; ++c) oh[c * kLuBlock] = 0.f;
+        for (int k = 0; k < 16; ++k) t[k] = ld_stream_i64(tg + (int64_t)min(row0 + k, rows - 1) * a.W);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (row0 + k < rows)
+            tcode[(row0 + k) * kLuBlock + tid] = t[k] < 0 ? 255 : (t[k] >= nclass || t[k] == a.ignore_label) ? 254 : (unsigned char)t[k];
+      }
+      if (tid < CP) wtab[tid] = (a.weight != nullptr && tid < nclass) ? __ldg(a.weight + tid) : 1.f;
+      if constexpr (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 2 * CP; ++k) oh[k * kLuBlock] = 0.f;
+      }
     }
   }
 
   // ---- backward staging (shared memory): [column (swizzled)][class], classes padded to a multiple of four ----------
-  constexpr int CP = (C + 3) & ~3, CQ = CP / 4;
   __shared__ __align__(16) float sa[GRAD ? kLuLd : 1][GRAD ? CP : 4];
   __shared__ __align__(16) float sb[GRAD ? kLuLd : 1][GRAD ? CP : 4];
   __shared__ int st[GRAD ? kLuBlock + 4 : 1];
@@ -247,38 +297,27 @@ loss_up_kernel(const LossUpArgs a) {
 #pragma unroll
     for (int p = 0; p < P; ++p) Gt[p] = Gb[p] = make_float2(0.f, 0.f);
   }
-  // flush: horizontal half of the transposed interpolation for one completed source row.  Every column stages
-  // l0*G (-> source column i0) and l1*G (-> i0 + 1) as float4 class quads; a work item (source column, class quad) sums
-  // the contiguous run of output columns that map to it and stores one float4 of the CTA's patch [row][column][CP].
+  // flush: horizontal half of the transposed interpolation for one completed source row.  Every column stages l0*G
+  // (-> source column i0) and l1*G (-> i0 + 1) as float4 class quads; a work item (source column, class quad) sums the
+  // contiguous run of output columns that map to it and stores one float4 of the CTA's patch [row][column][CP].
   auto flush = [&](const float2 (&G)[GRAD ? P : 1], int row) {
     if constexpr (GRAD) {
       const int sx = lu_swz(tid);
       const float2 wa = splat2(in_range ? (clamped ? tx.l0 + tx.l1 : tx.l0) : 0.f);
       const float2 wb = splat2((in_range && !clamped) ? tx.l1 : 0.f);
-      float* ohs = oh + (row & 1) * (C * kLuBlock);        // the row's one-hot accumulator (CE images)
+      float* ohs = oh + (row & 1) * (CP * kLuBlock);       // the row's one-hot accumulator (CE images)
 #pragma unroll
       for (int q = 0; q < CQ; ++q) {
-        float2 g[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int p = 2 * q + k;
-          g[k] = p < P ? G[p < P ? p : 0] : make_float2(0.f, 0.f);
-          if (!Col::on(2 * p, nclass)) g[k].x = 0.f;
-          if (!Col::on(2 * p + 1, nclass)) g[k].y = 0.f;
-          if constexpr (CE) {
-            if (ce_img) {
-              if (Col::on(2 * p, nclass)) {
-                g[k].x -= ohs[(2 * p) * kLuBlock];
-                ohs[(2 * p) * kLuBlock] = 0.f;
-              }
-              if (Col::on(2 * p + 1, nclass)) {
-                g[k].y -= ohs[(2 * p + 1) * kLuBlock];
-                ohs[(2 * p + 1) * kLuBlock] = 0.f;
-              }
-            }
+        float2 g0 = G[2 * q], g1 = G[2 * q + 1];
+        if constexpr (CE) {
+          if (ce_img) {
+            g0.x -= ohs[(4 * q) * kLuBlock], g0.y -= ohs[(4 * q + 1) * kLuBlock];
+            g1.x -= ohs[(4 * q + 2) * kLuBlock], g1.y -= ohs[(4 * q + 3) * kLuBlock];
+            ohs[(4 * q) * kLuBlock] = 0.f, ohs[(4 * q + 1) * kLuBlock] = 0.f;
+            ohs[(4 * q + 2) * kLuBlock] = 0.f, ohs[(4 * q + 3) * kLuBlock] = 0.f;
           }
         }
-        const float2 a0 = fmul2(wa, g[0]), a1 = fmul2(wa, g[1]), b0 = fmul2(wb, g[0]), b1 = fmul2(wb, g[1]);
+        const float2 a0 = fmul2(wa, g0), a1 = fmul2(wa, g1), b0 = fmul2(wb, g0), b1 = fmul2(wb, g1);
         *reinterpret_cast<float4*>(&sa[sx][4 * q]) = make_float4(a0.x, a0.y, a1.x, a1.y);
         *reinterpret_cast<float4*>(&sb[sx][4 * q]) = make_float4(b0.x, b0.y, b1.x, b1.y);
       }
@@ -301,25 +340,35 @@ loss_up_kernel(const LossUpArgs a) {
       __syncthreads();
     }
   };
+  // one horizontally interpolated source row of a view: from the tile, or (no tile) from global memory
+  auto load_row = [&](bool teacher) {
+    return [=](float2 (&dst)[P], int row, float sub) {
+      Col* none = nullptr;
+      if (a.tile) none->hrow_tile(dst, (teacher ? ttile : stile) + row * tile_row, tile_col, l0s, l1s, sub);
+      else none->hrow_global(dst, (teacher ? tcol : scol) + (int64_t)row * a.w, plane, pair ? 1 : 0, l0s, l1s, sub, nclass);
+    };
+  };
 
-  Col cs;
-  LerpColumn2<KD ? C : 1, PAD> ct;
+  Col cs;                                                    // student (top, dif): registers; teacher: shared memory
+  float2 es[P], ss[P];                                       // 2^v of the current row and its per-row factor
+  float2 et[KD ? P : 1], ts[KD ? P : 1];
+  bool bigcell = false;                                      // this warp evaluates the cell's rows with MUFU.EX2
+  float tref2 = 0.f;
   float acc_kd = 0.f, acc_ce = 0.f, acc_cnt = 0.f;
   int cur_r0 = -1, cur_r1 = -1;
-  int64_t tgt = 0, tgt_next = 0;
-  if (ce_img) tgt = ld_stream_i64(trow + (int64_t)Y0 * a.W);
+  const float sh_step = a.sh;
 
   int2 yt_next = ytab[0];
   for (int Y = Y0; Y < Yend; ++Y) {
-    if (ce_img && Y + 1 < Yend) tgt_next = ld_stream_i64(trow + (int64_t)(Y + 1) * a.W);
     const int2 yt = yt_next;
     yt_next = ytab[min(Y + 1, Yend - 1) - Y0];               // one row ahead: the tap is not on the row's critical path
     const int r0 = yt.x & 0xffff, r1 = r0 + (yt.x >> 16);
     const float yl1 = __int_as_float(yt.y), yl0 = 1.0f - yl1;
     const float2 yl1v = splat2(yl1);
     if (r0 != cur_r0) {                                      // first row, or crossed into the next source cell (CTA-uniform)
+      const bool fresh = cur_r0 < 0;
       if constexpr (GRAD) {
-        if (cur_r0 >= 0) {
+        if (!fresh) {
           flush(Gt, cur_r0);                                 // source row cur_r0 is complete for this strip
 #pragma unroll
           for (int p = 0; p < P; ++p) {
@@ -328,19 +377,41 @@ loss_up_kernel(const LossUpArgs a) {
           }
         }
       }
-      if (a.tile) {
-        cs.enter(cur_r0 < 0, stile, tile_row, Kp, r0, r1, pair, l0s, l1s, nclass);
-        if constexpr (KD) ct.enter(cur_r0 < 0, ttile, tile_row, Kp, r0, r1, pair, l0s, l1s, nclass);
-      } else {
-        cs.enter(cur_r0 < 0, scol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
-        if constexpr (KD) ct.enter(cur_r0 < 0, tcol, a.w, plane, r0, r1, pair, l0s, l1s, nclass);
+      cs.enter(fresh, r0, r1, load_row(false));
+      const float2 lseed = splat2(yl1 - sh_step), stepv = splat2(sh_step);   // the row loop multiplies before it uses
+      float mx = 0.f;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const float2 v = ffma2(lseed, cs.dif[p], cs.top[p]), d = fmul2(stepv, cs.dif[p]);
+        es[p] = make_float2(fast_ex2(v.x), fast_ex2(v.y));
+        ss[p] = make_float2(fast_ex2(d.x), fast_ex2(d.y));
+        mx = fmax3(mx, fabsf(cs.dif[p].x), fabsf(cs.dif[p].y));
       }
+      if constexpr (KD) {
+        Col ct;
+        ct.ref2 = tref2;
+        if (!fresh) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) ct.top[p] = teaT[p * kLuBlock], ct.dif[p] = teaD[p * kLuBlock];
+        }
+        ct.enter(fresh, r0, r1, load_row(true));
+        tref2 = ct.ref2;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          teaT[p * kLuBlock] = ct.top[p], teaD[p * kLuBlock] = ct.dif[p];
+          const float2 u = ffma2(lseed, ct.dif[p], ct.top[p]), d = fmul2(stepv, ct.dif[p]);
+          et[p] = make_float2(fast_ex2(u.x), fast_ex2(u.y));
+          ts[p] = make_float2(fast_ex2(d.x), fast_ex2(d.y));
+          mx = fmax3(mx, fabsf(ct.dif[p].x), fabsf(ct.dif[p].y));
+        }
+      }
+      bigcell = __any_sync(0xffffffffu, mx > kLuRecurrenceMax);
       if constexpr (CE) {
         if (ce_img) {
 #pragma unroll
           for (int p = 0; p < P; ++p) {
-            if (Col::on(2 * p, nclass)) tabT[(2 * p) * kLuBlock] = cs.top[p].x, tabD[(2 * p) * kLuBlock] = cs.dif[p].x;
-            if (Col::on(2 * p + 1, nclass)) tabT[(2 * p + 1) * kLuBlock] = cs.top[p].y, tabD[(2 * p + 1) * kLuBlock] = cs.dif[p].y;
+            tabT[(2 * p) * kLuBlock] = cs.top[p].x, tabD[(2 * p) * kLuBlock] = cs.dif[p].x;
+            tabT[(2 * p + 1) * kLuBlock] = cs.top[p].y, tabD[(2 * p + 1) * kLuBlock] = cs.dif[p].y;
           }
         }
       }
@@ -349,82 +420,87 @@ loss_up_kernel(const LossUpArgs a) {
     }
 
     // Per-pixel statistics in the log2 domain, relative to the cell reference (see LerpColumn):
-    //   es_c = 2^v_c, Ss = sum es_c, (KD) e_c = 2^u_c, St = sum e_c, cross2 = sum e_c v_c,
-    // on class pairs (FFMA2 / FADD2), two interleaved chains of pairs.  EXACT re-bases on the per-pixel max (taken only
-    // after an underflow).
-    float2 es[GRAD ? P : 1], et[(GRAD && KD) ? P : 1];
+    //   es_c = 2^v_c, Ss = sum es_c, (KD) et_c = 2^u_c, St = sum et_c, cross2 = sum et_c v_c,
+    // on class pairs (FMUL2 / FFMA2 / FADD2), two interleaved chains of pairs.
     float Ss = 0.f, St = 0.f, cross2 = 0.f, ms = 0.f;
-    auto stats = [&](auto exact_tag) {
-      constexpr bool EXACT = decltype(exact_tag)::value;
-      float mt = 0.f;
-      if constexpr (EXACT) {
-        ms = mt = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const float2 v = cs.value2(yl1v, p);
-          if (Col::on(2 * p, nclass)) ms = fmaxf(ms, v.x);
-          if (Col::on(2 * p + 1, nclass)) ms = fmaxf(ms, v.y);
-          if constexpr (KD) {
-            const float2 u = ct.value2(yl1v, p);
-            if (Col::on(2 * p, nclass)) mt = fmaxf(mt, u.x);
-            if (Col::on(2 * p + 1, nclass)) mt = fmaxf(mt, u.y);
-          }
-        }
-      }
-      const float2 nms = splat2(-ms), nmt = splat2(-mt);
+    if (!bigcell) {
       float2 S2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       [[maybe_unused]] float2 T2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       [[maybe_unused]] float2 X2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        float2 e_s = make_float2(0.f, 0.f), e_t = make_float2(0.f, 0.f);
-        if (Col::on(2 * p, nclass)) {
-          float2 v = cs.value2(yl1v, p);
-          if constexpr (EXACT) v = fadd2(v, nms);
-          e_s.x = fast_ex2(v.x);
-          if (Col::on(2 * p + 1, nclass)) e_s.y = fast_ex2(v.y);
-          S2[p & 1] = fadd2(S2[p & 1], e_s);
-          if constexpr (KD) {
-            float2 u = ct.value2(yl1v, p);
-            if constexpr (EXACT) u = fadd2(u, nmt);
-            e_t.x = fast_ex2(u.x);
-            if (Col::on(2 * p + 1, nclass)) e_t.y = fast_ex2(u.y);
-            T2[p & 1] = fadd2(T2[p & 1], e_t);
-            X2[p & 1] = ffma2(e_t, v, X2[p & 1]);
+        es[p] = fmul2(es[p], ss[p]);
+        S2[p & 1] = fadd2(S2[p & 1], es[p]);
+        if constexpr (KD) {
+          et[p] = fmul2(et[p], ts[p]);
+          T2[p & 1] = fadd2(T2[p & 1], et[p]);
+          X2[p & 1] = ffma2(et[p], cs.value2(yl1v, p), X2[p & 1]);
+        }
+      }
+      const float2 sv = fadd2(S2[0], S2[1]);
+      Ss = sv.x + sv.y;
+      if constexpr (KD) {
+        const float2 tv = fadd2(T2[0], T2[1]), xv = fadd2(X2[0], X2[1]);
+        St = tv.x + tv.y, cross2 = xv.x + xv.y;
+      }
+    } else {
+      // exact path: MUFU.EX2 per class and row; EXACT re-bases on the per-pixel max (taken only after an underflow)
+      auto stats = [&](auto exact_tag) {
+        constexpr bool EXACT = decltype(exact_tag)::value;
+        float mt = 0.f;
+        if constexpr (EXACT) {
+          ms = mt = -INFINITY;
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const float2 v = cs.value2(yl1v, p);
+            ms = fmax3(ms, v.x, v.y);
+            if constexpr (KD) {
+              const float2 u = ffma2(yl1v, teaD[p * kLuBlock], teaT[p * kLuBlock]);
+              mt = fmax3(mt, u.x, u.y);
+            }
           }
         }
-        if constexpr (GRAD) {
-          es[p] = e_s;
-          if constexpr (KD) et[p] = e_t;
+        const float2 nms = splat2(-ms), nmt = splat2(-mt);
+        float2 S2 = make_float2(0.f, 0.f);
+        [[maybe_unused]] float2 T2 = make_float2(0.f, 0.f), X2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          float2 v = cs.value2(yl1v, p);
+          if constexpr (EXACT) v = fadd2(v, nms);
+          es[p] = make_float2(fast_ex2(v.x), fast_ex2(v.y));
+          S2 = fadd2(S2, es[p]);
+          if constexpr (KD) {
+            float2 u = ffma2(yl1v, teaD[p * kLuBlock], teaT[p * kLuBlock]);
+            if constexpr (EXACT) u = fadd2(u, nmt);
+            et[p] = make_float2(fast_ex2(u.x), fast_ex2(u.y));
+            T2 = fadd2(T2, et[p]);
+            X2 = ffma2(et[p], v, X2);
+          }
         }
-      }
-      const float2 s = fadd2(S2[0], S2[1]);
-      Ss = s.x + s.y;
-      if constexpr (KD) {
-        const float2 t = fadd2(T2[0], T2[1]), x = fadd2(X2[0], X2[1]);
-        St = t.x + t.y;
-        cross2 = x.x + x.y;
-      }
-    };
-    stats(std::false_type{});
-    if (Ss < 0x1p-60f || (KD && St < 0x1p-60f)) stats(std::true_type{});   // adjacent source rows > 41 logits apart
+        Ss = S2.x + S2.y;
+        if constexpr (KD) St = T2.x + T2.y, cross2 = X2.x + X2.y;
+      };
+      stats(std::false_type{});
+      if (Ss < 0x1p-60f || (KD && St < 0x1p-60f)) stats(std::true_type{});   // adjacent source rows > 41 logits apart
+    }
 
     float inv_t = 0.f;
     if constexpr (KD) inv_t = fast_rcp(St);
     float wt = 1.f, dtgt = 0.f;
+    int code = 255;
     bool counted = false, valid = false;
     if constexpr (CE) {
       if (ce_img) {
-        counted = in_range && tgt >= 0;                               // loss.py:56  mask = target >= 0
-        valid = counted && tgt < nclass && tgt != a.ignore_label;     // 255 (any id >= C) is ignored by nll_loss
+        code = tcode[(Y - Y0) * kLuBlock + tid];
+        counted = in_range && code != 255;                            // loss.py:56  mask = target >= 0
+        valid = in_range && code < 254;
         if (ohem && valid) {                                          // OhemCrossEntropy keeps the hard pixels only
           const float pv = __ldg(prow + (int64_t)Y * a.W);
           valid = pv >= 0.f && pv < sel_thr;
         }
         if (valid) {
-          if (a.weight != nullptr) wt = __ldg(a.weight + tgt);
-          const int o = (int)tgt * kLuBlock;
-          dtgt = fmaf(yl1, tabD[o], tabT[o]) - ms;                    // the target class's logit, same frame as the sums
+          wt = wtab[code];
+          dtgt = fmaf(yl1, tabD[code * kLuBlock], tabT[code * kLuBlock]) - ms;   // same frame as the sums
         }
       }
     }
@@ -443,23 +519,21 @@ loss_up_kernel(const LossUpArgs a) {
       const float2 ga = splat2((ckd + cpx) * fast_rcp(Ss)), ngb = splat2(-(ckd * inv_t));
       const float2 yl0v = splat2(yl0);
 #pragma unroll
-      for (int p = 0; p < P; ++p)
-        if (Col::on(2 * p, nclass)) {
-          float2 g = fmul2(ga, es[p]);
-          if constexpr (KD) g = ffma2(ngb, et[p], g);
-          Gt[p] = ffma2(yl0v, g, Gt[p]);
-          Gb[p] = ffma2(yl1v, g, Gb[p]);
-        }
+      for (int p = 0; p < P; ++p) {
+        float2 g = fmul2(ga, es[p]);
+        if constexpr (KD) g = ffma2(ngb, et[p], g);
+        Gt[p] = ffma2(yl0v, g, Gt[p]);
+        Gb[p] = ffma2(yl1v, g, Gb[p]);
+      }
       if constexpr (CE) {
         if (valid) {                                                 // one-hot term, per source-row parity (see flush)
-          float* o0 = oh + ((r0 & 1) * C + (int)tgt) * kLuBlock;
+          float* o0 = oh + ((r0 & 1) * CP + code) * kLuBlock;
           *o0 += yl0 * cpx;
-          float* o1 = oh + ((r1 & 1) * C + (int)tgt) * kLuBlock;
+          float* o1 = oh + ((r1 & 1) * CP + code) * kLuBlock;
           *o1 += yl1 * cpx;
         }
       }
     }
-    tgt = tgt_next;
   }
 
   if constexpr (GRAD) {
@@ -560,10 +634,10 @@ loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlo
       kxA = max(0, (int)((float)max(x - 1, 0) * inv_sw_bx) - 1);
       kxB = min(SX - 1, (int)((float)(x + 1) * inv_sw_bx) + 1);
     }
-    while (kxA <= kxB && bilinear_tap(sw, min((kxA + 1) * kLuBlock, W) - 1, w).i1 < x) ++kxA;
-    while (kxB >= kxA && bilinear_tap(sw, kxB * kLuBlock, w).i0 > x) --kxB;
+    while (kxA <= kxB && bilinear_tap(sw, min((kxA + 1) * kLuCols, W) - 1, w).i1 < x) ++kxA;
+    while (kxB >= kxA && bilinear_tap(sw, kxB * kLuCols, w).i0 > x) --kxB;
     auto patch_ptr = [&](int ky, int kx) {
-      const int ylo = bilinear_tap(sh, ky * ry, h).i0, xlo = bilinear_tap(sw, kx * kLuBlock, w).i0;
+      const int ylo = bilinear_tap(sh, ky * ry, h).i0, xlo = bilinear_tap(sw, kx * kLuCols, w).i0;
       const int64_t cta = ((int64_t)img * SY + ky) * SX + kx;
       return reinterpret_cast<const float4*>(scratch + (((cta * R + (y - ylo)) * K) + (x - xlo)) * CP);
     };
@@ -644,10 +718,10 @@ template <bool KD, bool CE, bool LOSS, bool GRAD>
 static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* dlow, cudaStream_t st) {
   dim3 grid((unsigned)p.SX, (unsigned)p.SY, (unsigned)a.n);
   DIGA_REQUIRE((size_t)p.ry * sizeof(int2) <= 32 * 1024, DIGA_ERR_INVALID, "loss_up: strip height %d too large", p.ry);
-  const size_t tile_bytes = lu_tile_bytes(KD ? 2 : 1, p.R, (int)C, p.K);
+  const size_t tile_bytes = lu_tile_bytes(KD ? 2 : 1, p.R, ((int)C == 19 || (int)C == 16) ? (((int)C + 3) & ~3) : 32, p.K);
   a.tile = tile_bytes <= kLuTileMax && tunable("lossup_tile", 1) != 0;
   DIGA_DISPATCH_C(C, {
-    const size_t dyn = lu_dyn_bytes(p.ry, kC, CE, GRAD, a.tile ? tile_bytes : 0);
+    const size_t dyn = lu_smem(p.ry, (kC + 3) & ~3, KD, CE, GRAD, a.tile ? tile_bytes : 0).total;
     auto kernel = loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD>;
     static size_t configured_dev[64] = {0};            // per instantiation and device
     size_t& configured = configured_dev[device_slot()];
@@ -663,7 +737,7 @@ static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* d
     DIGA_CHECK_LAUNCH("loss_up_kernel");
     if (GRAD) {
       const float inv_sh_ry = a.sh > 0.f ? 1.0f / (a.sh * (float)p.ry) : 0.f;
-      const float inv_sw_bx = a.sw > 0.f ? 1.0f / (a.sw * (float)kLuBlock) : 0.f;
+      const float inv_sw_bx = a.sw > 0.f ? 1.0f / (a.sw * (float)kLuCols) : 0.f;
       loss_up_gather_kernel<kC, kPad><<<dim3((unsigned)a.h, (unsigned)a.n), 128, 0, st>>>(
           a.scratch, dlow, a.nclass, a.h, a.w, a.H, a.W, a.sh, a.sw, inv_sh_ry, inv_sw_bx, p.ry, p.R, p.K, p.SX, p.SY);
       DIGA_CHECK_LAUNCH("loss_up_gather_kernel");
