@@ -121,20 +121,18 @@ constexpr float kLuRecurrenceMax = 24.f;   // largest |dif| (log2 units per sour
 //                            shared loads + one FFMA instead of C compares and selects
 //   oh [2][CP][128]          (CE, gradient) the one-hot term of the CE gradient per source-row parity; subtracted from the
 //                            class gradients when the row is flushed
-//   tea [2][CP/2][128] float2 (KD) the teacher's (top, dif): only needed at cell crossings and on the exact path
 //   wtab [CP]                (CE) class weights (1 when the caller passes none)
 //   tcode [ry][128] uint8    (CE) the strip's targets: class id, 254 = counted but ignored, 255 = not counted
 // A per-column table entry is written and read by the thread that owns the column (tcode / wtab: before the first barrier).
 struct LuSmem {
-  size_t tile, tab, oh, tea, wtab, tcode, total;
+  size_t tile, tab, oh, wtab, tcode, total;
 };
 __host__ __device__ static inline LuSmem lu_smem(int ry, int cp, bool kd, bool ce, bool grad, size_t tile_bytes) {
   LuSmem m;
   m.tile = ((size_t)ry * sizeof(int2) + 15) & ~(size_t)15;
   m.tab = m.tile + tile_bytes;
   m.oh = m.tab + (ce ? (size_t)2 * cp * kLuBlock * sizeof(float) : 0);
-  m.tea = m.oh + ((ce && grad) ? (size_t)2 * cp * kLuBlock * sizeof(float) : 0);
-  m.wtab = m.tea + (kd ? (size_t)2 * (cp / 2) * kLuBlock * sizeof(float2) : 0);
+  m.wtab = m.oh + ((ce && grad) ? (size_t)2 * cp * kLuBlock * sizeof(float) : 0);
   m.tcode = m.wtab + (ce ? (size_t)cp * sizeof(float) : 0);
   m.total = m.tcode + (ce ? (((size_t)ry * kLuBlock + 15) & ~(size_t)15) : 0);
   return m;
@@ -188,8 +186,6 @@ loss_up_kernel(const LossUpArgs a) {
   float* tabT = reinterpret_cast<float*>(lu_dyn + lay.tab) + tid;                  // this column of [CP][128]
   float* tabD = tabT + CP * kLuBlock;
   float* oh = reinterpret_cast<float*>(lu_dyn + lay.oh) + tid;                     // [2][CP][128]
-  float2* teaT = reinterpret_cast<float2*>(lu_dyn + lay.tea) + tid;                // [CP/2][128] class pairs
-  float2* teaD = teaT + P * kLuBlock;
   float* wtab = reinterpret_cast<float*>(lu_dyn + lay.wtab);
   unsigned char* tcode = lu_dyn + lay.tcode;
 
@@ -219,29 +215,18 @@ loss_up_kernel(const LossUpArgs a) {
   const int Kp = a.K + 1;
   const int Rn = bilinear_tap(a.sh, Yend - 1, a.h).i1 - ylo + 1;
   if (a.tile) {
-    const int ncols = min(Kp, a.w - xbase);
-    const int segs = (KD ? 2 : 1) * Rn * nclass;             // segment = (view, row, class), `ncols` floats each
-    int seg = tid / ncols, col = tid - seg * ncols;
-    const int dseg = kLuBlock / ncols, dcol = kLuBlock - dseg * ncols;
-    int c = seg, r = 0, view = 0;                            // decode of `seg`, advanced incrementally
-    while (seg < segs) {
-      while (c >= nclass) {
-        c -= nclass;
-        if (++r == Rn) r = 0, ++view;
+    // one (view, row) per warp and step; lanes = columns, the loop walks the classes (source address + plane, tile slot + 1)
+    const int ncols = min(Kp, a.w - xbase), lane = tid & 31;
+    for (int vr = tid >> 5; vr < (KD ? 2 : 1) * Rn; vr += kLuBlock / 32) {
+      const int view = vr >= Rn, r = vr - view * Rn;
+      for (int col = lane; col < ncols; col += 32) {
+        const float* src = (view ? tcol : scol) - kc + xbase + (int64_t)r * a.w + col;
+        float* dst = tile + (vr * Kp + col) * CP;
+        for (int c = 0; c < nclass; ++c, src += plane) lu_cp_async4(dst + c, src);
+        for (int c = nclass; c < CP; ++c) dst[c] = kLerpPad;
       }
-      const float* src = (view ? tcol : scol) - kc + xbase + (int64_t)c * plane + (int64_t)r * a.w + col;
-      lu_cp_async4(tile + (((view * Rn + r) * Kp) + col) * CP + c, src);
-      col += dcol;
-      const int wrap = col >= ncols;
-      col -= wrap ? ncols : 0;
-      seg += dseg + wrap;
-      c += dseg + wrap;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (nclass < CP) {
-      const int npad = CP - nclass, total = (KD ? 2 : 1) * Rn * Kp * npad;
-      for (int i = tid; i < total; i += kLuBlock) tile[(i / npad) * CP + nclass + i % npad] = kLerpPad;
-    }
   }
   const float* stile = tile + (kc - xbase) * CP;           // (row 0, column kc) of the student view
   const float* ttile = stile + Rn * Kp * CP;
@@ -349,11 +334,10 @@ loss_up_kernel(const LossUpArgs a) {
     };
   };
 
-  Col cs;                                                    // student (top, dif): registers; teacher: shared memory
+  Col cs;                                                    // student (top, dif); the teacher's live only through a crossing
   float2 es[P], ss[P];                                       // 2^v of the current row and its per-row factor
   float2 et[KD ? P : 1], ts[KD ? P : 1];
   bool bigcell = false;                                      // this warp evaluates the cell's rows with MUFU.EX2
-  float tref2 = 0.f;
   float acc_kd = 0.f, acc_ce = 0.f, acc_cnt = 0.f;
   int cur_r0 = -1, cur_r1 = -1;
   const float sh_step = a.sh;
@@ -388,17 +372,10 @@ loss_up_kernel(const LossUpArgs a) {
         mx = fmax3(mx, fabsf(cs.dif[p].x), fabsf(cs.dif[p].y));
       }
       if constexpr (KD) {
-        Col ct;
-        ct.ref2 = tref2;
-        if (!fresh) {
-#pragma unroll
-          for (int p = 0; p < P; ++p) ct.top[p] = teaT[p * kLuBlock], ct.dif[p] = teaD[p * kLuBlock];
-        }
-        ct.enter(fresh, r0, r1, load_row(true));
-        tref2 = ct.ref2;
+        Col ct;                                              // re-based on its own cell: nothing carried between cells
+        ct.enter(true, r0, r1, load_row(true));
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          teaT[p * kLuBlock] = ct.top[p], teaD[p * kLuBlock] = ct.dif[p];
           const float2 u = ffma2(lseed, ct.dif[p], ct.top[p]), d = fmul2(stepv, ct.dif[p]);
           et[p] = make_float2(fast_ex2(u.x), fast_ex2(u.y));
           ts[p] = make_float2(fast_ex2(d.x), fast_ex2(d.y));
@@ -445,6 +422,8 @@ loss_up_kernel(const LossUpArgs a) {
       }
     } else {
       // exact path: MUFU.EX2 per class and row; EXACT re-bases on the per-pixel max (taken only after an underflow)
+      Col ct;
+      if constexpr (KD) ct.enter(true, cur_r0, cur_r1, load_row(true));
       auto stats = [&](auto exact_tag) {
         constexpr bool EXACT = decltype(exact_tag)::value;
         float mt = 0.f;
@@ -455,7 +434,7 @@ loss_up_kernel(const LossUpArgs a) {
             const float2 v = cs.value2(yl1v, p);
             ms = fmax3(ms, v.x, v.y);
             if constexpr (KD) {
-              const float2 u = ffma2(yl1v, teaD[p * kLuBlock], teaT[p * kLuBlock]);
+              const float2 u = ct.value2(yl1v, p);
               mt = fmax3(mt, u.x, u.y);
             }
           }
@@ -470,7 +449,7 @@ loss_up_kernel(const LossUpArgs a) {
           es[p] = make_float2(fast_ex2(v.x), fast_ex2(v.y));
           S2 = fadd2(S2, es[p]);
           if constexpr (KD) {
-            float2 u = ffma2(yl1v, teaD[p * kLuBlock], teaT[p * kLuBlock]);
+            float2 u = ct.value2(yl1v, p);
             if constexpr (EXACT) u = fadd2(u, nmt);
             et[p] = make_float2(fast_ex2(u.x), fast_ex2(u.y));
             T2 = fadd2(T2, et[p]);
