@@ -704,7 +704,7 @@ static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* d
     auto kernel = loss_up_kernel<kC, kPad, KD, CE, LOSS, GRAD>;
     static size_t configured_dev[64] = {0};            // per instantiation and device
     size_t& configured = configured_dev[device_slot()];
-    if (dyn > 16 * 1024 && configured < dyn) {           // static staging + dynamic tables can pass the 48 KB default
+    if (configured < dyn) {                              // static staging + dynamic tables can pass the 48 KB default
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("loss_up: cannot reserve %zu bytes of shared memory", dyn);
