@@ -140,6 +140,33 @@ __device__ __forceinline__ float fast_rcp(float x) {   // MUFU.RCP, 1 ulp
   return r;
 }
 
+// ---- packed single precision (sm_100: FFMA2 / FADD2 / FMUL2 — two IEEE fp32 operations per issue slot) ---------------
+// Every lane is one IEEE operation: results are bit-identical to the scalar instructions (the label kernels rely on it).
+#define DIGA_F32X2_3(name, op)                                                                                          \
+  __device__ __forceinline__ float2 name(float2 a, float2 b, float2 c) {                                               \
+    float2 d;                                                                                                          \
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t" op \
+        " rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                              \
+        : "=f"(d.x), "=f"(d.y)                                                                                         \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));                                                 \
+    return d;                                                                                                          \
+  }
+#define DIGA_F32X2_2(name, op)                                                                                          \
+  __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                         \
+    float2 d;                                                                                                          \
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" op                          \
+        " rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                                  \
+        : "=f"(d.x), "=f"(d.y)                                                                                         \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                                     \
+    return d;                                                                                                          \
+  }
+DIGA_F32X2_3(ffma2, "fma.rn.f32x2")
+DIGA_F32X2_2(fadd2, "add.rn.f32x2")
+DIGA_F32X2_2(fmul2, "mul.rn.f32x2")
+#undef DIGA_F32X2_3
+#undef DIGA_F32X2_2
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
 // First index of the maximum of v[0..C) (torch.max / np.argmax tie rule) as a pairwise tournament: in every comparison
 // the left operand covers the lower indices and the right one wins only if STRICTLY greater, so ties resolve to the lowest
 // index exactly like the left-to-right scan, but the dependency depth is log2(C) instead of C (the scan left the

@@ -86,33 +86,6 @@ struct LerpColumn {
   __device__ __forceinline__ float value(float l1, int c) const { return fmaf(l1, dif[c], top[c]); }
 };
 
-// ---- packed single precision (sm_100: FFMA2 / FADD2 / FMUL2 — two IEEE fp32 operations per issue slot) ---------------
-// The loss kernels are bound by issue slots, not by the FMA pipe: the per-class arithmetic runs on class PAIRS.
-#define DIGA_F32X2_3(name, op)                                                                                          \
-  __device__ __forceinline__ float2 name(float2 a, float2 b, float2 c) {                                               \
-    float2 d;                                                                                                          \
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t" op \
-        " rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                              \
-        : "=f"(d.x), "=f"(d.y)                                                                                         \
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));                                                 \
-    return d;                                                                                                          \
-  }
-#define DIGA_F32X2_2(name, op)                                                                                          \
-  __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                         \
-    float2 d;                                                                                                          \
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" op                          \
-        " rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                                  \
-        : "=f"(d.x), "=f"(d.y)                                                                                         \
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                                     \
-    return d;                                                                                                          \
-  }
-DIGA_F32X2_3(ffma2, "fma.rn.f32x2")
-DIGA_F32X2_2(fadd2, "add.rn.f32x2")
-DIGA_F32X2_2(fmul2, "mul.rn.f32x2")
-#undef DIGA_F32X2_3
-#undef DIGA_F32X2_2
-__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-
 // LerpColumn on class pairs (NP pairs = 2 NP class slots per thread).  A slot without a class (odd C, or c >= nclass in
 // the padded variant) is fed kLerpPad from both source rows: its value stays hugely negative (dif == 0 exactly, top
 // absorbs every re-basing), so its exponential is an exact zero and it never wins a maximum — no special case in the

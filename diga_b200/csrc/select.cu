@@ -86,8 +86,7 @@ consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseu
 #pragma unroll
     for (int v = 0; v < PX; ++v) {
       float val[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) val[c] = (!PAD || c < nclass) ? ci.value(ty, v, c) : -INFINITY;
+      ci.values(ty, v, nclass, val);
       float best;
       int arg;
       argmax_first<C>(val, best, arg);

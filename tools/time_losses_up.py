@@ -64,7 +64,7 @@ def main():
     tgt = S.block_labels(n2 // 2, hi[0], hi[1], g)
     up = torch.tensor(0.25, device=dev)
     one = torch.tensor(1.0, device=dev)
-    rys = [int(v) for v in os.environ.get("RYS", "16").split(",")]
+    rys = [int(v) for v in os.environ.get("RYS", "32").split(",")]
     for ry in rys:
         L.set_tunable("lossup_ry", ry)
         tag = {"ry": ry}
