@@ -575,7 +575,7 @@ def bench_stages(D, S, dev, peak, world):
     lowres_bytes = 3 * C * 4 * (h * w) / (hh * ww)          # teacher + student read, gradient written, per output pixel
     add("kd_fused_upsample_fwd_bwd", 8 * hh * ww, lowres_bytes, kd_up_step,
         extra={"note": "distillation_loss_upsampled + autograd from [8,19,65,129]: replaces 2 up-samplings (76 B/px written each), "
-                       "the 380 B/px KD pair and the up-sampling backward; ALU/MUFU-bound (38 ex2 per pixel-position)"})
+                       "the 380 B/px KD pair and the up-sampling backward; latency-bound walk (exponentials by one multiply per row inside a source cell, MUFU only at cell crossings)"})
     add("cross_entropy2d_fused_upsample_fwd_bwd", 4 * hh * ww, 8 + 2 * C * 4 * (h * w) / (hh * ww), ce_up_step)
     ohem = D.OhemCrossEntropy(255, 0.7, 100000)
 
@@ -742,7 +742,7 @@ def bench_stages(D, S, dev, peak, world):
     del pool4, sp, cf_exact
 
     # config 5: full-resolution pseudo-labels with prototype rectification.  The set is walked PER_CALL images per call (the
-    # persistent distance kernel fills whole rounds and the two arg-max kernels whole waves: 104.6 / 91.0 / 85.5 us per image
+    # persistent distance kernel fills whole rounds and the two arg-max kernels whole waves: 100.0 / 87.9 / 83.6 us per image
     # at 1 / 2 / 4 images per call, tools/time_config5_batch.py); the reference's batch-1 loop is timed beside it.
     PER_CALL = 4
     pool5 = [(S.features((PER_CALL, d, 129, 257), g), S.logits((PER_CALL, C, 129, 257), g), S.logits((PER_CALL, C, 65, 129), g))

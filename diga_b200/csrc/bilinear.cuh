@@ -14,8 +14,6 @@
 //     val     = fma(h0, top, h1 * bottom)                    FMUL, FFMA
 #pragma once
 
-#include "common.cuh"
-
 namespace diga {
 
 struct Tap {
@@ -50,18 +48,14 @@ __device__ __forceinline__ float bilinear_col(const Tap& ty, float top, float bo
 // next output row inside the same cell costs one FMUL + FFMA per class; crossing into the next cell re-uses `bot`
 // as the new `top` (same inputs, same expression => bit-identical) and interpolates one new source row.  The
 // values are exactly those of ATen's per-pixel expression (common sub-expressions are merely not recomputed).
-// The classes are held as PAIRS and interpolated with the packed FMUL2 / FFMA2 of sm_100 (common.cuh): each lane is the
-// same IEEE multiply / fused multiply-add as the scalar instruction, so the bit pattern is unchanged while the two
-// instructions per class and row become one.
 template <int C, bool PAD, int PX>
 struct ColumnInterp {
-  static constexpr int P = (C + 1) / 2;
-  float2 top[PX][P], bot[PX][P];
+  float top[PX][C], bot[PX][C];
   int i0 = -1, i1 = -1;
 
   // One pointer pair per pixel, bumped by `plane` per class: two 64-bit adds per class and pixel instead of a fresh
   // index -> address computation per load (the setup code was a third of the selection kernel's instructions).
-  __device__ __forceinline__ void row(float2 (&dst)[PX][P], const float* __restrict__ base, int64_t plane, int w, int r,
+  __device__ __forceinline__ void row(float (&dst)[PX][C], const float* __restrict__ base, int64_t plane, int w, int r,
                                       const Tap (&tx)[PX], int nclass) {
     const float* q0[PX];
     const float* q1[PX];
@@ -71,25 +65,15 @@ struct ColumnInterp {
       q1[v] = base + (int64_t)r * w + tx[v].i1;
     }
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
+    for (int c = 0; c < C; ++c)
+      if (!PAD || c < nclass) {
 #pragma unroll
-      for (int v = 0; v < PX; ++v) {
-        float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-        if (!PAD || 2 * p < nclass) {
-          a.x = __ldg(q0[v]);
-          b.x = __ldg(q1[v]);
+        for (int v = 0; v < PX; ++v) {
+          dst[v][c] = bilinear_row(tx[v], __ldg(q0[v]), __ldg(q1[v]));
           q0[v] += plane;
           q1[v] += plane;
         }
-        if (2 * p + 1 < C && (!PAD || 2 * p + 1 < nclass)) {
-          a.y = __ldg(q0[v]);
-          b.y = __ldg(q1[v]);
-          q0[v] += plane;
-          q1[v] += plane;
-        }
-        dst[v][p] = ffma2(splat2(tx[v].l0), a, fmul2(splat2(tx[v].l1), b));      // bilinear_row on both lanes
       }
-    }
   }
 
   __device__ __forceinline__ void seek(const Tap& ty, const float* __restrict__ base, int64_t plane, int w, const Tap (&tx)[PX],
@@ -97,17 +81,17 @@ struct ColumnInterp {
     if (ty.i0 == i0 && ty.i1 == i1) return;
     if (ty.i0 == i1 && i1 >= 0) {
 #pragma unroll
-      for (int p = 0; p < P; ++p)
+      for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int v = 0; v < PX; ++v) top[v][p] = bot[v][p];
+        for (int v = 0; v < PX; ++v) top[v][c] = bot[v][c];
     } else if (ty.i0 != i0) {
       row(top, base, plane, w, ty.i0, tx, nclass);
     }
     if (ty.i1 == ty.i0) {
 #pragma unroll
-      for (int p = 0; p < P; ++p)
+      for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int v = 0; v < PX; ++v) bot[v][p] = top[v][p];
+        for (int v = 0; v < PX; ++v) bot[v][c] = top[v][c];
     } else {
       row(bot, base, plane, w, ty.i1, tx, nclass);
     }
@@ -115,19 +99,7 @@ struct ColumnInterp {
     i1 = ty.i1;
   }
 
-  // the interpolated values of classes (2p, 2p + 1) of pixel v: bilinear_col on both lanes
-  __device__ __forceinline__ float2 value2(const Tap& ty, int v, int p) const {
-    return ffma2(splat2(ty.l0), top[v][p], fmul2(splat2(ty.l1), bot[v][p]));
-  }
-  // all classes of pixel v into z[0..C) (-inf for c >= nclass in the padded variant)
-  __device__ __forceinline__ void values(const Tap& ty, int v, int nclass, float (&z)[C]) const {
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float2 val = value2(ty, v, p);
-      z[2 * p] = (!PAD || 2 * p < nclass) ? val.x : -INFINITY;
-      if (2 * p + 1 < C) z[2 * p + 1] = (!PAD || 2 * p + 1 < nclass) ? val.y : -INFINITY;
-    }
-  }
+  __device__ __forceinline__ float value(const Tap& ty, int v, int c) const { return bilinear_col(ty, top[v][c], bot[v][c]); }
 };
 
 }  // namespace diga

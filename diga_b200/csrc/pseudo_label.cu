@@ -156,12 +156,14 @@ pseudo_label_upsampled_kernel(const float* __restrict__ z1, int h1, int w1, floa
       c2.seek(ty2, b2, pl2, w2, tx2, nclass);
     }
     float z[C];
-    c1.values(ty1, 0, nclass, z);
-    if constexpr (HAS2) {                                             // torch.max(output_ds, output), :80
-      float zb[C];
-      c2.values(ty2, 0, nclass, zb);
 #pragma unroll
-      for (int c = 0; c < C; ++c) z[c] = fmaxf(z[c], zb[c]);
+    for (int c = 0; c < C; ++c) {
+      float val = -INFINITY;
+      if (!PAD || c < nclass) {
+        val = c1.value(ty1, 0, c);
+        if constexpr (HAS2) val = fmaxf(val, c2.value(ty2, 0, c));   // torch.max(output_ds, output), :80
+      }
+      z[c] = val;
     }
     float m;
     int am;

@@ -60,9 +60,9 @@ __device__ __forceinline__ void store_px(T* __restrict__ p, const int64_t (&src)
 }
 
 template <int C, bool PAD, int PX, int BLOCK, typename T>
-__global__ void __launch_bounds__(BLOCK)
-consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseudo, int nclass, int h, int w, int H,
-                        int W, float sh, float sw, int RY, T* __restrict__ kept, T* __restrict__ feat_pseudo) {
+__device__ __forceinline__ void consensus_select_body(const float* __restrict__ wl, const T* __restrict__ pseudo, int nclass, int h, int w,
+                                                      int H, int W, float sh, float sw, int RY, T* __restrict__ kept,
+                                                      T* __restrict__ feat_pseudo) {
   const int64_t img = blockIdx.z;
   const int Y0 = blockIdx.y * RY;
   const int X0 = (blockIdx.x * BLOCK + threadIdx.x) * PX;
@@ -86,7 +86,8 @@ consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseu
 #pragma unroll
     for (int v = 0; v < PX; ++v) {
       float val[C];
-      ci.values(ty, v, nclass, val);
+#pragma unroll
+      for (int c = 0; c < C; ++c) val[c] = (!PAD || c < nclass) ? ci.value(ty, v, c) : -INFINITY;
       float best;
       int arg;
       argmax_first<C>(val, best, arg);
@@ -101,6 +102,21 @@ consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseu
 #pragma unroll
     for (int v = 0; v < PX; ++v) lab[v] = nxt[v];
   }
+}
+
+template <int C, bool PAD, int PX, int BLOCK, typename T>
+__global__ void __launch_bounds__(BLOCK)
+consensus_select_kernel(const float* __restrict__ wl, const T* __restrict__ pseudo, int nclass, int h, int w, int H, int W, float sh,
+                        float sw, int RY, T* __restrict__ kept, T* __restrict__ feat_pseudo) {
+  consensus_select_body<C, PAD, PX, BLOCK, T>(wl, pseudo, nclass, h, w, H, W, sh, sw, RY, kept, feat_pseudo);
+}
+// uint8 labels, two columns per thread (config 5, the PNG path): left alone the compiler takes 136 registers, i.e. three CTAs
+// per SM; capped at 128 it fits a fourth without spilling.
+template <int C, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 4)
+consensus_select_u8x2_kernel(const float* __restrict__ wl, const uint8_t* __restrict__ pseudo, int nclass, int h, int w, int H, int W,
+                             float sh, float sw, int RY, uint8_t* __restrict__ kept, uint8_t* __restrict__ feat_pseudo) {
+  consensus_select_body<C, false, 2, BLOCK, uint8_t>(wl, pseudo, nclass, h, w, H, W, sh, sw, RY, kept, feat_pseudo);
 }
 
 }  // namespace diga
@@ -131,8 +147,12 @@ static int consensus_select_impl(const float* weights_lowres, const T* pseudo, i
   DIGA_DISPATCH_C(C, {
     if (two) {
       dim3 grid((unsigned)((W / 2 + BLOCK - 1) / BLOCK), gy, (unsigned)B);
-      consensus_select_kernel<kC, kPad, 2, BLOCK, T><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
-                                                                            (int)W, sh, sw, RY, kept, feat_pseudo);
+      if constexpr (sizeof(T) == 1 && !kPad)
+        consensus_select_u8x2_kernel<kC, BLOCK><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H, (int)W, sh,
+                                                                        sw, RY, kept, feat_pseudo);
+      else
+        consensus_select_kernel<kC, kPad, 2, BLOCK, T><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
+                                                                              (int)W, sh, sw, RY, kept, feat_pseudo);
     } else {
       dim3 grid((unsigned)((W + BLOCK - 1) / BLOCK), gy, (unsigned)B);
       consensus_select_kernel<kC, kPad, 1, BLOCK, T><<<grid, BLOCK, 0, st>>>(weights_lowres, pseudo, (int)C, (int)h, (int)w, (int)H,
