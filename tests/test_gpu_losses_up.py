@@ -248,3 +248,65 @@ def test_weighted_total_single_pass(D, n2, c, lo, hi):
         with torch.no_grad():
             t2, _, _ = D.seg_distillation_total_upsampled(tea, stu, tgt, lam_s, lam_d, 0.5, weight, avg)
         assert torch.equal(t2, total.detach())
+
+
+@pytest.mark.parametrize("sigma", [8.0, 20.0, 60.0, 300.0])
+@pytest.mark.parametrize("n2,c,lo,hi", [GEOMS[1], GEOMS[2], GEOMS[4]])
+def test_wide_logit_ranges_take_the_exact_paths(D, n2, c, lo, hi, sigma):
+    """csrc/loss_up.cu advances the exponentials by one multiply per row only while |dif| <= 24 inside a warp's source cell;
+    wider cells are evaluated with ex2 per row (sigma 8: a mix of both; 20: nearly every cell), and rows more than 41 logits
+    apart re-base on the per-pixel max (sigma 60, 300).  Every regime against the fp64 chain of the reference statements."""
+    tea, stu, g = inputs(n2, c, lo, 23, sigma)
+    tgt = labels(n2 // 2, hi, c, g)
+    s1 = stu.clone().requires_grad_(True)
+    l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s1, tgt, 0.5)
+    (1.0 * l_ce + 0.25 * l_kd).backward()
+    s2 = stu.double().cpu().requires_grad_(True)
+    r_ce, r_kd = O.seg_distillation_losses_upsampled(tea.double().cpu(), s2, tgt.cpu(), 0.5)
+    (1.0 * r_ce + 0.25 * r_kd).backward()
+    assert torch.isfinite(l_ce) and torch.isfinite(l_kd) and torch.isfinite(s1.grad).all()
+    rel(l_ce, r_ce, f"ce, sigma {sigma}")
+    rel(l_kd, r_kd, f"kd, sigma {sigma}")
+    normwise(s1.grad, s2.grad, f"grad, sigma {sigma}")
+
+
+def test_one_confident_class_next_to_flat_rows(D):
+    """A cell whose top row is flat and whose bottom row has one class 100 logits up: the re-based exact pass inside an
+    otherwise ordinary map (the warp votes, so its neighbours go through the same pass)."""
+    n2, c, lo, hi = 2, 19, (9, 13), (64, 96)
+    tea, stu, g = inputs(n2, c, lo, 29, 1.0)
+    stu[:, 3, 4, :] += 100.0
+    tea[:, 7, 5, 2:9] -= 150.0
+    tgt = labels(1, hi, c, g)
+    s1 = stu.clone().requires_grad_(True)
+    l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s1, tgt, 0.25)
+    (l_ce + l_kd).backward()
+    s2 = stu.double().cpu().requires_grad_(True)
+    r_ce, r_kd = O.seg_distillation_losses_upsampled(tea.double().cpu(), s2, tgt.cpu(), 0.25)
+    (r_ce + r_kd).backward()
+    rel(l_ce, r_ce, "ce")
+    rel(l_kd, r_kd, "kd")
+    normwise(s1.grad, s2.grad, "grad")
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", [GEOMS[0], GEOMS[2], GEOMS[4], GEOMS[5]])
+def test_source_rows_from_global_memory_equal_the_shared_memory_tile(D, n2, c, lo, hi):
+    """Geometries whose source tile would not fit in shared memory read the rows from global memory (forced here through
+    the `lossup_tile` tunable): same expressions, bit-equal losses and gradients."""
+    from diga_b200 import _lib as L
+    tea, stu, g = inputs(n2, c, lo, 31)
+    tgt = labels(n2 // 2, hi, c, g)
+
+    def run():
+        s = stu.clone().requires_grad_(True)
+        l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s, tgt, 0.5)
+        (l_ce + 0.3 * l_kd).backward()
+        return l_ce.detach(), l_kd.detach(), s.grad
+
+    a = run()
+    L.set_tunable("lossup_tile", 0)
+    try:
+        b = run()
+    finally:
+        L.set_tunable("lossup_tile", 1)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
