@@ -320,3 +320,60 @@ def test_png_table_constants_match_the_fixture():
     assert nbits == len(fix["header_bits"])
     assert "".join(str((words[i // 32] >> (i % 32)) & 1) for i in range(nbits)) == fix["header_bits"]
     assert int(re.search(r"kPngMaxLitBits = (\d+)", src).group(1)) == max(lengths[:256])
+
+
+def test_png_crc_combine_constants_and_operator():
+    """csrc/png.cu joins the CRC-32 remainders of 256 byte ranges with x^(8 n) mod P (zlib's crc32_combine construction).  The
+    kernel's constants `kCrcX2n[k] = x^(2^k) mod P` are re-derived here by squaring in GF(2)[x]/P, and the operator itself
+    (restated in Python) must reproduce zlib.crc32 over a split message for every split point class."""
+    import re
+    import zlib
+    POLY = 0xEDB88320
+
+    def multmodp(a, b):
+        p, m = 0, 1 << 31
+        while True:
+            if a & m:
+                p ^= b
+                if (a & (m - 1)) == 0:
+                    break
+            m >>= 1
+            if m == 0:
+                break
+            b = (b >> 1) ^ POLY if b & 1 else b >> 1
+        return p
+
+    want = [1 << 30]
+    for _ in range(31):
+        want.append(multmodp(want[-1], want[-1]))
+    src = open(os.path.join(ROOT, "diga_b200", "csrc", "png.cu")).read()
+    body = re.search(r"kCrcX2n\[32\]\s*=\s*\{(.*?)\};", src, re.S).group(1)
+    body = re.sub(r"//[^\n]*", "", body)
+    got = [int(v.rstrip("u"), 16) for v in re.findall(r"0x[0-9a-fA-F]+u?", body)]
+    assert got == want
+
+    def x8n(nbytes):                      # x^(8 nbytes) mod P from the table, as crc_x8n() in the kernel
+        p, k, n = 1 << 31, 3, nbytes
+        while n:
+            if n & 1:
+                p = multmodp(want[k & 31], p)
+            n >>= 1
+            k += 1
+        return p
+
+    def raw(data):                        # CRC register without the pre / post conditioning
+        c = 0
+        for byte in data:
+            c ^= byte
+            for _ in range(8):
+                c = (c >> 1) ^ POLY if c & 1 else c >> 1
+        return c
+
+    rng = np.random.default_rng(9)
+    msg = rng.integers(0, 256, 700, dtype=np.uint8).tobytes()
+    for cut in (0, 1, 4, 255, 256, 699, 700):
+        a, b = msg[:cut], msg[cut:]
+        joined = multmodp(x8n(len(b)), raw(a)) ^ raw(b)
+        assert joined == raw(msg)
+    total = raw(msg) ^ multmodp(x8n(len(msg)), 0xFFFFFFFF) ^ 0xFFFFFFFF
+    assert total == zlib.crc32(msg)
