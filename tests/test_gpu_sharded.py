@@ -237,6 +237,42 @@ def test_long_update_kernel_matches_short_kernel(D):
     assert torch.equal(one.objective_vectors, many.objective_vectors)
 
 
+@pytest.mark.parametrize("start", [0.0, 2990.0, 17.5])
+def test_long_update_division_is_ieee_for_every_count_and_magnitude(D, start):
+    """The whole-pass kernel against the short kernel on the same rows: 3100 rows in 'mean' mode walk every divisor 1..3001
+    (then the clamp), on vectors from 1e-30 to 1e30 with zeros, negative zeros and infinities mixed in, from integer and
+    non-integer start counts.  Bit-equal centroids and counts.  (Written for an experiment that took the reciprocal of
+    `num + 1` off the per-channel chain — exact, but not faster, DESIGN.md §8 — and kept as a guard of the replay.)"""
+    from diga_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(41)
+    n, c, d = 3100, 3, 320
+    mag = torch.exp(torch.empty((n, c, d), device="cuda").uniform_(-69.0, 69.0, generator=g))
+    vec = mag * torch.where(torch.rand((n, c, d), device="cuda", generator=g) < 0.5, -1.0, 1.0)
+    r = torch.rand((n, c, d), device="cuda", generator=g)
+    vec[r < 0.02] = 0.0
+    vec[(r >= 0.02) & (r < 0.03)] = -0.0
+    vec[:, 2, :7] = float("inf")                                    # one class sees infinities in a few channels
+    vec[:, 1] = torch.randn((n, d), device="cuda", generator=g)      # and one class ordinary values
+    vecsum = torch.ones((n, c), device="cuda")
+    vecsum[torch.rand((n, c), device="cuda", generator=g) < 0.05] = 0.0          # skipped rows
+    valid = torch.ones((n, c), dtype=torch.uint8, device="cuda")
+
+    def run(chunks):
+        obj = torch.zeros((c, d), device="cuda")
+        num = torch.full((c,), start, device="cuda")
+        for lo, hi in chunks:
+            L.check(L.lib.diga_centroid_update(vec[lo:hi].data_ptr(), vecsum[lo:hi].data_ptr(), valid[lo:hi].data_ptr(), hi - lo, c, d,
+                                               obj.data_ptr(), num.data_ptr(), L.UPDATE_MEAN, 0, 1e-4, L.stream()))
+        return obj, num
+
+    short = run([(i, min(i + 32, n)) for i in range(0, n, 32)])      # <= 32 rows per call: the short kernel
+    long_ = run([(0, n)])
+    assert torch.equal(short[1], long_[1])
+    same = (short[0] == long_[0]) | (torch.isnan(short[0]) & torch.isnan(long_[0]))
+    assert bool(same.all()), f"{int((~same).sum())} of {same.numel()} centroid entries differ"
+    assert torch.equal(short[0].view(torch.int32)[~torch.isnan(short[0])], long_[0].view(torch.int32)[~torch.isnan(long_[0])])
+
+
 NCCL_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
