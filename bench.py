@@ -742,9 +742,9 @@ def bench_stages(D, S, dev, peak, world):
     del pool4, sp, cf_exact
 
     # config 5: full-resolution pseudo-labels with prototype rectification.  The set is walked PER_CALL images per call (the
-    # persistent distance kernel fills whole rounds and the two arg-max kernels whole waves: 100.0 / 87.9 / 83.6 us per image
-    # at 1 / 2 / 4 images per call, tools/time_config5_batch.py); the reference's batch-1 loop is timed beside it.
-    PER_CALL = 4
+    # persistent distance kernel fills whole rounds and the two arg-max kernels whole waves: 100.3 / 88.2 / 83.3 / 79.6 us per image
+    # at 1 / 2 / 4 / 8 images per call, tools/time_config5_batch.py); the reference's batch-1 loop is timed beside it.
+    PER_CALL = 8
     pool5 = [(S.features((PER_CALL, d, 129, 257), g), S.logits((PER_CALL, C, 129, 257), g), S.logits((PER_CALL, C, 65, 129), g))
              for _ in range(3)]
 
@@ -772,7 +772,7 @@ def bench_stages(D, S, dev, peak, world):
         "frac_hbm": mine * ((d * 4 + C * 4) * 129 * 257 + 3 * px5) / (ms5 * 1e-3) / 1e9 / peak,
         "ms_one_image_per_call": ms5_one,
         "note": "pseudolabel_generator.py:69-85 + the rectification of self_training.py:298-304: fused two-scale labels, "
-                "prototype weights of [4,2048,129,257], consensus selection, 4 images per call (ms_one_image_per_call = the "
+                "prototype weights of [8,2048,129,257], consensus selection, 8 images per call (ms_one_image_per_call = the "
                 "reference's batch-1 loop); no collective (image-sharded)"}
     # config 5 end to end INCLUDING the files (pseudolabel_generator.py:89-105): the kept maps go to 'P'-mode PNGs on local
     # disk through PseudoLabelWriter; wall clock from the first kernel to the last closed file.  The GPU encoder runs over
@@ -832,7 +832,7 @@ def bench_stages(D, S, dev, peak, world):
                            "file_bytes_per_image": size_p, "d2h_bytes_per_image": d2h_p},
         "speedup_vs_pillow_encoder": (ms_p / n_pil) / (ms_g / mine),
         "note": "config 5 per image + the PNG file: zlib stream made on the GPU (csrc/png.cu: Up filter, run tokens, fixed "
-                "Huffman, IDAT CRC-32), 4 images per label call and 8 maps per encoder call, host threads only frame and write; wall clock incl. file I/O (tmpfs when available).  The synthetic "
+                "Huffman, IDAT CRC-32), 8 images per label call and 8 maps per encoder call, host threads only frame and write; wall clock incl. file I/O (tmpfs when available).  The synthetic "
                 "label maps (arg-max of up-sampled random logits) are noise-like, the worst case for a run-length encoder; "
                 "pillow_encoder = the same pipeline with the reference's Image.save on the host threads"}
     del pool5

@@ -3,9 +3,9 @@
 # and of the config-3 step, the loss timings, and compute-sanitizer over the rewritten loss / label kernels.
 set -u
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_c.json 2> gpurun_out/r02_bench_n1_c.err
-tail -c 400 gpurun_out/r02_bench_n1_c.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_n1_c_reference_arm.json 2>/dev/null
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_d.json 2> gpurun_out/r02_bench_n1_d.err
+tail -c 400 gpurun_out/r02_bench_n1_d.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_n1_d_reference_arm.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r02_bench_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_step3_launches.csv \

@@ -1,4 +1,4 @@
-"""Config 5 per image at 1, 2 and 4 images per call (labels from the two-scale logits, prototype weights of
+"""Config 5 per image at 1, 2, 4 and 8 images per call (labels from the two-scale logits, prototype weights of
 [n,2048,129,257], consensus selection on the uint8 maps): CUDA-event time per image over 240 images."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ dev = torch.device("cuda", 0)
 g = S.gen(3, dev)
 cf = D.Class_Features(19, 2048)
 cf.objective_vectors = S.centroids(19, 2048, g)
-for n in (1, 2, 4):
+for n in (1, 2, 4, 8):
     pool = [(S.features((n, 2048, 129, 257), g), S.logits((n, 19, 129, 257), g), S.logits((n, 19, 65, 129), g)) for _ in range(3)]
 
     def run(calls):
