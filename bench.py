@@ -149,6 +149,34 @@ def bind_to_gpu_numa_node(index: int):
     return info
 
 
+def launch_pairs_ms(launch, iters, warm=3, tries=3):
+    """Average duration of one launch: a CUDA event pair around every launch on the launching stream.  The stream is first
+    gated with a ~3 ms spin kernel so that every pair is already queued when the GPU reaches the first one (an event pair
+    otherwise also times whatever the host does between ``record`` and the launch: one scheduler hiccup of the Python thread
+    inside a pair is worth ten launches).  A try whose slowest pair exceeds 1.5x its median is repeated (at most ``tries``);
+    the try with the lowest mean is returned together with what was seen."""
+    for i in range(warm):
+        launch(i)
+    best = None
+    for t in range(tries):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        torch.cuda.synchronize()
+        torch.cuda._sleep(6_000_000)
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            launch(i)
+            b.record()
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        cur = {"mean_ms": statistics.mean(ts), "median_ms": statistics.median(ts), "max_ms": max(ts), "launches": iters, "tries": t + 1}
+        if best is None or cur["mean_ms"] < best["mean_ms"]:
+            best = dict(cur)
+        best["tries"] = t + 1
+        if cur["max_ms"] <= 1.5 * cur["median_ms"]:
+            break
+    return best["mean_ms"], best
+
+
 def time_loop(fn, iters, warmup, world=1, device=None, graph=False):
     """CUDA-event timing of ``iters`` calls, barrier + synchronize on both sides, max over ranks -> ms per call.
     ``graph=True`` captures one call (a sync-free public-API call) in a CUDA graph and times its replays, which removes
@@ -370,18 +398,9 @@ def accum_kernel_rows(L, S, dev, peak):
             L.check(L.lib.diga_centroid_accum(feats[i % 3].data_ptr(), cls.data_ptr(), counts.data_ptr(), clsw.data_ptr(), n, d, C, hw,
                                               sums.data_ptr(), st))
 
-        for i in range(3):
-            launch(i)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
-        torch.cuda.synchronize()
-        for i, (a, b) in enumerate(evs):
-            a.record()
-            launch(i)
-            b.record()
-        torch.cuda.synchronize()
-        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        ms, _ = launch_pairs_ms(launch, 30)
         rows.append(("a6", f"centroid_accum_lean_kernel ({'i.i.d. classes' if pattern == 'iid' else '4x4-block class maps'})", "hbm",
-                     "feature-px", n * hw, d * 4 + 1, ms, "CUDA event pair per launch, C-ABI launches queued back to back, 3 rotating 550 MB inputs",
+                     "feature-px", n * hw, d * 4 + 1, ms, "CUDA event pair per launch, C-ABI launches queued behind a spin-kernel gate, 3 rotating 550 MB inputs",
                      "accum_dram_bytes_per_launch" if pattern == "iid" else None))
     return rows
 
@@ -948,20 +967,7 @@ def main():
         L.check(L.lib.diga_kd_fwd_bwd(t.data_ptr(), s.data_ptr(), n2, C, hw_px, 0.5, UPSTREAM, loss_buf.data_ptr(),
                                       ds_buf.data_ptr(), kd_ws.data_ptr(), st))
 
-    def kernel_ms(launch, iters=K_eager, warm=3):
-        """Average launch duration: one CUDA event pair per launch on the launching stream, launches queued back to back."""
-        for i in range(warm):
-            launch(i)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        torch.cuda.synchronize()
-        for i, (a, b) in enumerate(evs):
-            a.record()
-            launch(i)
-            b.record()
-        torch.cuda.synchronize()
-        return statistics.mean(a.elapsed_time(b) for a, b in evs)
-
-    fwd_ms, bwd_ms, fused_ms = kernel_ms(kd_fwd_launch), kernel_ms(kd_bwd_launch), kernel_ms(kd_fused_launch)
+    (fwd_ms, _), (bwd_ms, bwd_seen), (fused_ms, _) = (launch_pairs_ms(f, K_eager) for f in (kd_fwd_launch, kd_bwd_launch, kd_fused_launch))
     del ds_buf
 
     # ---- timed region 2 (headline): the same API calls captured once per input set in CUDA graphs and replayed ----
@@ -1162,7 +1168,7 @@ def main():
                 r.update(extra)
             return r
 
-        ev_how = "CUDA event pair per launch, C-ABI launches queued back to back, rotating inputs >> L2"
+        ev_how = "CUDA event pair per launch, C-ABI launches queued behind a spin-kernel gate, rotating inputs >> L2"
         gr_how = "public-API call replayed from a CUDA graph (CUDA events around 20 replays)"
         rows = [
             row("a1", "kd_kernel<LOSS> (forward)", "hbm", "pixel-position", px_step, KD_BYTES_FWD, fwd_ms, ev_how, "kd_fwd_dram_bytes_per_launch"),
@@ -1213,7 +1219,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "kd_kernel<GRAD> (backward)", "achieved": bwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algo_bytes_per_launch": px_step * KD_BYTES_BWD, "avg_launch_ms": bwd_ms,
-                         "frac_of_8000_spec": bwd_gbs / 8000.0, "rows": rows},
+                         "frac_of_8000_spec": bwd_gbs / 8000.0, "launch_timing": bwd_seen,
+                         "share_of_step": bwd_ms / ms_step, "rows": rows},
             "eager_ms_per_step": eager_ms_step,
             "gpu_launches": launches, "clocks": clocks.summary(), "e2e": e2e, "stages": stages, "cpu_baseline": cpu,
         }
