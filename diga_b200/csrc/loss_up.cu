@@ -101,6 +101,7 @@ struct LossUpArgs {
   float* loss_kd;
   float* loss_ce;
   float* denom_out;
+  float* loss_total;       // single-pass KD + CE variant: up_ce_host * loss_ce + up_kd_host * loss_kd (:356,:382), or null
 };
 
 __device__ __forceinline__ int lu_swz(int x) { return x + (x >> 3); }
@@ -580,6 +581,11 @@ loss_up_kernel(const LossUpArgs a) {
           const float cnt = (float)dr[2][0], tot = (float)(dr[1][0] * 0.6931471805599453);
           if (a.loss_ce) a.loss_ce[0] = a.size_average ? tot / cnt : tot;   // fp32 division like `loss /= mask.data.sum()`
           if (a.denom_out) a.denom_out[0] = cnt;
+          if constexpr (KD && LOSS && GRAD) {                // the weighted sum the call site would form with three scalar ops
+            if (a.loss_total)
+              a.loss_total[0] = __fadd_rn(__fmul_rn(a.up_ce_host, a.size_average ? tot / cnt : tot),
+                                          __fmul_rn(a.up_kd_host, (float)(dr[0][0] * 0.6931471805599453 * (double)a.inv_count_kd)));
+          }
         }
         *a.ticket = 0;                                       // leave the workspace ready for the next launch
       }
@@ -679,6 +685,27 @@ count_targets_kernel(const int64_t* __restrict__ target, int64_t total, unsigned
       denom_out[0] = (float)atomicExch(&counter[0], 0ull);
       counter[1] = 0ull;
     }
+  }
+}
+
+// out = x * (num / den) (den null: x * num) with the scalars read on the device: the backward of the single-pass losses scales the
+// gradient the forward left behind by the upstream scalar (and 1 / #(target >= 0)).  Same fp32 operations, in the same order,
+// as the tensor expression `x * (g / denom)` it replaces.
+__global__ void __launch_bounds__(256)
+scale_by_scalars_kernel(const float* __restrict__ x, const float* __restrict__ num, const float* __restrict__ den, int64_t n,
+                        float* __restrict__ out, int vec) {
+  const float coef = den ? __fdiv_rn(num[0], den[0]) : num[0];
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  if (vec) {
+    const int64_t n4 = n / 4;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+      v.x = __fmul_rn(v.x, coef), v.y = __fmul_rn(v.y, coef), v.z = __fmul_rn(v.z, coef), v.w = __fmul_rn(v.w, coef);
+      reinterpret_cast<float4*>(out)[i] = v;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn(x[i], coef);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn(x[i], coef);
   }
 }
 
@@ -849,7 +876,7 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
                            int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
-                           float* denom_out, float* dstudent_low, void* workspace, diga_stream_t stream) {
+                           float* denom_out, float* loss_total, float* dstudent_low, void* workspace, diga_stream_t stream) {
   using namespace diga;
   if (int rc = check_common("seg_kd_up_fwd_bwd", student_low, n2, C, h, w, H, W, workspace)) return rc;
   DIGA_REQUIRE(teacher_low && target && loss_kd && loss_ce && denom_out && dstudent_low && (n2 % 2) == 0 && n_ce >= 1 && n_ce <= n2,
@@ -875,7 +902,24 @@ int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, c
   a.loss_kd = loss_kd;
   a.loss_ce = loss_ce;
   a.denom_out = denom_out;                                // rewritten with the same value by the loss reduction
+  a.loss_total = loss_total;
   return launch_loss_up<true, true, true, true>(a, p, C, dstudent_low, st);
+}
+
+int diga_scale_by_scalars(const float* x, const float* num, const float* den, int64_t n, float* out, diga_stream_t stream) {
+  using namespace diga;
+  DIGA_REQUIRE(n >= 0 && (n == 0 || (x && out)) && num, DIGA_ERR_INVALID, "scale_by_scalars: null pointer or negative size");
+  DIGA_REQUIRE(aligned(x, 4) && aligned(out, 4) && aligned(num, 4) && aligned(den, 4), DIGA_ERR_MISALIGNED,
+               "scale_by_scalars: misaligned pointer");
+  if (n == 0) return DIGA_OK;
+  const int vec = aligned(x, 16) && aligned(out, 16);
+  int64_t grid = ((vec ? n / 4 : n) + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  scale_by_scalars_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, num, den, n, out, vec);
+  DIGA_CHECK_LAUNCH("scale_by_scalars_kernel");
+  return DIGA_OK;
 }
 
 /* OhemCrossEntropy backward (csrc/ohem_up.cu holds the forward): the CE gradient pass restricted to the kept pixels

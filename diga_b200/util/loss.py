@@ -156,11 +156,11 @@ class _LossesUpsampled(torch.autograd.Function):
         hh, ww = size
         n_ce = 0 if tg is None else tg.shape[0]
         dev = s.device
+        ctx.set_materialize_grads(False)               # an unused loss arrives as None in backward, not as a zeros() launch
         new = lambda: torch.empty((), dtype=torch.float32, device=dev)
-        zero = lambda: torch.zeros((), dtype=torch.float32, device=dev)
-        loss_kd = zero() if t is None else new()
-        loss_ce = zero() if tg is None else new()
-        denom = torch.ones((), dtype=torch.float32, device=dev)
+        loss_kd = None if t is None else new()         # the switched-off loss is None (no fill kernel for a value nobody reads)
+        loss_ce = None if tg is None else new()
+        denom = None if tg is None else new()          # written by the kernel whenever CE is on
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
         size_average = int(bool(size_average))
         unit = None
@@ -176,8 +176,8 @@ class _LossesUpsampled(torch.autograd.Function):
             ctx.save_for_backward(unit, denom)
         else:
             L.check(L.lib.diga_loss_up_fwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww,
-                                           float(scale), size_average, loss_kd.data_ptr(), loss_ce.data_ptr(),
-                                           denom.data_ptr(), ws.data_ptr(), L.stream()))
+                                           float(scale), size_average, L.ptr(loss_kd), L.ptr(loss_ce),
+                                           L.ptr(denom), ws.data_ptr(), L.stream()))
             ctx.save_for_backward(s, denom)
         ctx.aux = (t, tg, wt, (hh, ww), float(scale), size_average, n_ce, unit is not None)
         return loss_ce, loss_kd
@@ -188,18 +188,33 @@ class _LossesUpsampled(torch.autograd.Function):
         t, tg, wt, (hh, ww), scale, size_average, n_ce, have_unit = ctx.aux
         n, c, h, w = s.shape
         dev = s.device
-        as_scalar = lambda g: (torch.zeros((), dtype=torch.float32, device=dev) if g is None
-                               else g.to(dtype=torch.float32, device=dev).contiguous())
+        as_scalar = lambda g: None if g is None else g.to(dtype=torch.float32, device=dev).contiguous()
         g_ce, g_kd = as_scalar(g_ce), as_scalar(g_kd)                 # 0-dim device scalars, read on the GPU
         if have_unit:                                                 # `s` is the unit gradient saved by the forward
-            coef = g_kd if tg is None else (g_ce / denom if size_average else g_ce)
-            return None, s * coef, None, None, None, None, None
+            g = g_kd if tg is None else g_ce
+            if g is None:
+                return None, None, None, None, None, None, None
+            return None, _scaled(s, g, denom if (tg is not None and size_average) else None), None, None, None, None, None
+        if g_ce is None and g_kd is None:
+            return None, None, None, None, None, None, None
+        zero = None
+        if (t is not None and g_kd is None) or (tg is not None and g_ce is None):   # one of two live losses left out of the graph
+            zero = torch.zeros((), dtype=torch.float32, device=dev)
         ds = torch.empty_like(s)
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
         L.check(L.lib.diga_loss_up_bwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww, scale,
-                                       size_average, g_kd.data_ptr(), g_ce.data_ptr(), denom.data_ptr(), ds.data_ptr(),
+                                       size_average, L.ptr(zero if (t is not None and g_kd is None) else g_kd),
+                                       L.ptr(zero if (tg is not None and g_ce is None) else g_ce), L.ptr(denom), ds.data_ptr(),
                                        ws.data_ptr(), L.stream()))
         return None, ds, None, None, None, None, None
+
+
+def _scaled(x, num, den=None):
+    """``x * (num / den)`` (``den`` None: ``x * num``) with 0-dim device scalars, one launch (diga_scale_by_scalars) with the
+    same fp32 roundings as the tensor expression."""
+    out = torch.empty_like(x)
+    L.check(L.lib.diga_scale_by_scalars(x.data_ptr(), num.data_ptr(), L.ptr(den), x.numel(), out.data_ptr(), L.stream()))
+    return out
 
 
 def _check_low(student_low, size, what):
@@ -279,27 +294,31 @@ class _SegDistillationTotal(torch.autograd.Function):
         n, c, h, w = s.shape
         hh, ww = size
         dev = s.device
+        ctx.set_materialize_grads(False)
         loss_kd, loss_ce, denom = (torch.empty((), dtype=torch.float32, device=dev) for _ in range(3))
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
         if ctx.needs_input_grad[1]:
             ds = torch.empty_like(s)
+            total = torch.empty((), dtype=torch.float32, device=dev)     # written by the kernel's last CTA: no scalar launches
             L.check(L.lib.diga_seg_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w,
                                                  hh, ww, float(scale), int(bool(size_average)), float(lambda_seg),
                                                  float(lambda_distil), loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(),
-                                                 ds.data_ptr(), ws.data_ptr(), L.stream()))
+                                                 total.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
             ctx.save_for_backward(ds)
         else:
             L.check(L.lib.diga_loss_up_fwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w, hh, ww,
                                            float(scale), int(bool(size_average)), loss_kd.data_ptr(), loss_ce.data_ptr(),
                                            denom.data_ptr(), ws.data_ptr(), L.stream()))
-        total = lambda_seg * loss_ce + lambda_distil * loss_kd
+            total = lambda_seg * loss_ce + lambda_distil * loss_kd
         ctx.mark_non_differentiable(loss_ce, loss_kd)
         return total, loss_ce, loss_kd
 
     @staticmethod
     def backward(ctx, g_total, _g_ce, _g_kd):
         (ds,) = ctx.saved_tensors
-        return None, ds * g_total.to(dtype=torch.float32, device=ds.device), None, None, None, None, None, None, None
+        if g_total is None:
+            return (None,) * 9
+        return None, _scaled(ds, g_total.to(dtype=torch.float32, device=ds.device).contiguous()), None, None, None, None, None, None, None
 
 
 @L.on_device

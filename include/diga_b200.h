@@ -284,11 +284,16 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
                        int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
                        float* dlogits_sum, void* workspace, diga_stream_t stream);
 /* Both losses of self_training.py:348-352 and the gradient of lambda_ce * loss_ce + lambda_kd * loss_kd (:382) in ONE pass
- * over the stride-8 logits, for call sites that know the two loss weights when the losses are computed. */
+ * over the stride-8 logits, for call sites that know the two loss weights when the losses are computed.  `loss_total`
+ * (nullable) receives that weighted sum, rounded like the three fp32 scalar operations of :356 / :382. */
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
                            int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
-                           float* denom_out, float* dstudent_low, void* workspace, diga_stream_t stream);
+                           float* denom_out, float* loss_total, float* dstudent_low, void* workspace, diga_stream_t stream);
+/* out[i] = x[i] * (num[0] / den[0]) (den null: x[i] * num[0]); num, den device scalars.  The autograd backward of the
+ * single-pass losses: the stored gradient times the upstream scalar of `loss.backward()` (util/loss.py has no counterpart:
+ * autograd's MulBackward does this in the reference).  out must not overlap x. */
+int diga_scale_by_scalars(const float* x, const float* num, const float* den, int64_t n, float* out, diga_stream_t stream);
 int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
                        int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
                        void* workspace, diga_stream_t stream);

@@ -310,3 +310,50 @@ def test_source_rows_from_global_memory_equal_the_shared_memory_tile(D, n2, c, l
     finally:
         L.set_tunable("lossup_tile", 1)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("n,offset", [(0, 0), (1, 0), (5, 0), (1 << 12, 0), (19 * 65 * 129 * 3 + 3, 0), (4099, 1), (70001, 3)])
+def test_scale_by_scalars_equals_the_tensor_expression(D, n, offset):
+    """The backward of the single-pass losses scales the stored gradient with one launch (diga_scale_by_scalars): bit-equal to
+    `x * (g / denom)` and `x * g` of the tensor expression it replaces, on vector-aligned and unaligned buffers, with
+    upstream scalars that make the quotient inexact."""
+    from diga_b200 import _lib as L
+    g = torch.Generator(device=DEV).manual_seed(5 + n)
+    base = torch.randn((n + 8,), generator=g, device=DEV) * 37.0
+    x = base[offset:offset + n]
+    for num_v, den_v in ((0.3, 2097151.0), (1.0, 3.0), (-7.25, None), (0.0, 1.0)):
+        num = torch.tensor(num_v, device=DEV)
+        den = None if den_v is None else torch.tensor(den_v, device=DEV)
+        out_base = torch.full((n + 8,), 7.0, device=DEV)
+        out = out_base[offset:offset + n]
+        L.check(L.lib.diga_scale_by_scalars(L.ptr(x) if n else None, num.data_ptr(), L.ptr(den), n, L.ptr(out) if n else None,
+                                            L.stream()))
+        want = x * (num if den is None else num / den)
+        assert torch.equal(out, want)
+        assert torch.all(out_base[:offset] == 7.0) and torch.all(out_base[offset + n:] == 7.0)
+
+
+def test_single_loss_outputs_and_unused_upstreams(D):
+    """A switched-off loss is None inside the autograd function (no fill launch), an upstream that never arrives leaves the
+    other loss's gradient untouched, and the result equals the two-loss call with an explicit zero weight."""
+    tea, stu, g = inputs(2, 19, (12, 21), 41)
+    tgt = labels(1, (83, 301), 19, g)
+    s1 = stu.clone().requires_grad_(True)
+    l_ce, l_kd = D.seg_distillation_losses_upsampled(tea, s1, tgt, 0.5)
+    (0.7 * l_kd).backward()                                   # the CE upstream is None in backward
+    s2 = stu.clone().requires_grad_(True)
+    a_ce, a_kd = D.seg_distillation_losses_upsampled(tea, s2, tgt, 0.5)
+    (0.0 * a_ce + 0.7 * a_kd).backward()                      # the CE upstream is a device zero
+    assert torch.equal(s1.grad, s2.grad)
+    s3 = stu.clone().requires_grad_(True)
+    D.distillation_loss_upsampled(tea, s3, (83, 301), 0.5).mul(0.7).backward()
+    normwise(s3.grad, s1.grad, "KD-only single pass vs KD part of the two-loss backward")
+    s4 = stu[:1].clone().requires_grad_(True)
+    l = D.cross_entropy2d_upsampled(s4, tgt)
+    (g4,) = torch.autograd.grad(l * 3.0, s4)
+    s5 = stu.clone().requires_grad_(True)
+    b_ce, _ = D.seg_distillation_losses_upsampled(tea, s5, tgt, 0.5)
+    (3.0 * b_ce).backward()
+    rel(l, b_ce, "CE-only loss vs the CE part of the two-loss call")
+    normwise(g4, s5.grad[:1], "CE-only single pass vs CE part of the two-loss backward")
+    assert float(s5.grad[1:].abs().max()) == 0.0
