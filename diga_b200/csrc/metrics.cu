@@ -4,15 +4,51 @@
 // stay on the GPU: 2 label reads per pixel (uint8 or int64, as the producers deliver them), nothing written but the
 // n x n counters.  Integer counting: exact, order-independent, bit-equal to the reference matrix.
 //
-// A CTA keeps the matrix in shared memory (<= 32 x 32 counters); a warp first groups its lanes by bin
-// (__match_any_sync: label maps are piecewise constant, so most of a warp lands in one or two bins) and issues one
-// shared atomic per distinct bin; the CTA adds its non-zero counters to the global int64 matrix at the end.
+// A CTA keeps the matrix in shared memory (<= 32 x 32 counters); a warp issues one shared atomic per distinct bin (label
+// maps are piecewise constant, so most warps land in one bin); the CTA adds its non-zero counters to the global int64
+// matrix at the end.
 #include "common.cuh"
 
 namespace diga {
 
 int tunable(const char* name, int dflt);
 
+// Four consecutive labels of one map as signed 64-bit values: one 32-bit load (uint8) / two 128-bit loads (int64) when the
+// map's base is aligned for it (`vec`) and the group lies inside the map, else element by element (-1 = past the end).
+template <typename T>
+__device__ __forceinline__ void load_labels4(const T* __restrict__ p, int64_t i, int64_t total, bool vec, long long (&v)[4]) {
+  if (vec && i + 3 < total) {
+    if constexpr (sizeof(T) == 1) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + i));
+      v[0] = w & 0xffu, v[1] = (w >> 8) & 0xffu, v[2] = (w >> 16) & 0xffu, v[3] = w >> 24;
+    } else {
+      const longlong2 a = ld_stream_i64x2(reinterpret_cast<const int64_t*>(p + i));
+      const longlong2 b = ld_stream_i64x2(reinterpret_cast<const int64_t*>(p + i + 2));
+      v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i + k < total ? (long long)p[i + k] : -1;
+  }
+}
+
+// One shared atomic per RUN of equal bins over consecutive lanes (bin < 0: not counted): a lane whose lower neighbour holds
+// another bin heads a run and adds weight x (distance to the next head).  Label maps are piecewise constant, so a warp
+// holds one or two runs; no __match_any_sync (whose cost grows with the number of distinct values in the warp).
+__device__ __forceinline__ void add_runs(unsigned int* sh, int bin, int lane, unsigned weight) {
+  const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || bin != prev);
+  if (bin >= 0 && ((heads >> lane) & 1u)) {
+    const unsigned above = heads & ~((2u << lane) - 1u);          // heads above this lane (lane 31: none)
+    const int next = above ? __ffs(above) - 1 : 32;
+    atomicAdd(&sh[bin], weight * (unsigned)(next - lane));
+  }
+}
+
+// A thread owns four consecutive pixels per round (both maps' loads issued before the first use: at one pixel per thread the
+// kernel was bound by the bytes in flight, 2.4 TB/s), consecutive threads consecutive groups.  Counting: when every
+// thread's four pixels agree — the common case on piecewise-constant maps — one pass of `add_runs` with weight 4, otherwise
+// one pass per pixel slot.
 template <typename TT, typename TP, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 confusion_kernel(const TT* __restrict__ label_true, const TP* __restrict__ label_pred, int64_t total, int n_class,
@@ -22,22 +58,32 @@ confusion_kernel(const TT* __restrict__ label_true, const TP* __restrict__ label
   for (int i = threadIdx.x; i < bins; i += BLOCK) sh[i] = 0;
   __syncthreads();
   bool bad_pred = false;
-  // one label pair per thread and iteration, consecutive threads on consecutive pixels (coalesced for either type)
+  const bool vec_t = (reinterpret_cast<uintptr_t>(label_true) & (sizeof(TT) == 1 ? 3 : 15)) == 0;   // groups start at i % 4 == 0
+  const bool vec_p = (reinterpret_cast<uintptr_t>(label_pred) & (sizeof(TP) == 1 ? 3 : 15)) == 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t groups = (total + 3) / 4;
   const int64_t stride = (int64_t)gridDim.x * BLOCK;
-  const int64_t rounds = (total + stride - 1) / stride;      // every lane runs every round: __match_any_sync needs them all
+  const int64_t rounds = (groups + stride - 1) / stride;     // every lane runs every round: the warp votes need them all
   for (int64_t r = 0; r < rounds; ++r) {
-    const int64_t i = r * stride + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    int bin = -1;
-    if (i < total) {
-      const long long t = (long long)label_true[i];
-      const long long p = (long long)label_pred[i];
-      if (t >= 0 && t < n_class) {                               // metrics.py:33  mask = (true >= 0) & (true < n_class)
-        if (p >= 0 && p < n_class) bin = (int)(n_class * t + p); // :35
-        else bad_pred = true;                                    // np.bincount(...).reshape would raise in the reference
+    const int64_t i = (r * stride + (int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
+    long long t[4], p[4];
+    load_labels4(label_true, i, total, vec_t, t);          // groups past the end load nothing and come back as -1
+    load_labels4(label_pred, i, total, vec_p, p);
+    int bin[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bin[k] = -1;
+      if (i + k < total && t[k] >= 0 && t[k] < n_class) {            // metrics.py:33  mask = (true >= 0) & (true < n_class)
+        if (p[k] >= 0 && p[k] < n_class) bin[k] = (int)(n_class * t[k] + p[k]);   // :35
+        else bad_pred = true;                                        // np.bincount(...).reshape would raise in the reference
       }
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+    if (__all_sync(0xffffffffu, bin[0] == bin[1] && bin[1] == bin[2] && bin[2] == bin[3])) {
+      add_runs(sh, bin[0], lane, 4u);                     // every thread's four pixels agree: one pass over the lanes
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add_runs(sh, bin[k], lane, 1u);
+    }
   }
   if (bad_pred) atomicOr(flags, 1u);
   __syncthreads();
@@ -49,12 +95,12 @@ template <typename TT, typename TP>
 static int launch_confusion(const void* lt, const void* lp, int64_t total, int n_class, int64_t* hist, unsigned int* flags,
                             cudaStream_t st) {
   constexpr int BLOCK = 256;
-  int64_t grid = (total + BLOCK - 1) / BLOCK;
+  int64_t grid = ((total + 3) / 4 + BLOCK - 1) / BLOCK;
   // a CTA must not count more than 2^32 - 1 pixels into one 32-bit shared counter
   const int64_t cap = (int64_t)sm_count() * tunable("confusion_ctas_per_sm", 8);
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  while ((total + grid - 1) / grid >= ((int64_t)1 << 32)) grid *= 2;
+  while ((total + grid - 1) / grid + 4 * BLOCK >= ((int64_t)1 << 32)) grid *= 2;
   confusion_kernel<TT, TP, BLOCK><<<(unsigned)grid, BLOCK, 0, st>>>(reinterpret_cast<const TT*>(lt), reinterpret_cast<const TP*>(lp),
                                                                     total, n_class, reinterpret_cast<unsigned long long*>(hist), flags);
   DIGA_CHECK_LAUNCH("confusion_kernel");
