@@ -116,7 +116,9 @@ def cross_entropy2d(input, target, weight=None, size_average=True):
     """``util.loss.cross_entropy2d`` (G/util/loss.py:48-62): pixel-wise cross entropy with ``ignore_index=255``;
     pixels with a negative target are dropped; ``size_average`` divides by the number of pixels with target >= 0
     (ignore-255 pixels included, exactly like the reference).  ``input [N,C,H,W]`` fp32, ``target [N,H,W]`` int64.
-    An output of ``diga_b200.nn.Upsample`` is consumed at its stride-8 resolution (fused up-sampling, :344,:348-349,:355)."""
+    An output of ``diga_b200.nn.Upsample`` is consumed at its stride-8 resolution (fused up-sampling, :344,:348-349,:355).
+    Targets in ``[C, 255)`` are outside the reference's domain (``F.nll_loss`` raises a device-side assert there): the kernels
+    treat them like 255 — ignored in the loss, counted in the ``size_average`` denominator — instead of aborting the step."""
     if isinstance(input, LazyUpsampled):
         if tuple(target.shape[1:]) == input.out_size:
             return cross_entropy2d_upsampled(input.low, target, weight, size_average)
