@@ -32,6 +32,33 @@ def test_library_exports_every_declared_symbol():
     assert _lib.launch_count() == 0
 
 
+def test_ctypes_table_matches_header_prototypes():
+    """Arity and scalar / pointer kind of every ctypes signature against the C prototype in include/diga_b200.h (a drifted
+    table would pass pointers in float slots without any error)."""
+    import ctypes as C
+    from diga_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "diga_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//.*", "", src)
+    decls = re.findall(r"\b(diga_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert {n for n, _ in decls} == set(_lib.SIGNATURES)
+    kinds = {"ptr": (C.c_void_p, C.c_char_p), "int64_t": (C.c_int64,), "float": (C.c_float,), "double": (C.c_double,),
+             "int": (C.c_int,), "size_t": (C.c_size_t,), "uint32_t": (C.c_uint32, C.c_uint)}
+
+    def kind(param):
+        param = param.strip()
+        if "*" in param or "diga_stream_t" in param:
+            return "ptr"
+        return param.replace("const", "").split()[0]
+
+    for name, params in decls:
+        plist = [] if params.strip() in ("", "void") else params.split(",")
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(plist) == len(argtypes), f"{name}: header has {len(plist)} parameters, ctypes table {len(argtypes)}"
+        for i, (prm, at) in enumerate(zip(plist, argtypes)):
+            assert at in kinds[kind(prm)], f"{name} parameter {i} ({prm.strip()}): ctypes {at.__name__}"
+
+
 def test_c_abi_argument_validation_without_gpu():
     """Validation happens before any CUDA call, so bad arguments are reported even on a GPU-less host."""
     from diga_b200 import _lib as L
