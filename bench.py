@@ -1159,12 +1159,15 @@ def main():
                     rec["gpu_over_cpu_all_threads"] = rec["cpu_ms_all_threads"] / gpu["gpu_ms"]
 
     if rank == 0:
-        def row(stage, kernel, bound, unit, units, bytes_per_unit, ms, how, traffic_key=None, extra=None):
+        def row(stage, kernel, bound, unit, units, bytes_per_unit, ms, how, traffic_key=None, extra=None, issue_key=None):
             gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
             r = {"row": stage, "kernel": kernel, "bound": bound, "unit": unit, "units_per_launch": units,
                  "algo_bytes_per_unit": bytes_per_unit, "algo_bytes_per_launch": units * bytes_per_unit, "avg_launch_ms": ms,
                  "units_per_s_per_gpu": units / (ms * 1e-3), "achieved_gbs": gbs, "frac": gbs / peak,
                  "frac_of_8000_spec": gbs / 8000.0, "traffic": traffic_db.get(traffic_key) if traffic_key else None, "how": how}
+            if bound == "alu":      # the HBM fraction of an ALU / latency-bound kernel says little: its issue-slot utilisation (ncu) beside it
+                r["frac_note"] = "fraction of the HBM peak on the algorithmic bytes; the kernel is bound by issue slots / latency"
+                r["ncu_issue_active_pct"] = traffic_db.get(issue_key) if issue_key else None
             if extra:
                 r.update(extra)
             return r
@@ -1177,15 +1180,15 @@ def main():
             row("a1", "kd_kernel<LOSS,GRAD> (single pass)", "hbm", "pixel-position", px_step, KD_BYTES_BWD, fused_ms, ev_how),
         ] + [row(*r) for r in accum_rows]
         if stages:
-            def from_stage(stage, key, kernel, bound, unit, traffic_key=None, extra=None):
+            def from_stage(stage, key, kernel, bound, unit, traffic_key=None, extra=None, issue_key=None):
                 st_ = stages.get(key)
                 if st_ and "ms" in st_:
                     px = st_["px_per_s"] / world * st_["ms"] * 1e-3
-                    rows.append(row(stage, kernel, bound, unit, px, st_["algo_bytes_per_px"], st_["ms"], gr_how, traffic_key, extra))
+                    rows.append(row(stage, kernel, bound, unit, px, st_["algo_bytes_per_px"], st_["ms"], gr_how, traffic_key, extra, issue_key))
             from_stage("a3", "pseudo_label_1scale", "pseudo_label_kernel (one scale)", "hbm", "px", "pl1_dram_bytes_per_launch")
             from_stage("a3", "pseudo_label_2scale", "pseudo_label_kernel (two scales, max-fused)", "hbm", "px", "pl2_dram_bytes_per_launch")
-            from_stage("a3+f1", "pseudo_label_fused_upsample_labels_only", "pseudo_label_upsampled_kernel (labels from stride-8 logits)", "alu", "px")
-            from_stage("a4", "consensus_select", "consensus_select_kernel", "alu", "px", "select_dram_bytes_per_launch")
+            from_stage("a3+f1", "pseudo_label_fused_upsample_labels_only", "pseudo_label_upsampled_kernel (labels from stride-8 logits)", "alu", "px", issue_key="plup_issue_active_pct")
+            from_stage("a4", "consensus_select", "consensus_select_kernel", "alu", "px", "select_dram_bytes_per_launch", issue_key="select_issue_active_pct")
             from_stage("a2", "classmix_dacs_blend_kernel", "classmix_blend_kernel (DACS)", "hbm", "px", "cm_dram_bytes_per_launch")
             from_stage("a5", "proto_distance_softmax_d2048", "proto_umma_kernel (tcgen05 3xTF32)", "hbm", "feature-px", "proto_dram_bytes_per_launch")
             from_stage("a6+a7", "centroid_accumulate_update_d2048_iid_classes", "update_from_features call: assign + accum + finish (i.i.d. classes)", "hbm", "feature-px")
@@ -1193,8 +1196,8 @@ def main():
             from_stage("f2", "cross_entropy2d_fwd_bwd", "ce_kernel fwd + bwd", "hbm", "px")
             from_stage("f4", "ema_teacher_update", "ema_update_kernel", "hbm", "parameter")
             from_stage("f1", "kd_fused_upsample_fwd_bwd", "loss_up_kernel<KD> loss+gradient from the stride-8 logits (distillation_loss_upsampled + autograd)", "alu", "pixel-position")
-            from_stage("f1+f2", "cross_entropy2d_fused_upsample_fwd_bwd", "loss_up_kernel<CE> loss+gradient from the stride-8 logits", "alu", "px")
-            from_stage("f1", "seg_plus_kd_fused_upsample_fwd_bwd", "loss_up_kernel<KD+CE> loss pass + gradient pass (self_training.py:348-352)", "alu", "pixel-position")
+            from_stage("f1+f2", "cross_entropy2d_fused_upsample_fwd_bwd", "loss_up_kernel<CE> loss+gradient from the stride-8 logits", "alu", "px", issue_key="lossup_ce_issue_active_pct")
+            from_stage("f1", "seg_plus_kd_fused_upsample_fwd_bwd", "loss_up_kernel<KD+CE> loss pass + gradient pass (self_training.py:348-352)", "alu", "pixel-position", issue_key="lossup_kdce_issue_active_pct")
             from_stage("f5", "confusion_matrix_eval", "confusion_matrix_kernel (runningScore.update)", "hbm", "px")
             from_stage("f3", "label_reader_resize_remap", "label_resize_remap_kernel (CityLoader NEAREST resize + id look-up)", "hbm", "px")
             for key, label in (("config3_self_training_step_dropin_functions", "config 3: self-training step hot path with ONLY the function names swapped (losses behind torch's nn.Upsample)"),

@@ -13,10 +13,16 @@ namespace diga {
 
 int tunable(const char* name, int dflt);
 
-// Four consecutive labels of one map as signed 64-bit values: one 32-bit load (uint8) / two 128-bit loads (int64) when the
-// map's base is aligned for it (`vec`) and the group lies inside the map, else element by element (-1 = past the end).
+// Four consecutive labels of one map as 32-bit values, anything outside [0, 2^31) folded to -1 (neither a class nor a
+// countable prediction): one 32-bit load (uint8) / two 128-bit loads (int64) when the map's base is aligned for it (`vec`)
+// and the group lies inside the map, else element by element (-1 past the end).
 template <typename T>
-__device__ __forceinline__ void load_labels4(const T* __restrict__ p, int64_t i, int64_t total, bool vec, long long (&v)[4]) {
+__device__ __forceinline__ int fold_label(T x) {
+  if constexpr (sizeof(T) == 1) return (int)x;
+  else return (unsigned long long)x < 0x80000000ull ? (int)x : -1;
+}
+template <typename T>
+__device__ __forceinline__ void load_labels4(const T* __restrict__ p, int64_t i, int64_t total, bool vec, int (&v)[4]) {
   if (vec && i + 3 < total) {
     if constexpr (sizeof(T) == 1) {
       const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + i));
@@ -24,11 +30,12 @@ __device__ __forceinline__ void load_labels4(const T* __restrict__ p, int64_t i,
     } else {
       const longlong2 a = ld_stream_i64x2(reinterpret_cast<const int64_t*>(p + i));
       const longlong2 b = ld_stream_i64x2(reinterpret_cast<const int64_t*>(p + i + 2));
-      v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+      v[0] = fold_label<long long>(a.x), v[1] = fold_label<long long>(a.y);
+      v[2] = fold_label<long long>(b.x), v[3] = fold_label<long long>(b.y);
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = i + k < total ? (long long)p[i + k] : -1;
+    for (int k = 0; k < 4; ++k) v[k] = i + k < total ? fold_label<T>(p[i + k]) : -1;
   }
 }
 
@@ -66,17 +73,16 @@ confusion_kernel(const TT* __restrict__ label_true, const TP* __restrict__ label
   const int64_t rounds = (groups + stride - 1) / stride;     // every lane runs every round: the warp votes need them all
   for (int64_t r = 0; r < rounds; ++r) {
     const int64_t i = (r * stride + (int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
-    long long t[4], p[4];
+    int t[4], p[4];
     load_labels4(label_true, i, total, vec_t, t);          // groups past the end load nothing and come back as -1
     load_labels4(label_pred, i, total, vec_p, p);
     int bin[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      bin[k] = -1;
-      if (i + k < total && t[k] >= 0 && t[k] < n_class) {            // metrics.py:33  mask = (true >= 0) & (true < n_class)
-        if (p[k] >= 0 && p[k] < n_class) bin[k] = (int)(n_class * t[k] + p[k]);   // :35
-        else bad_pred = true;                                        // np.bincount(...).reshape would raise in the reference
-      }
+      const bool counted = (unsigned)t[k] < (unsigned)n_class;       // metrics.py:33  mask = (true >= 0) & (true < n_class)
+      const bool in_range = (unsigned)p[k] < (unsigned)n_class;
+      bin[k] = counted && in_range ? n_class * t[k] + p[k] : -1;     // :35
+      bad_pred |= counted && !in_range;                              // np.bincount(...).reshape would raise in the reference
     }
     if (__all_sync(0xffffffffu, bin[0] == bin[1] && bin[1] == bin[2] && bin[2] == bin[3])) {
       add_runs(sh, bin[0], lane, 4u);                     // every thread's four pixels agree: one pass over the lanes
