@@ -630,10 +630,15 @@ def bench_stages(D, S, dev, peak, world):
     lazy_up = D.nn.Upsample(size=(hh, ww), mode="bilinear", align_corners=True)
 
     def st_step(fused, lazy=False):
-        if fused:      # one presence pass over slabelv serves both ClassMix blocks; its host round trip hides behind a5 + a4
+        if fused:      # one presence pass over slabelv serves both ClassMix blocks.  In the script its 32 B/image host round trip
+            # hides behind the backbone passes queued in between; this step has no backbone, so the statements that do not
+            # depend on the class choice (a5, a4, and the two centroid updates, which read neither mix) are queued before the
+            # host waits for it — same data dependencies, same results, ClassMix draws still in script order
             pres = D.present_classes_async(sl)
             wts = cf.get_centroid_weight(feat)                                                     # :301
             kept, feat_pseudo = D.consensus_select(tl, wts, (hh, ww))                              # :302-304
+            cf.update_from_features(feat, t_pred, start_mean=False, labels_full=kept)              # :327-334
+            cf.update_from_features(s_feat, s_pred, start_mean=False, labels_full=sl)              # :336-341
             _, mix1 = D.classmix(sl, rec, saug, rng=rng3, present=pres, return_mask=False)         # :259-275
             _, mix2, mixlabel = D.classmix(sl, tdata_aug, sdata, kept, rng=rng3, present=pres, return_mask=False)   # :306-325
         else:
@@ -641,10 +646,7 @@ def bench_stages(D, S, dev, peak, world):
             wts = cf.get_centroid_weight(feat)                                                     # :301
             kept, feat_pseudo = D.consensus_select(tl, wts, (hh, ww))                              # :302-304
             _, mix2, mixlabel = D.classmix(sl, tdata_aug, sdata, kept, rng=rng3)                   # :306-325
-        if fused:      # label down-sampling (.float() + F.interpolate(nearest), :328-330, :336-337) folded into the assign kernel
-            cf.update_from_features(feat, t_pred, start_mean=False, labels_full=kept)                      # :327-334
-            cf.update_from_features(s_feat, s_pred, start_mean=False, labels_full=sl)                      # :336-341
-        else:
+        if not fused:  # (fused: label down-sampling — .float() + F.interpolate(nearest), :328-330, :336-337 — folded into the assign kernel above)
             cf.update_from_features(feat, t_pred, _labels_on_feature_grid(kept, (h, w)), start_mean=False)
             cf.update_from_features(s_feat, s_pred, _labels_on_feature_grid(sl, (h, w)), start_mean=False)
         stu = stu_cat.detach().requires_grad_(True)

@@ -43,10 +43,14 @@ def build():
 
 def st_step(x, fused):
     cf, rng, sl, tl, feat = x["cf"], x["rng"], x["sl"], x["tl"], x["feat"]
-    if fused:      # one presence pass over slabelv serves both ClassMix blocks; its host round trip hides behind a5 + a4
+    if fused:      # one presence pass over slabelv serves both ClassMix blocks; its host round trip hides behind the statements
+        # that do not depend on the class choice (a5, a4, the two centroid updates: they read neither mix) — in the script
+        # it hides behind the backbone passes.  Label down-sampling (:328-330, :336-337) folded into the assign kernel.
         pres = D.present_classes_async(sl)
         wts = cf.get_centroid_weight(feat)                                                         # :301
         kept, _ = D.consensus_select(tl, wts, (hh, ww))                                            # :302-304
+        cf.update_from_features(feat, x["t_pred"], start_mean=False, labels_full=kept)             # :327-334
+        cf.update_from_features(x["s_feat"], x["s_pred"], start_mean=False, labels_full=sl)        # :336-341
         _, mix1 = D.classmix(sl, x["rec"], x["saug"], rng=rng, present=pres, return_mask=False)    # :259-275
         _, mix2, mixlabel = D.classmix(sl, x["tdata_aug"], x["sdata"], kept, rng=rng, present=pres, return_mask=False)
     else:
@@ -54,10 +58,7 @@ def st_step(x, fused):
         wts = cf.get_centroid_weight(feat)
         kept, _ = D.consensus_select(tl, wts, (hh, ww))
         _, mix2, mixlabel = D.classmix(sl, x["tdata_aug"], x["sdata"], kept, rng=rng)
-    if fused:          # label down-sampling (.float() + F.interpolate(nearest), :328-330, :336-337) folded into the assign kernel
-        cf.update_from_features(feat, x["t_pred"], start_mean=False, labels_full=kept)                          # :327-334
-        cf.update_from_features(x["s_feat"], x["s_pred"], start_mean=False, labels_full=sl)                     # :336-341
-    else:
+    if not fused:
         cf.update_from_features(feat, x["t_pred"], _labels_on_feature_grid(kept, (h, w)), start_mean=False)
         cf.update_from_features(x["s_feat"], x["s_pred"], _labels_on_feature_grid(sl, (h, w)), start_mean=False)
     stu = x["stu_cat"].detach().requires_grad_(True)
