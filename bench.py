@@ -652,7 +652,8 @@ def bench_stages(D, S, dev, peak, world):
         stu = stu_cat.detach().requires_grad_(True)
         cpm = cross_low.detach().requires_grad_(True)
         if fused:      # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each
-            part, l_src, l_kd = D.seg_distillation_total_upsampled(tea_cat, stu, sl, 1.0, 0.25, 0.5)   # :289,:348-352,:382
+            part, l_src, l_kd = D.seg_distillation_total_upsampled(tea_cat, stu, sl, 1.0, 0.25, 0.5,   # :289,:348-352,:382
+                                                                   targets_nonnegative=True)   # loader labels: trainIds or 255
             total = part + D.cross_entropy2d_upsampled(cpm, mixlabel)                              # :344,:355-356
         else:          # the reference's call sites as they are; `lazy`: its three nn.Upsample modules built from diga_b200.nn.Upsample
             up = lazy_up if lazy else (lambda x: F.interpolate(x, size=(hh, ww), mode="bilinear", align_corners=True))

@@ -90,6 +90,7 @@ struct LossUpArgs {
   const float* denom;
   float up_kd_host;        // used when up_kd == null (single-pass variants)
   float up_ce_host;        // used when up_ce == null
+  float denom_host;        // > 0: the caller's #(target >= 0) (size_average, denom == null); checked against the counted value
   const float* sel_pred;   // OHEM (csrc/ohem_up.cu): per-pixel target probability [n_ce,H,W], < 0 = ignored; null = plain CE
   const float* sel_thr;    // OHEM: device scalar, a pixel is kept iff 0 <= sel_pred < sel_thr[0]
   int ignore_label;        // OHEM: target value that is masked out (CE: 255 is >= nclass anyway)
@@ -193,7 +194,7 @@ loss_up_kernel(const LossUpArgs a) {
   float ckd = 0.f, cce = 0.f;
   if constexpr (GRAD) {
     if constexpr (KD) ckd = (a.up_kd != nullptr ? __ldg(a.up_kd) : a.up_kd_host) * a.inv_count_kd * wkd;
-    if (ce_img) cce = (a.up_ce != nullptr ? __ldg(a.up_ce) : a.up_ce_host) / ((a.size_average && a.denom != nullptr) ? __ldg(a.denom) : 1.0f);
+    if (ce_img) cce = (a.up_ce != nullptr ? __ldg(a.up_ce) : a.up_ce_host) / (!a.size_average ? 1.0f : a.denom != nullptr ? __ldg(a.denom) : a.denom_host > 0.f ? a.denom_host : 1.0f);
   }
 
   const bool ohem = CE && a.sel_pred != nullptr;
@@ -585,6 +586,12 @@ loss_up_kernel(const LossUpArgs a) {
             if (a.loss_total)
               a.loss_total[0] = __fadd_rn(__fmul_rn(a.up_ce_host, a.size_average ? tot / cnt : tot),
                                           __fmul_rn(a.up_kd_host, (float)(dr[0][0] * 0.6931471805599453 * (double)a.inv_count_kd)));
+            // a promised denominator that the count contradicts scaled the CE gradient wrongly: fail loudly, not quietly
+            if (a.size_average && a.denom == nullptr && a.denom_host > 0.f && cnt != a.denom_host) {
+              const float bad = __int_as_float(0x7fc00000);
+              if (a.loss_ce) a.loss_ce[0] = bad;
+              if (a.loss_total) a.loss_total[0] = bad;
+            }
           }
         }
         *a.ticket = 0;                                       // leave the workspace ready for the next launch
@@ -875,8 +882,9 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
 
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
-                           int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
-                           float* denom_out, float* loss_total, float* dstudent_low, void* workspace, diga_stream_t stream) {
+                           int size_average, float lambda_ce_host, float lambda_kd_host, float denom_known, float* loss_kd,
+                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, void* workspace,
+                           diga_stream_t stream) {
   using namespace diga;
   if (int rc = check_common("seg_kd_up_fwd_bwd", student_low, n2, C, h, w, H, W, workspace)) return rc;
   DIGA_REQUIRE(teacher_low && target && loss_kd && loss_ce && denom_out && dstudent_low && (n2 % 2) == 0 && n_ce >= 1 && n_ce <= n2,
@@ -886,7 +894,10 @@ int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, c
   cudaStream_t st = (cudaStream_t)stream;
   const LossUpPlan p = make_plan(n2, C, h, w, H, W);
   LossUpArgs a = fill_args(p, workspace, teacher_low, student_low, target, weight, n2, n_ce, C, h, w, H, W, scale, size_average);
-  if (size_average) {                                     // the CE gradient is divided by #(target >= 0): count it first
+  DIGA_REQUIRE(denom_known >= 0.f, DIGA_ERR_INVALID, "seg_kd_up_fwd_bwd: negative denom_known");
+  if (size_average && denom_known > 0.f) {                // the caller knows #(target >= 0) (e.g. loader labels: trainIds or 255)
+    a.denom_host = denom_known;
+  } else if (size_average) {                              // the CE gradient is divided by #(target >= 0): count it first
     const int64_t total = n_ce * H * W;
     int64_t grid = (total / 2 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;

@@ -290,7 +290,8 @@ class _SegDistillationTotal(torch.autograd.Function):
     launches the loss+gradient kernel once (the weighted gradient comes out of the same pass), the backward scales it."""
 
     @staticmethod
-    def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average, lambda_seg, lambda_distil):
+    def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average, lambda_seg, lambda_distil,
+                targets_nonnegative):
         s, t, tg = L.f32c(student_low.detach()), L.f32c(teacher_low.detach()), L.i64c(target)
         wt = None if weight is None else L.f32c(weight.detach()).to(s.device)
         n, c, h, w = s.shape
@@ -304,8 +305,9 @@ class _SegDistillationTotal(torch.autograd.Function):
             total = torch.empty((), dtype=torch.float32, device=dev)     # written by the kernel's last CTA: no scalar launches
             L.check(L.lib.diga_seg_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w,
                                                  hh, ww, float(scale), int(bool(size_average)), float(lambda_seg),
-                                                 float(lambda_distil), loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(),
-                                                 total.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
+                                                 float(lambda_distil), float(tg.numel()) if targets_nonnegative else 0.0,
+                                                 loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(), total.data_ptr(),
+                                                 ds.data_ptr(), ws.data_ptr(), L.stream()))
             ctx.save_for_backward(ds)
         else:
             L.check(L.lib.diga_loss_up_fwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w, hh, ww,
@@ -319,17 +321,21 @@ class _SegDistillationTotal(torch.autograd.Function):
     def backward(ctx, g_total, _g_ce, _g_kd):
         (ds,) = ctx.saved_tensors
         if g_total is None:
-            return (None,) * 9
-        return None, _scaled(ds, g_total.to(dtype=torch.float32, device=ds.device).contiguous()), None, None, None, None, None, None, None
+            return (None,) * 10
+        return (None, _scaled(ds, g_total.to(dtype=torch.float32, device=ds.device).contiguous())) + (None,) * 8
 
 
 @L.on_device
 def seg_distillation_total_upsampled(teacher_low, student_low, target, lambda_seg=1.0, lambda_distil=0.25, scale=0.5,
-                                     weight=None, size_average=True):
+                                     weight=None, size_average=True, targets_nonnegative=False):
     """``total = lambda_seg * seg_loss(upsample(student_low[:B]), target) + lambda_distil * distillation_loss(upsample(
     teacher_low), upsample(student_low), scale)`` — self_training.py:348-352 and the source-image part of :382 — with the
     loss weights known when the losses are computed, so loss and gradient cost ONE pass over the stride-8 logits.
-    Returns ``(total, loss_seg, loss_distil)``; only ``total`` carries a gradient (the two parts are for logging)."""
+    Returns ``(total, loss_seg, loss_distil)``; only ``total`` carries a gradient (the two parts are for logging).
+    ``targets_nonnegative=True`` is the caller's promise that no target is negative (the loaders deliver trainIds or 255),
+    which makes the ``size_average`` denominator ``#(target >= 0)`` (util/loss.py:56,:60) the number of target pixels and saves
+    the counting pass in front of the loss kernel; the kernel still counts, and ``total`` / ``loss_seg`` are NaN if the promise
+    was wrong."""
     L.require_cuda(teacher_low, student_low, target, weight, what="seg_distillation_total_upsampled input")
     if teacher_low.shape != student_low.shape or student_low.dim() != 4 or student_low.shape[0] % 2:
         raise ValueError("seg_distillation_total_upsampled: expected two [2B,C,h,w] logit tensors")
@@ -337,7 +343,7 @@ def seg_distillation_total_upsampled(teacher_low, student_low, target, lambda_se
         raise ValueError("seg_distillation_total_upsampled: target must be [n_ce,H,W] with 1 <= n_ce <= 2B")
     size = _check_low(student_low, target.shape[1:], "seg_distillation_total_upsampled")
     return _SegDistillationTotal.apply(teacher_low, student_low, target, weight, size, scale, size_average, float(lambda_seg),
-                                       float(lambda_distil))
+                                       float(lambda_distil), bool(targets_nonnegative))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -285,11 +285,15 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
                        float* dlogits_sum, void* workspace, diga_stream_t stream);
 /* Both losses of self_training.py:348-352 and the gradient of lambda_ce * loss_ce + lambda_kd * loss_kd (:382) in ONE pass
  * over the stride-8 logits, for call sites that know the two loss weights when the losses are computed.  `loss_total`
- * (nullable) receives that weighted sum, rounded like the three fp32 scalar operations of :356 / :382. */
+ * (nullable) receives that weighted sum, rounded like the three fp32 scalar operations of :356 / :382.  The CE gradient is
+ * divided by #(target >= 0) (util/loss.py:56,:60): `denom_known` = 0 counts it first (one pass over the targets);
+ * `denom_known` > 0 is the caller's promise of that count (loader labels are trainIds or 255, so it is n_ce * H * W) — the
+ * value counted by the loss reduction is compared with it and loss_ce / loss_total come back NaN if they differ. */
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
-                           int size_average, float lambda_ce_host, float lambda_kd_host, float* loss_kd, float* loss_ce,
-                           float* denom_out, float* loss_total, float* dstudent_low, void* workspace, diga_stream_t stream);
+                           int size_average, float lambda_ce_host, float lambda_kd_host, float denom_known, float* loss_kd,
+                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, void* workspace,
+                           diga_stream_t stream);
 /* out[i] = x[i] * (num[0] / den[0]) (den null: x[i] * num[0]); num, den device scalars.  The autograd backward of the
  * single-pass losses: the stored gradient times the upstream scalar of `loss.backward()` (util/loss.py has no counterpart:
  * autograd's MulBackward does this in the reference).  out must not overlap x. */

@@ -357,3 +357,30 @@ def test_single_loss_outputs_and_unused_upstreams(D):
     rel(l, b_ce, "CE-only loss vs the CE part of the two-loss call")
     normwise(g4, s5.grad[:1], "CE-only single pass vs CE part of the two-loss backward")
     assert float(s5.grad[1:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", [GEOMS[0], GEOMS[2], GEOMS[3]])
+def test_promised_denominator_skips_the_count_and_is_checked(D, n2, c, lo, hi):
+    """targets_nonnegative=True (loader labels: trainIds or 255) hands the size_average denominator to the kernel instead of
+    counting it first: bit-equal losses and gradient when the promise holds, NaN losses when a negative target breaks it."""
+    from diga_b200 import _lib as L
+    tea, stu, g = inputs(n2, c, lo, 57)
+    tgt = labels(n2 // 2, hi, c, g)
+    clean = torch.where(tgt < 0, torch.full_like(tgt, 255), tgt)
+
+    def run(target, promise):
+        s = stu.clone().requires_grad_(True)
+        n0 = L.launch_count()
+        total, l_ce, l_kd = D.seg_distillation_total_upsampled(tea, s, target, 0.7, 1.3, 0.5, targets_nonnegative=promise)
+        launches = L.launch_count() - n0
+        total.backward()
+        return total.detach(), l_ce, l_kd, s.grad, launches
+
+    a, b = run(clean, False), run(clean, True)
+    assert all(torch.equal(x, y) for x, y in zip(a[:4], b[:4]))
+    assert a[4] == b[4] + 1                                    # the counting launch is gone
+    assert (tgt < 0).any()
+    bad = run(tgt, True)
+    assert torch.isnan(bad[0]) and torch.isnan(bad[1]) and torch.isfinite(bad[2])
+    good = run(tgt, False)
+    assert torch.isfinite(good[0]) and torch.isfinite(good[1])

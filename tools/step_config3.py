@@ -64,7 +64,8 @@ def st_step(x, fused):
     stu = x["stu_cat"].detach().requires_grad_(True)
     cpm = x["cross_low"].detach().requires_grad_(True)
     if fused:          # loss weights (lambda_seg = 1, lambda_distil = 0.25, :102-103) known up front: one pass each
-        part, l_src, l_kd = D.seg_distillation_total_upsampled(x["tea_cat"], stu, sl, 1.0, 0.25, 0.5)   # :289,:348-352,:382
+        part, l_src, l_kd = D.seg_distillation_total_upsampled(x["tea_cat"], stu, sl, 1.0, 0.25, 0.5,   # :289,:348-352,:382
+                                                               targets_nonnegative=True)   # loader labels: trainIds or 255
         total = part + D.cross_entropy2d_upsampled(cpm, mixlabel)                                  # :344,:355-356
     else:
         up = lambda t: F.interpolate(t, size=(hh, ww), mode="bilinear", align_corners=True)
