@@ -72,10 +72,11 @@ SIGNATURES = {
     "diga_loss_up_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64, _i64, _i64, _i64]),
     "diga_loss_up_fwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p]),
     "diga_loss_up_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _p, _p, _p, _p, _p, _p]),
-    "diga_ce_up_fwd_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p, _p]),
-    "diga_seg_kd_up_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
-    "diga_scale_by_scalars": (_i, [_p, _p, _p, _i64, _p, _p]),
-    "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
+    "diga_ce_up_fwd_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "diga_seg_kd_up_fwd_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "diga_loss_up_scratch_bytes": (C.c_size_t, [_i64, _i64, _i64, _i64, _i64, _i64]),
+    "diga_loss_up_gather": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "diga_kd_up_fwd_bwd": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p, _p]),
     "diga_ohem_up_workspace_bytes": (C.c_size_t, []),
     "diga_ohem_up_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "diga_ohem_up_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),

@@ -603,13 +603,18 @@ loss_up_kernel(const LossUpArgs a) {
 // dlow[n,c,y,x] = sum of the scratch patches that cover (y,x): strips in increasing ky, tiles in increasing kx (fixed
 // order: deterministic).  One CTA per (image, source row): the matching strips are CTA-uniform, a thread owns one
 // source column, resolves its patches (at most 2 x 2, else the generic loop) and adds their class vectors as float4s;
-// the stores are coalesced per class plane.
+// the stores are coalesced per class plane.  `num` != null (the deferred gather of the autograd backward): every sum is
+// multiplied by num[0] / den[0] (den null: num[0]) — the upstream scalar, read on the device — before it is stored, the
+// same two roundings as gathering first and scaling the tensor afterwards.
 template <int C, bool PAD>
 __global__ void __launch_bounds__(128)
 loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlow, int nclass, int h, int w, int H, int W,
-                      float sh, float sw, float inv_sh_ry, float inv_sw_bx, int ry, int R, int K, int SX, int SY) {
+                      float sh, float sw, float inv_sh_ry, float inv_sw_bx, int ry, int R, int K, int SX, int SY,
+                      const float* __restrict__ num, const float* __restrict__ den) {
   constexpr int CP = (C + 3) & ~3, CQ = CP / 4;
   const int y = blockIdx.x, img = blockIdx.y;
+  const bool scaled = num != nullptr;
+  const float coef = scaled ? (den != nullptr ? __fdiv_rn(__ldg(num), __ldg(den)) : __ldg(num)) : 1.f;
   // candidate strips: output rows with i0 in {y-1, y} lie in [(y-1)/sh, (y+1)/sh]; one strip of slack either side,
   // then the exact test with the kernel's own tap arithmetic (matching strips are contiguous: ylo, yhi are monotone)
   int kyA = 0, kyB = SY - 1;
@@ -657,7 +662,7 @@ loss_up_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dlo
     const float* av = reinterpret_cast<const float*>(acc);
 #pragma unroll
     for (int c = 0; c < C; ++c)
-      if (!PAD || c < nclass) dst[c * plane] = av[c];
+      if (!PAD || c < nclass) dst[c * plane] = scaled ? __fmul_rn(av[c], coef) : av[c];
   }
 }
 
@@ -695,27 +700,6 @@ count_targets_kernel(const int64_t* __restrict__ target, int64_t total, unsigned
   }
 }
 
-// out = x * (num / den) (den null: x * num) with the scalars read on the device: the backward of the single-pass losses scales the
-// gradient the forward left behind by the upstream scalar (and 1 / #(target >= 0)).  Same fp32 operations, in the same order,
-// as the tensor expression `x * (g / denom)` it replaces.
-__global__ void __launch_bounds__(256)
-scale_by_scalars_kernel(const float* __restrict__ x, const float* __restrict__ num, const float* __restrict__ den, int64_t n,
-                        float* __restrict__ out, int vec) {
-  const float coef = den ? __fdiv_rn(num[0], den[0]) : num[0];
-  const int64_t stride = (int64_t)gridDim.x * 256;
-  if (vec) {
-    const int64_t n4 = n / 4;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
-      float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
-      v.x = __fmul_rn(v.x, coef), v.y = __fmul_rn(v.y, coef), v.z = __fmul_rn(v.z, coef), v.w = __fmul_rn(v.w, coef);
-      reinterpret_cast<float4*>(out)[i] = v;
-    }
-    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn(x[i], coef);
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn(x[i], coef);
-  }
-}
-
 static int check_common(const char* who, const float* stu, int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W,
                         const void* workspace) {
   DIGA_REQUIRE(stu && workspace, DIGA_ERR_INVALID, "%s: null input / workspace", who);
@@ -748,11 +732,11 @@ static int launch_loss_up(LossUpArgs a, const LossUpPlan& p, int64_t C, float* d
     }
     kernel<<<grid, kLuBlock, dyn, st>>>(a);
     DIGA_CHECK_LAUNCH("loss_up_kernel");
-    if (GRAD) {
+    if (GRAD && dlow != nullptr) {                       // dlow null: the patches stay in the caller's scratch (deferred gather)
       const float inv_sh_ry = a.sh > 0.f ? 1.0f / (a.sh * (float)p.ry) : 0.f;
       const float inv_sw_bx = a.sw > 0.f ? 1.0f / (a.sw * (float)kLuCols) : 0.f;
       loss_up_gather_kernel<kC, kPad><<<dim3((unsigned)a.h, (unsigned)a.n), 128, 0, st>>>(
-          a.scratch, dlow, a.nclass, a.h, a.w, a.H, a.W, a.sh, a.sw, inv_sh_ry, inv_sw_bx, p.ry, p.R, p.K, p.SX, p.SY);
+          a.scratch, dlow, a.nclass, a.h, a.w, a.H, a.W, a.sh, a.sw, inv_sh_ry, inv_sw_bx, p.ry, p.R, p.K, p.SX, p.SY, nullptr, nullptr);
       DIGA_CHECK_LAUNCH("loss_up_gather_kernel");
     }
   });
@@ -851,14 +835,16 @@ int diga_loss_up_bwd(const float* teacher_low, const float* student_low, const i
 
 int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
                        int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
-                       void* workspace, diga_stream_t stream) {
+                       float* scratch, void* workspace, diga_stream_t stream) {
   using namespace diga;
   if (int rc = check_common("kd_up_fwd_bwd", student_low, n2, C, h, w, H, W, workspace)) return rc;
-  DIGA_REQUIRE(teacher_low && loss_out && dstudent_low && (n2 % 2) == 0, DIGA_ERR_INVALID,
-               "kd_up_fwd_bwd: teacher, loss_out, dstudent_low and an even batch are required");
-  DIGA_REQUIRE(aligned(teacher_low, 4) && aligned(dstudent_low, 4), DIGA_ERR_MISALIGNED, "kd_up_fwd_bwd: misaligned pointer");
+  DIGA_REQUIRE(teacher_low && loss_out && (dstudent_low || scratch) && (n2 % 2) == 0, DIGA_ERR_INVALID,
+               "kd_up_fwd_bwd: teacher, loss_out, dstudent_low (or scratch) and an even batch are required");
+  DIGA_REQUIRE(aligned(teacher_low, 4) && aligned(dstudent_low, 4) && aligned(scratch, 16), DIGA_ERR_MISALIGNED,
+               "kd_up_fwd_bwd: misaligned pointer");
   const LossUpPlan p = make_plan(n2, C, h, w, H, W);
   LossUpArgs a = fill_args(p, workspace, teacher_low, student_low, nullptr, nullptr, n2, 0, C, h, w, H, W, scale, 1);
+  if (scratch) a.scratch = scratch;
   a.up_kd_host = upstream_host;
   a.loss_kd = loss_out;
   return launch_loss_up<true, false, true, true>(a, p, C, dstudent_low, (cudaStream_t)stream);
@@ -866,14 +852,15 @@ int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64
 
 int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
                        int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
-                       float* dlogits_sum, void* workspace, diga_stream_t stream) {
+                       float* dlogits_sum, float* scratch, void* workspace, diga_stream_t stream) {
   using namespace diga;
   if (int rc = check_common("ce_up_fwd_bwd", logits_low, n, C, h, w, H, W, workspace)) return rc;
-  DIGA_REQUIRE(target && loss_out && denom_out && dlogits_sum, DIGA_ERR_INVALID, "ce_up_fwd_bwd: null pointer");
-  DIGA_REQUIRE(aligned(target, 8) && aligned(weight, 4) && aligned(dlogits_sum, 4), DIGA_ERR_MISALIGNED,
+  DIGA_REQUIRE(target && loss_out && denom_out && (dlogits_sum || scratch), DIGA_ERR_INVALID, "ce_up_fwd_bwd: null pointer");
+  DIGA_REQUIRE(aligned(target, 8) && aligned(weight, 4) && aligned(dlogits_sum, 4) && aligned(scratch, 16), DIGA_ERR_MISALIGNED,
                "ce_up_fwd_bwd: misaligned pointer");
   const LossUpPlan p = make_plan(n, C, h, w, H, W);
   LossUpArgs a = fill_args(p, workspace, nullptr, logits_low, target, weight, n, n, C, h, w, H, W, 0.f, size_average);
+  if (scratch) a.scratch = scratch;
   a.loss_ce = loss_out;
   a.denom_out = denom_out;
   a.up_ce_host = 1.0f;              // unit upstream, no denominator: the gradient of the SUMMED loss (the caller scales it)
@@ -883,17 +870,19 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
                            int size_average, float lambda_ce_host, float lambda_kd_host, float denom_known, float* loss_kd,
-                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, void* workspace,
-                           diga_stream_t stream) {
+                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, float* scratch,
+                           void* workspace, diga_stream_t stream) {
   using namespace diga;
   if (int rc = check_common("seg_kd_up_fwd_bwd", student_low, n2, C, h, w, H, W, workspace)) return rc;
-  DIGA_REQUIRE(teacher_low && target && loss_kd && loss_ce && denom_out && dstudent_low && (n2 % 2) == 0 && n_ce >= 1 && n_ce <= n2,
+  DIGA_REQUIRE(teacher_low && target && loss_kd && loss_ce && denom_out && (dstudent_low || scratch) && (n2 % 2) == 0 && n_ce >= 1 &&
+                   n_ce <= n2,
                DIGA_ERR_INVALID, "seg_kd_up_fwd_bwd: all pointers, an even batch and 1 <= n_ce <= n2 are required");
-  DIGA_REQUIRE(aligned(teacher_low, 4) && aligned(target, 8) && aligned(weight, 4) && aligned(dstudent_low, 4), DIGA_ERR_MISALIGNED,
-               "seg_kd_up_fwd_bwd: misaligned pointer");
+  DIGA_REQUIRE(aligned(teacher_low, 4) && aligned(target, 8) && aligned(weight, 4) && aligned(dstudent_low, 4) && aligned(scratch, 16),
+               DIGA_ERR_MISALIGNED, "seg_kd_up_fwd_bwd: misaligned pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const LossUpPlan p = make_plan(n2, C, h, w, H, W);
   LossUpArgs a = fill_args(p, workspace, teacher_low, student_low, target, weight, n2, n_ce, C, h, w, H, W, scale, size_average);
+  if (scratch) a.scratch = scratch;
   DIGA_REQUIRE(denom_known >= 0.f, DIGA_ERR_INVALID, "seg_kd_up_fwd_bwd: negative denom_known");
   if (size_average && denom_known > 0.f) {                // the caller knows #(target >= 0) (e.g. loader labels: trainIds or 255)
     a.denom_host = denom_known;
@@ -917,19 +906,31 @@ int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, c
   return launch_loss_up<true, true, true, true>(a, p, C, dstudent_low, st);
 }
 
-int diga_scale_by_scalars(const float* x, const float* num, const float* den, int64_t n, float* out, diga_stream_t stream) {
+size_t diga_loss_up_scratch_bytes(int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W) {
+  if (n < 1 || C < 1 || h < 1 || w < 1 || H < 1 || W < 1) return 0;
+  const diga::LossUpPlan p = diga::make_plan(n, C, h, w, H, W);
+  return p.bytes - p.off_scratch;
+}
+
+int diga_loss_up_gather(const float* scratch, const float* num, const float* den, int64_t n, int64_t C, int64_t h, int64_t w,
+                        int64_t H, int64_t W, float* dlow, diga_stream_t stream) {
   using namespace diga;
-  DIGA_REQUIRE(n >= 0 && (n == 0 || (x && out)) && num, DIGA_ERR_INVALID, "scale_by_scalars: null pointer or negative size");
-  DIGA_REQUIRE(aligned(x, 4) && aligned(out, 4) && aligned(num, 4) && aligned(den, 4), DIGA_ERR_MISALIGNED,
-               "scale_by_scalars: misaligned pointer");
-  if (n == 0) return DIGA_OK;
-  const int vec = aligned(x, 16) && aligned(out, 16);
-  int64_t grid = ((vec ? n / 4 : n) + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  scale_by_scalars_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, num, den, n, out, vec);
-  DIGA_CHECK_LAUNCH("scale_by_scalars_kernel");
+  DIGA_REQUIRE(scratch && num && dlow, DIGA_ERR_INVALID, "loss_up_gather: null pointer");
+  DIGA_REQUIRE(C >= 1 && C <= DIGA_MAX_CLASSES && n >= 1 && n <= 65535 && h >= 1 && w >= 1 && H >= h && W >= w && H < (1 << 24) &&
+                   W < (1 << 24),
+               DIGA_ERR_INVALID, "loss_up_gather: bad geometry");
+  DIGA_REQUIRE(aligned(scratch, 16) && aligned(num, 4) && aligned(den, 4) && aligned(dlow, 4), DIGA_ERR_MISALIGNED,
+               "loss_up_gather: misaligned pointer");
+  const LossUpPlan p = make_plan(n, C, h, w, H, W);
+  const float sh = bilinear_scale_host(h, H), sw = bilinear_scale_host(w, W);
+  const float inv_sh_ry = sh > 0.f ? 1.0f / (sh * (float)p.ry) : 0.f;
+  const float inv_sw_bx = sw > 0.f ? 1.0f / (sw * (float)kLuCols) : 0.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  DIGA_DISPATCH_C(C, {
+    loss_up_gather_kernel<kC, kPad><<<dim3((unsigned)h, (unsigned)n), 128, 0, st>>>(
+        scratch, dlow, (int)C, (int)h, (int)w, (int)H, (int)W, sh, sw, inv_sh_ry, inv_sw_bx, p.ry, p.R, p.K, p.SX, p.SY, num, den);
+    DIGA_CHECK_LAUNCH("loss_up_gather_kernel");
+  });
   return DIGA_OK;
 }
 

@@ -143,10 +143,11 @@ def _size2(size):
 class _LossesUpsampled(torch.autograd.Function):
     """(loss_ce, loss_kd) of the first ``n_ce`` / all images of ``student_low``; either part may be switched off.
 
-    With a single loss and a student that requires grad, the forward launches the loss+gradient kernel (the gradient with
-    a unit upstream costs one pass instead of two: both passes are bound by the same 38 exponentials per pixel) and the
-    backward only scales it by the upstream scalar on the device.  With both losses the backward is its own pass, because
-    the two upstream scalars are unknown until then."""
+    With a single loss and a student that requires grad, the forward launches the loss+gradient kernel with a unit upstream
+    (one pass instead of two) and leaves the per-CTA gradient patches in a scratch buffer of its own; the backward is the
+    gather over those patches, multiplied by the upstream scalar on the device (``diga_loss_up_gather``: one launch, where
+    gather + scale were two).  With both losses the backward is its own pass, because the two upstream scalars are unknown
+    until then."""
 
     @staticmethod
     def forward(ctx, teacher_low, student_low, target, weight, size, scale, size_average):
@@ -167,15 +168,16 @@ class _LossesUpsampled(torch.autograd.Function):
         size_average = int(bool(size_average))
         unit = None
         if ctx.needs_input_grad[1] and (t is None) != (tg is None):
-            unit = torch.empty_like(s)
+            unit = _new_scratch(n, c, h, w, hh, ww, dev)          # the unit gradient as patches: gathered (and scaled) in backward
             if tg is None:
                 L.check(L.lib.diga_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), n, c, h, w, hh, ww, float(scale), 1.0,
-                                                 loss_kd.data_ptr(), unit.data_ptr(), ws.data_ptr(), L.stream()))
+                                                 loss_kd.data_ptr(), None, unit.data_ptr(), ws.data_ptr(), L.stream()))
             else:
                 L.check(L.lib.diga_ce_up_fwd_bwd(s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, c, h, w, hh, ww, size_average,
-                                                 loss_ce.data_ptr(), denom.data_ptr(), unit.data_ptr(), ws.data_ptr(),
+                                                 loss_ce.data_ptr(), denom.data_ptr(), None, unit.data_ptr(), ws.data_ptr(),
                                                  L.stream()))
             ctx.save_for_backward(unit, denom)
+            ctx.low_shape = (n, c, h, w)
         else:
             L.check(L.lib.diga_loss_up_fwd(L.ptr(t), s.data_ptr(), L.ptr(tg), L.ptr(wt), n, n_ce, c, h, w, hh, ww,
                                            float(scale), size_average, L.ptr(loss_kd), L.ptr(loss_ce),
@@ -188,15 +190,16 @@ class _LossesUpsampled(torch.autograd.Function):
     def backward(ctx, g_ce, g_kd):
         s, denom = ctx.saved_tensors
         t, tg, wt, (hh, ww), scale, size_average, n_ce, have_unit = ctx.aux
-        n, c, h, w = s.shape
+        n, c, h, w = ctx.low_shape if have_unit else s.shape
         dev = s.device
         as_scalar = lambda g: None if g is None else g.to(dtype=torch.float32, device=dev).contiguous()
         g_ce, g_kd = as_scalar(g_ce), as_scalar(g_kd)                 # 0-dim device scalars, read on the GPU
-        if have_unit:                                                 # `s` is the unit gradient saved by the forward
+        if have_unit:                                                 # `s` holds the unit gradient's patches saved by the forward
             g = g_kd if tg is None else g_ce
             if g is None:
                 return None, None, None, None, None, None, None
-            return None, _scaled(s, g, denom if (tg is not None and size_average) else None), None, None, None, None, None
+            ds = _gathered(s, g, denom if (tg is not None and size_average) else None, (n, c, h, w), (hh, ww))
+            return None, ds, None, None, None, None, None
         if g_ce is None and g_kd is None:
             return None, None, None, None, None, None, None
         zero = None
@@ -211,12 +214,18 @@ class _LossesUpsampled(torch.autograd.Function):
         return None, ds, None, None, None, None, None
 
 
-def _scaled(x, num, den=None):
-    """``x * (num / den)`` (``den`` None: ``x * num``) with 0-dim device scalars, one launch (diga_scale_by_scalars) with the
-    same fp32 roundings as the tensor expression."""
-    out = torch.empty_like(x)
-    L.check(L.lib.diga_scale_by_scalars(x.data_ptr(), num.data_ptr(), L.ptr(den), x.numel(), out.data_ptr(), L.stream()))
-    return out
+def _new_scratch(n, c, h, w, hh, ww, device):
+    """Uninitialised buffer for the per-CTA gradient patches of one loss+gradient launch (diga_loss_up_scratch_bytes)."""
+    return torch.empty((int(L.lib.diga_loss_up_scratch_bytes(n, c, h, w, hh, ww)) // 4,), dtype=torch.float32, device=device)
+
+
+def _gathered(scratch, num, den, low_shape, size):
+    """``dlow = (sum of the patches in scratch) * (num / den)`` (``den`` None: ``* num``), 0-dim device scalars: one launch."""
+    n, c, h, w = low_shape
+    dlow = torch.empty(low_shape, dtype=torch.float32, device=scratch.device)
+    L.check(L.lib.diga_loss_up_gather(scratch.data_ptr(), num.data_ptr(), L.ptr(den), n, c, h, w, size[0], size[1], dlow.data_ptr(),
+                                      L.stream()))
+    return dlow
 
 
 def _check_low(student_low, size, what):
@@ -281,7 +290,7 @@ def distillation_loss_upsampled_and_grad(teacher_low, student_low, size, scale=0
     ds = torch.empty_like(s)
     ws = L.loss_up_workspace(n, c, h, w, hh, ww, s.device)
     L.check(L.lib.diga_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), n, c, h, w, hh, ww, float(scale), float(grad_scale),
-                                     loss.data_ptr(), ds.data_ptr(), ws.data_ptr(), L.stream()))
+                                     loss.data_ptr(), ds.data_ptr(), None, ws.data_ptr(), L.stream()))
     return loss, ds
 
 
@@ -301,14 +310,15 @@ class _SegDistillationTotal(torch.autograd.Function):
         loss_kd, loss_ce, denom = (torch.empty((), dtype=torch.float32, device=dev) for _ in range(3))
         ws = L.loss_up_workspace(n, c, h, w, hh, ww, dev)
         if ctx.needs_input_grad[1]:
-            ds = torch.empty_like(s)
+            ds = _new_scratch(n, c, h, w, hh, ww, dev)                   # gradient patches: gathered and scaled in backward
             total = torch.empty((), dtype=torch.float32, device=dev)     # written by the kernel's last CTA: no scalar launches
             L.check(L.lib.diga_seg_kd_up_fwd_bwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w,
                                                  hh, ww, float(scale), int(bool(size_average)), float(lambda_seg),
                                                  float(lambda_distil), float(tg.numel()) if targets_nonnegative else 0.0,
                                                  loss_kd.data_ptr(), loss_ce.data_ptr(), denom.data_ptr(), total.data_ptr(),
-                                                 ds.data_ptr(), ws.data_ptr(), L.stream()))
+                                                 None, ds.data_ptr(), ws.data_ptr(), L.stream()))
             ctx.save_for_backward(ds)
+            ctx.geom = ((n, c, h, w), (hh, ww))
         else:
             L.check(L.lib.diga_loss_up_fwd(t.data_ptr(), s.data_ptr(), tg.data_ptr(), L.ptr(wt), n, tg.shape[0], c, h, w, hh, ww,
                                            float(scale), int(bool(size_average)), loss_kd.data_ptr(), loss_ce.data_ptr(),
@@ -322,7 +332,7 @@ class _SegDistillationTotal(torch.autograd.Function):
         (ds,) = ctx.saved_tensors
         if g_total is None:
             return (None,) * 10
-        return (None, _scaled(ds, g_total.to(dtype=torch.float32, device=ds.device).contiguous())) + (None,) * 8
+        return (None, _gathered(ds, g_total.to(dtype=torch.float32, device=ds.device).contiguous(), None, *ctx.geom)) + (None,) * 8
 
 
 @L.on_device

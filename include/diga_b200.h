@@ -282,7 +282,15 @@ int diga_loss_up_bwd(const float* teacher_low, const float* student_low, const i
  * it by upstream / denom_out — what the autograd wrapper does when the logits require a gradient. */
 int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const float* weight, int64_t n, int64_t C, int64_t h,
                        int64_t w, int64_t H, int64_t W, int size_average, float* loss_out, float* denom_out,
-                       float* dlogits_sum, void* workspace, diga_stream_t stream);
+                       float* dlogits_sum, float* scratch, void* workspace, diga_stream_t stream);
+/* Deferred gather (the three *_fwd_bwd entry points): with `scratch` (diga_loss_up_scratch_bytes bytes, 16-byte aligned,
+ * need not be initialised) the per-CTA gradient patches go there instead of the workspace, and with the gradient pointer NULL
+ * they stay there: diga_loss_up_gather sums them into dlow [n,C,h,w] later, multiplied by num[0] / den[0] (den NULL: num[0]) read
+ * on the device — the autograd backward, where the upstream scalar of loss.backward() first becomes known.  One launch instead
+ * of gather + scale; the same roundings. */
+size_t diga_loss_up_scratch_bytes(int64_t n, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W);
+int diga_loss_up_gather(const float* scratch, const float* num, const float* den, int64_t n, int64_t C, int64_t h, int64_t w,
+                        int64_t H, int64_t W, float* dlow, diga_stream_t stream);
 /* Both losses of self_training.py:348-352 and the gradient of lambda_ce * loss_ce + lambda_kd * loss_kd (:382) in ONE pass
  * over the stride-8 logits, for call sites that know the two loss weights when the losses are computed.  `loss_total`
  * (nullable) receives that weighted sum, rounded like the three fp32 scalar operations of :356 / :382.  The CE gradient is
@@ -292,15 +300,11 @@ int diga_ce_up_fwd_bwd(const float* logits_low, const int64_t* target, const flo
 int diga_seg_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, const int64_t* target, const float* weight,
                            int64_t n2, int64_t n_ce, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W, float scale,
                            int size_average, float lambda_ce_host, float lambda_kd_host, float denom_known, float* loss_kd,
-                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, void* workspace,
-                           diga_stream_t stream);
-/* out[i] = x[i] * (num[0] / den[0]) (den null: x[i] * num[0]); num, den device scalars.  The autograd backward of the
- * single-pass losses: the stored gradient times the upstream scalar of `loss.backward()` (util/loss.py has no counterpart:
- * autograd's MulBackward does this in the reference).  out must not overlap x. */
-int diga_scale_by_scalars(const float* x, const float* num, const float* den, int64_t n, float* out, diga_stream_t stream);
+                           float* loss_ce, float* denom_out, float* loss_total, float* dstudent_low, float* scratch,
+                           void* workspace, diga_stream_t stream);
 int diga_kd_up_fwd_bwd(const float* teacher_low, const float* student_low, int64_t n2, int64_t C, int64_t h, int64_t w,
                        int64_t H, int64_t W, float scale, float upstream_host, float* loss_out, float* dstudent_low,
-                       void* workspace, diga_stream_t stream);
+                       float* scratch, void* workspace, diga_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * OhemCrossEntropy — util/loss.py:65-122 (the segmentation loss of the Synthia tree), from the stride-8 scores

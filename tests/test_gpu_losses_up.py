@@ -223,8 +223,14 @@ def test_no_grad_forward_takes_the_loss_only_pass(D):
     s = stu.clone().requires_grad_(True)
     before = L.launch_count()
     b = D.distillation_loss_upsampled(tea, s, (64, 96))
-    assert L.launch_count() - before == 2                      # loss+gradient kernel and the patch gather
+    assert L.launch_count() - before == 1                      # loss+gradient kernel; the patches wait for the upstream scalar
     assert torch.equal(a, b.detach())
+    before = L.launch_count()
+    (b * 0.37).backward()
+    assert L.launch_count() - before == 1                      # the patch gather, scaled by the upstream scalar on the device
+    s2 = stu.clone().requires_grad_(True)
+    loss, grad = D.distillation_loss_upsampled_and_grad(tea, s2, (64, 96), 0.5, 0.37)   # upstream known: gathered at once
+    normwise(s.grad, grad, "deferred gather x upstream vs upstream folded into the pass")
 
 
 @pytest.mark.parametrize("n2,c,lo,hi", [GEOMS[0], GEOMS[2], GEOMS[3], GEOMS[7]])
@@ -312,27 +318,6 @@ def test_source_rows_from_global_memory_equal_the_shared_memory_tile(D, n2, c, l
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
-@pytest.mark.parametrize("n,offset", [(0, 0), (1, 0), (5, 0), (1 << 12, 0), (19 * 65 * 129 * 3 + 3, 0), (4099, 1), (70001, 3)])
-def test_scale_by_scalars_equals_the_tensor_expression(D, n, offset):
-    """The backward of the single-pass losses scales the stored gradient with one launch (diga_scale_by_scalars): bit-equal to
-    `x * (g / denom)` and `x * g` of the tensor expression it replaces, on vector-aligned and unaligned buffers, with
-    upstream scalars that make the quotient inexact."""
-    from diga_b200 import _lib as L
-    g = torch.Generator(device=DEV).manual_seed(5 + n)
-    base = torch.randn((n + 8,), generator=g, device=DEV) * 37.0
-    x = base[offset:offset + n]
-    for num_v, den_v in ((0.3, 2097151.0), (1.0, 3.0), (-7.25, None), (0.0, 1.0)):
-        num = torch.tensor(num_v, device=DEV)
-        den = None if den_v is None else torch.tensor(den_v, device=DEV)
-        out_base = torch.full((n + 8,), 7.0, device=DEV)
-        out = out_base[offset:offset + n]
-        L.check(L.lib.diga_scale_by_scalars(L.ptr(x) if n else None, num.data_ptr(), L.ptr(den), n, L.ptr(out) if n else None,
-                                            L.stream()))
-        want = x * (num if den is None else num / den)
-        assert torch.equal(out, want)
-        assert torch.all(out_base[:offset] == 7.0) and torch.all(out_base[offset + n:] == 7.0)
-
-
 def test_single_loss_outputs_and_unused_upstreams(D):
     """A switched-off loss is None inside the autograd function (no fill launch), an upstream that never arrives leaves the
     other loss's gradient untouched, and the result equals the two-loss call with an explicit zero weight."""
@@ -384,3 +369,36 @@ def test_promised_denominator_skips_the_count_and_is_checked(D, n2, c, lo, hi):
     assert torch.isnan(bad[0]) and torch.isnan(bad[1]) and torch.isfinite(bad[2])
     good = run(tgt, False)
     assert torch.isfinite(good[0]) and torch.isfinite(good[1])
+
+
+@pytest.mark.parametrize("n2,c,lo,hi", GEOMS)
+def test_deferred_gather_reads_only_what_the_pass_wrote(D, n2, c, lo, hi, monkeypatch):
+    """The loss+gradient pass leaves its patches in an UNINITIALISED scratch buffer and the backward gathers them: with the
+    buffer poisoned with NaN beforehand every gradient must come out finite and bit-equal to the run on a zeroed buffer."""
+    from diga_b200.util import loss as LM
+    tea, stu, g = inputs(n2, c, lo, 77)
+    tgt = labels(n2 // 2, hi, c, g)
+    real = LM._new_scratch
+
+    def run(fill):
+        def poisoned(*a):
+            buf = real(*a)
+            buf.fill_(fill)
+            return buf
+        monkeypatch.setattr(LM, "_new_scratch", poisoned)
+        out = []
+        s = stu.clone().requires_grad_(True)
+        D.seg_distillation_total_upsampled(tea, s, tgt, 0.7, 1.3, 0.5)[0].backward()
+        out.append(s.grad)
+        s = stu.clone().requires_grad_(True)
+        (D.distillation_loss_upsampled(tea, s, hi, 0.5) * 0.3).backward()
+        out.append(s.grad)
+        s = stu[: n2 // 2].clone().requires_grad_(True)
+        (D.cross_entropy2d_upsampled(s, tgt) * 1.7).backward()
+        out.append(s.grad)
+        return out
+
+    zeroed, nan = run(0.0), run(float("nan"))
+    for a, b in zip(zeroed, nan):
+        assert torch.isfinite(b).all()
+        assert torch.equal(a, b)
