@@ -404,3 +404,26 @@ def test_png_crc_combine_constants_and_operator():
         assert joined == raw(msg)
     total = raw(msg) ^ multmodp(x8n(len(msg)), 0xFFFFFFFF) ^ 0xFFFFFFFF
     assert total == zlib.crc32(msg)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (no GPU needed): one JSON line with the arm's keys, the same `config` / metric / unit the GPU
+    arm prints, and — under torchrun — ranks other than 0 exit 0 without work or output."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-400:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "pixel-positions/s" and line["higher_is_better"] is True
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.CONFIG and line["metric"] == bench.METRIC and "l2" in line["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120,
+                           env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
